@@ -427,6 +427,8 @@ typedef struct {
   int32_t* row_leaf;          /* leaf node (tree-local id) per row of the tree being grown */
   OrcModel model;
   int32_t iter;               /* boosted rounds so far */
+  int32_t quant_bits;         /* 0 = reference behaviour; >0 = study knob: round gpair to a 2^-k grid like the
+                                 product's fixed-point histogram (scale = power of two from max|g|, max h) */
 } OrcTrainer;
 
 /* counter-based RNG shared with the product (csrc/rng.h): splitmix64 on (seed, stream, index) */
@@ -621,12 +623,23 @@ int orc_update_one_iter(OrcTrainer* t) {
       if (!(rng_uniform(p->seed, 0x2000 + (uint64_t)t->iter, (uint64_t)r) < p->subsample))
         for (int k = 0; k < K; ++k) { t->gpair[(r * K + k) * 2] = 0; t->gpair[(r * K + k) * 2 + 1] = 0; }
   }
+  if (t->quant_bits > 0) {
+    float mg = 0, mh = 0;
+    for (int64_t i = 0; i < t->n * K; ++i) { mg = fmaxf(mg, fabsf(t->gpair[2 * i])); mh = fmaxf(mh, t->gpair[2 * i + 1]); }
+    int eg, eh; frexpf(mg, &eg); frexpf(mh, &eh);      /* m < 2^e */
+    float sg = ldexpf(1.0f, t->quant_bits - 1 - eg), sh = ldexpf(1.0f, t->quant_bits - 1 - eh);
+    for (int64_t i = 0; i < t->n * K; ++i) {
+      t->gpair[2 * i] = rintf(t->gpair[2 * i] * sg) / sg;
+      t->gpair[2 * i + 1] = rintf(t->gpair[2 * i + 1] * sh) / sh;
+    }
+  }
   for (int k = 0; k < K; ++k) grow_tree(t, k, t->iter * K + k);
   t->iter++;
   return 0;
 }
 
 /* accessors for the Python wrapper */
+void orc_set_quant_bits(OrcTrainer* t, int32_t bits) { t->quant_bits = bits; }
 int32_t orc_num_trees(const OrcTrainer* t) { return t->model.n_trees; }
 int64_t orc_num_nodes(const OrcTrainer* t) { return t->model.n_nodes; }
 float orc_get_base_score(const OrcTrainer* t) { return t->base_score; }

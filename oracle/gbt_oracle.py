@@ -75,6 +75,7 @@ def lib():
         L.orc_build_hist_fixed.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_quant_bits.argtypes = [C.c_void_p, C.c_int32]
         _lib = L
     return _lib
 
@@ -221,6 +222,10 @@ class Trainer:
     @property
     def K(self):
         return max(1, self.p.num_class)
+
+    def set_quant_bits(self, bits):
+        """Study knob: emulate the product's fixed-point gradient grid (0 = reference behaviour)."""
+        lib().orc_set_quant_bits(self.h, int(bits))
 
     def update(self):
         rc = lib().orc_update_one_iter(self.h)

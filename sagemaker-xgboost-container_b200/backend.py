@@ -1,0 +1,316 @@
+"""ctypes binding of libb200xgb.so (include/b200xgb.h) -- the only compute backend of this package.
+
+The functions bound here carry the names and conventions of libxgboost's C API, i.e. what the reference
+container reaches through `import xgboost`.  There is deliberately NO CPU fallback: if the
+CUDA library is missing, or no GPU is visible, every call fails loudly with XGBoostError.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200xgb.so")
+
+c_bst_ulong = C.c_uint64
+
+
+class XGBoostError(ValueError):
+    """Error raised by the native library (same name and base class as xgboost.core.XGBoostError)."""
+
+
+def _cstr(s):
+    return C.c_char_p(s.encode("utf-8"))
+
+
+def _from_cstr_array(ptr, n):
+    return [ptr[i].decode("utf-8") for i in range(n)]
+
+
+class CudaBackend:
+    """Thin, stateless wrapper: one method per C-ABI entry point."""
+
+    name = "cuda"
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise XGBoostError(
+                "libb200xgb.so not found at %s -- build it with `python sagemaker-xgboost-container_b200/build.py` "
+                "(nvcc, sm_100a). This package has no CPU fallback." % path)
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.XGBGetLastError.restype = C.c_char_p
+        for name in dir(self):
+            pass
+        self.path = path
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, ret):
+        if ret != 0:
+            raise XGBoostError(self.lib.XGBGetLastError().decode("utf-8", "replace"))
+
+    def build_info(self):
+        out = C.c_char_p()
+        self._check(self.lib.XGBuildInfo(C.byref(out)))
+        return json.loads(out.value.decode())
+
+    # ------------------------------------------------------------------ DMatrix
+    def dmatrix_from_dense(self, arr, missing):
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        if arr.ndim != 2:
+            raise ValueError("Expecting 2 dimensional numpy.ndarray, got: %s" % (arr.shape,))
+        h = C.c_void_p()
+        self._check(self.lib.XGDMatrixCreateFromMat(arr.ctypes.data_as(C.POINTER(C.c_float)), c_bst_ulong(arr.shape[0]),
+                                                    c_bst_ulong(arr.shape[1]), C.c_float(missing), C.byref(h)))
+        return h
+
+    def dmatrix_from_csr(self, indptr, indices, data, ncol):
+        indptr = np.ascontiguousarray(indptr, dtype=np.uint64)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        h = C.c_void_p()
+        self._check(self.lib.XGDMatrixCreateFromCSREx(indptr.ctypes.data_as(C.POINTER(C.c_size_t)),
+                                                      indices.ctypes.data_as(C.POINTER(C.c_uint)),
+                                                      data.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(len(indptr)),
+                                                      C.c_size_t(len(data)), C.c_size_t(ncol), C.byref(h)))
+        return h
+
+    def dmatrix_free(self, h):
+        self._check(self.lib.XGDMatrixFree(h))
+
+    def dmatrix_num_row(self, h):
+        out = c_bst_ulong()
+        self._check(self.lib.XGDMatrixNumRow(h, C.byref(out)))
+        return int(out.value)
+
+    def dmatrix_num_col(self, h):
+        out = c_bst_ulong()
+        self._check(self.lib.XGDMatrixNumCol(h, C.byref(out)))
+        return int(out.value)
+
+    def dmatrix_set_float_info(self, h, field, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
+        self._check(self.lib.XGDMatrixSetFloatInfo(h, _cstr(field), arr.ctypes.data_as(C.POINTER(C.c_float)), c_bst_ulong(arr.size)))
+
+    def dmatrix_get_float_info(self, h, field):
+        n = c_bst_ulong()
+        ptr = C.POINTER(C.c_float)()
+        self._check(self.lib.XGDMatrixGetFloatInfo(h, _cstr(field), C.byref(n), C.byref(ptr)))
+        if n.value == 0:
+            return np.zeros(0, np.float32)
+        return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy()
+
+    def dmatrix_slice(self, h, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        out = C.c_void_p()
+        self._check(self.lib.XGDMatrixSliceDMatrix(h, idx.ctypes.data_as(C.POINTER(C.c_int)), c_bst_ulong(len(idx)), C.byref(out)))
+        return out
+
+    def dmatrix_set_str_info(self, h, field, values):
+        values = list(values or [])
+        arr = (C.c_char_p * len(values))(*[v.encode("utf-8") for v in values])
+        self._check(self.lib.XGDMatrixSetStrFeatureInfo(h, _cstr(field), arr, c_bst_ulong(len(values))))
+
+    def dmatrix_get_str_info(self, h, field):
+        n = c_bst_ulong()
+        ptr = C.POINTER(C.c_char_p)()
+        self._check(self.lib.XGDMatrixGetStrFeatureInfo(h, _cstr(field), C.byref(n), C.byref(ptr)))
+        return _from_cstr_array(ptr, n.value)
+
+    # ------------------------------------------------------------------ Booster
+    def booster_create(self, dmat_handles=()):
+        arr = (C.c_void_p * len(dmat_handles))(*[d.value if isinstance(d, C.c_void_p) else d for d in dmat_handles])
+        h = C.c_void_p()
+        self._check(self.lib.XGBoosterCreate(arr, c_bst_ulong(len(dmat_handles)), C.byref(h)))
+        return h
+
+    def booster_free(self, h):
+        self._check(self.lib.XGBoosterFree(h))
+
+    def booster_set_param(self, h, k, v):
+        self._check(self.lib.XGBoosterSetParam(h, _cstr(str(k)), _cstr(str(v))))
+
+    def booster_update(self, h, it, dh):
+        self._check(self.lib.XGBoosterUpdateOneIter(h, C.c_int(it), dh))
+
+    def booster_eval(self, h, it, dhs, names):
+        dm = (C.c_void_p * len(dhs))(*[d.value for d in dhs])
+        nm = (C.c_char_p * len(names))(*[n.encode("utf-8") for n in names])
+        out = C.c_char_p()
+        self._check(self.lib.XGBoosterEvalOneIter(h, C.c_int(it), dm, nm, c_bst_ulong(len(dhs)), C.byref(out)))
+        return out.value.decode("utf-8")
+
+    def booster_predict(self, h, dh, cfg):
+        shape = C.POINTER(c_bst_ulong)()
+        dim = c_bst_ulong()
+        res = C.POINTER(C.c_float)()
+        self._check(self.lib.XGBoosterPredictFromDMatrix(h, dh, _cstr(json.dumps(cfg)), C.byref(shape), C.byref(dim), C.byref(res)))
+        shp = tuple(int(shape[i]) for i in range(dim.value))
+        n = int(np.prod(shp)) if shp else 0
+        if n == 0:
+            return np.zeros(shp, np.float32)
+        return np.ctypeslib.as_array(res, shape=(n,)).copy().reshape(shp)
+
+    def booster_save_raw(self, h, fmt):
+        n = c_bst_ulong()
+        ptr = C.POINTER(C.c_char)()
+        self._check(self.lib.XGBoosterSaveModelToBuffer(h, _cstr(json.dumps({"format": fmt})), C.byref(n), C.byref(ptr)))
+        return C.string_at(ptr, n.value)
+
+    def booster_load_raw(self, h, buf):
+        buf = bytes(buf)
+        self._check(self.lib.XGBoosterLoadModelFromBuffer(h, buf, c_bst_ulong(len(buf))))
+
+    def booster_serialize(self, h):
+        n = c_bst_ulong()
+        ptr = C.POINTER(C.c_char)()
+        self._check(self.lib.XGBoosterSerializeToBuffer(h, C.byref(n), C.byref(ptr)))
+        return C.string_at(ptr, n.value)
+
+    def booster_unserialize(self, h, buf):
+        buf = bytes(buf)
+        self._check(self.lib.XGBoosterUnserializeFromBuffer(h, buf, c_bst_ulong(len(buf))))
+
+    def booster_save_config(self, h):
+        n = c_bst_ulong()
+        out = C.c_char_p()
+        self._check(self.lib.XGBoosterSaveJsonConfig(h, C.byref(n), C.byref(out)))
+        return out.value.decode("utf-8")
+
+    def booster_load_config(self, h, s):
+        self._check(self.lib.XGBoosterLoadJsonConfig(h, _cstr(s)))
+
+    def booster_num_features(self, h):
+        out = c_bst_ulong()
+        self._check(self.lib.XGBoosterGetNumFeature(h, C.byref(out)))
+        return int(out.value)
+
+    def booster_boosted_rounds(self, h):
+        out = C.c_int()
+        self._check(self.lib.XGBoosterBoostedRounds(h, C.byref(out)))
+        return int(out.value)
+
+    def booster_slice(self, h, begin, end, step):
+        out = C.c_void_p()
+        self._check(self.lib.XGBoosterSlice(h, C.c_int(begin), C.c_int(end), C.c_int(step), C.byref(out)))
+        return out
+
+    def booster_get_attr(self, h, key):
+        out = C.c_char_p()
+        ok = C.c_int()
+        self._check(self.lib.XGBoosterGetAttr(h, _cstr(key), C.byref(out), C.byref(ok)))
+        return out.value.decode("utf-8") if ok.value else None
+
+    def booster_set_attr(self, h, key, value):
+        self._check(self.lib.XGBoosterSetAttr(h, _cstr(key), None if value is None else _cstr(str(value))))
+
+    def booster_attr_names(self, h):
+        n = c_bst_ulong()
+        ptr = C.POINTER(C.c_char_p)()
+        self._check(self.lib.XGBoosterGetAttrNames(h, C.byref(n), C.byref(ptr)))
+        return _from_cstr_array(ptr, n.value)
+
+    def booster_set_str_info(self, h, field, values):
+        values = list(values or [])
+        arr = (C.c_char_p * len(values))(*[v.encode("utf-8") for v in values])
+        self._check(self.lib.XGBoosterSetStrFeatureInfo(h, _cstr(field), arr, c_bst_ulong(len(values))))
+
+    def booster_get_str_info(self, h, field):
+        n = c_bst_ulong()
+        ptr = C.POINTER(C.c_char_p)()
+        self._check(self.lib.XGBoosterGetStrFeatureInfo(h, _cstr(field), C.byref(n), C.byref(ptr)))
+        return _from_cstr_array(ptr, n.value)
+
+    # ------------------------------------------------------------------ collective
+    def comm_unique_id(self):
+        out = C.c_char_p()
+        self._check(self.lib.XGCommunicatorGetUniqueId(C.byref(out)))
+        return out.value.decode()
+
+    def comm_init(self, cfg):
+        self._check(self.lib.XGCommunicatorInit(_cstr(json.dumps(cfg))))
+
+    def comm_finalize(self):
+        self._check(self.lib.XGCommunicatorFinalize())
+
+    def comm_rank(self):
+        return int(self.lib.XGCommunicatorGetRank())
+
+    def comm_world(self):
+        return int(self.lib.XGCommunicatorGetWorldSize())
+
+    # ------------------------------------------------------------------ introspection (tests / bench)
+    def dmatrix_get_cuts(self, h, max_bin):
+        n_ptrs, n_vals = c_bst_ulong(), c_bst_ulong()
+        ptrs, vals, mins = C.POINTER(C.c_int)(), C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+        hm = C.c_int()
+        self._check(self.lib.XGB200DMatrixGetCuts(h, C.c_int(max_bin), C.byref(n_ptrs), C.byref(ptrs), C.byref(n_vals), C.byref(vals),
+                                                  C.byref(mins), C.byref(hm)))
+        F = n_ptrs.value - 1
+        return (np.ctypeslib.as_array(ptrs, shape=(n_ptrs.value,)).copy(), np.ctypeslib.as_array(vals, shape=(n_vals.value,)).copy(),
+                np.ctypeslib.as_array(mins, shape=(F,)).copy() if F else np.zeros(0, np.float32), bool(hm.value))
+
+    def dmatrix_set_cuts(self, h, ptrs, vals, mins):
+        ptrs = np.ascontiguousarray(ptrs, np.int32)
+        vals = np.ascontiguousarray(vals, np.float32)
+        mins = np.ascontiguousarray(mins, np.float32)
+        self._check(self.lib.XGB200DMatrixSetCuts(h, ptrs.ctypes.data_as(C.POINTER(C.c_int)), c_bst_ulong(len(ptrs)),
+                                                  vals.ctypes.data_as(C.POINTER(C.c_float)), mins.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def dmatrix_get_bins(self, h, max_bin):
+        n, F = self.dmatrix_num_row(h), self.dmatrix_num_col(h)
+        out = np.zeros((n, F), np.uint8)
+        self._check(self.lib.XGB200DMatrixGetBins(h, C.c_int(max_bin), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def booster_export_model(self, h):
+        nt, nn = c_bst_ulong(), c_bst_ulong()
+        bs = C.c_float()
+        nc = C.c_int()
+        self._check(self.lib.XGB200BoosterModelShape(h, C.byref(nt), C.byref(nn), C.byref(bs), C.byref(nc)))
+        nt, nn = nt.value, nn.value
+        m = {"tree_offset": np.zeros(nt + 1, np.int64), "tree_info": np.zeros(nt, np.int32)}
+        for k in ("left", "right", "parent", "split_index", "split_bin"):
+            m[k] = np.zeros(nn, np.int32)
+        m["default_left"] = np.zeros(nn, np.uint8)
+        for k in ("split_cond", "base_weight", "loss_chg", "sum_hess"):
+            m[k] = np.zeros(nn, np.float32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.XGB200BoosterExportModel(h, p(m["tree_offset"]), p(m["tree_info"]), p(m["left"]), p(m["right"]), p(m["parent"]),
+                                                      p(m["split_index"]), p(m["split_bin"]), p(m["default_left"]), p(m["split_cond"]),
+                                                      p(m["base_weight"]), p(m["loss_chg"]), p(m["sum_hess"])))
+        m["base_score"] = float(bs.value)
+        m["num_class"] = int(nc.value)
+        return m
+
+    def build_root_histogram(self, bh, dh, gpair, repeats=1):
+        gpair = np.ascontiguousarray(gpair, np.float32)
+        F = self.dmatrix_num_col(dh)
+        hist = np.zeros((F, 256, 2), np.int64)
+        scales = np.zeros(4, np.float32)
+        ms = C.c_float()
+        self._check(self.lib.XGB200BuildRootHistogram(bh, dh, gpair.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(repeats),
+                                                      hist.ctypes.data_as(C.POINTER(C.c_int64)), scales.ctypes.data_as(C.POINTER(C.c_float)),
+                                                      C.byref(ms)))
+        return hist, scales, float(ms.value)
+
+    def booster_cached_margin(self, bh, dh, K):
+        n = self.dmatrix_num_row(dh)
+        out = np.zeros((n, K), np.float32)
+        self._check(self.lib.XGB200BoosterGetCachedMargin(bh, dh, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def synchronize(self):
+        self._check(self.lib.XGB200Synchronize())
+
+
+_BACKEND = None
+
+
+def get_backend():
+    """The process-wide backend. Tests may replace `_BACKEND` (e.g. with the oracle-backed engine in tests/)."""
+    global _BACKEND
+    if _BACKEND is None:
+        _BACKEND = CudaBackend()
+    return _BACKEND

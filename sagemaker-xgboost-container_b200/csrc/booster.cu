@@ -1,0 +1,806 @@
+// booster.cu -- DMatrix / Booster implementation: the round loop of `xgb.train` (Booster.update) on the device.
+// Reference call sites served: algorithm_mode/train.py:367-376,432-442 (xgb.train), serve_utils.py:244-250
+// (Booster.predict), data_utils.py:309-313,361,384 (DMatrix construction).  Upstream behaviour restated:
+// src/learner.cc (UpdateOneIter, EvalOneIter, base_score), src/gbm/gbtree.cc (DoBoost, one tree per class).
+#include "booster.h"
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include "comm.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// process-wide device context
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DeviceCtx {
+  cudaStream_t stream = nullptr; int num_sms = 148; bool ok = false; std::string why;
+  DeviceCtx() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) { why = std::string("no CUDA device available (") + cudaGetErrorString(e) + ")"; cudaGetLastError(); return; }
+    int dev = 0;
+    if (const char* lr = getenv("LOCAL_RANK")) { dev = atoi(lr) % count; }
+    if (const char* d = getenv("B200XGB_DEVICE")) { dev = atoi(d) % count; }
+    if (cudaSetDevice(dev) != cudaSuccess) { why = "cudaSetDevice failed"; return; }
+    if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) { why = "cudaStreamCreate failed"; return; }
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    ok = true;
+  }
+};
+DeviceCtx& ctx() { static DeviceCtx c; if (!c.ok) throw Error("b200xgb: " + c.why + "; this library has no CPU fallback"); return c; }
+std::atomic<uint64_t> g_uid{1};
+}  // namespace
+
+cudaStream_t engine_stream() { return ctx().stream; }
+int engine_num_sms() { return ctx().num_sms; }
+
+// ---------------------------------------------------------------------------------------------
+// DMatrix
+// ---------------------------------------------------------------------------------------------
+DMatrix::DMatrix() : uid(g_uid++) {}
+
+void DMatrix::finish_upload(float missing) {
+  cudaStream_t s = engine_stream();
+  const int64_t count = n * F;
+  const bool use_missing = !std::isnan(missing);
+  DevBuf<unsigned long long> cnt; cnt.alloc(1); cnt.zero(s);
+  launch_count_nan(X.p, count, missing, use_missing ? 1 : 0, cnt.p, s);
+  if (use_missing) launch_replace_missing(X.p, count, missing, s);
+  unsigned long long c = 0;
+  CUDA_OK(cudaMemcpyAsync(&c, cnt.p, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  has_missing = c > 0;
+}
+
+std::unique_ptr<DMatrix> DMatrix::from_dense(const float* data, int64_t nrow, int ncol, float missing) {
+  B200_CHECK(nrow >= 0 && ncol >= 0, "DMatrix: negative shape");
+  B200_CHECK(nrow < (int64_t)0x7fffffff, "DMatrix: more than 2^31-1 rows per GPU are not supported");
+  auto dm = std::make_unique<DMatrix>();
+  dm->n = nrow; dm->F = ncol;
+  cudaStream_t s = engine_stream();
+  dm->X.alloc((size_t)nrow * ncol);
+  if (nrow * ncol > 0) {
+    CUDA_OK(cudaMemcpyAsync(dm->X.p, data, sizeof(float) * (size_t)nrow * ncol, cudaMemcpyHostToDevice, s));
+  }
+  dm->finish_upload(missing);
+  return dm;
+}
+
+std::unique_ptr<DMatrix> DMatrix::from_csr(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr,
+                                           size_t nelem, size_t ncol) {
+  // densify on the host with NaN for absent entries (upstream keeps CSR; the hist path needs a dense bin matrix anyway)
+  B200_CHECK(nindptr >= 1, "DMatrix: empty indptr");
+  const size_t nrow = nindptr - 1;
+  size_t F = ncol;
+  for (size_t i = 0; i < nelem; ++i) F = std::max<size_t>(F, (size_t)indices[i] + 1);
+  std::vector<float> dense(nrow * F, std::nanf(""));
+  for (size_t r = 0; r < nrow; ++r)
+    for (size_t j = indptr[r]; j < indptr[r + 1]; ++j) dense[r * F + indices[j]] = data[j];
+  return from_dense(dense.data(), (int64_t)nrow, (int)F, std::nanf(""));
+}
+
+__global__ void gather_rows_kernel(const float* X, int F, const int* idx, int64_t len, float* out) {
+  const int64_t total = len * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / F; int f = (int)(i % F);
+    out[i] = X[(int64_t)idx[r] * F + f];
+  }
+}
+
+std::unique_ptr<DMatrix> DMatrix::slice(const int* idx, int64_t len) const {
+  for (int64_t i = 0; i < len; ++i) B200_CHECK(idx[i] >= 0 && idx[i] < n, "DMatrix.slice: row index out of range");
+  auto dm = std::make_unique<DMatrix>();
+  dm->n = len; dm->F = F; dm->has_missing = has_missing;
+  dm->feature_names = feature_names; dm->feature_types = feature_types;
+  cudaStream_t s = engine_stream();
+  dm->X.alloc((size_t)len * F);
+  if (len * F > 0) {
+    DevBuf<int> didx; didx.alloc(len);
+    CUDA_OK(cudaMemcpyAsync(didx.p, idx, sizeof(int) * len, cudaMemcpyHostToDevice, s));
+    int grid = (int)std::min<int64_t>((len * F + 255) / 256, 148 * 16);
+    gather_rows_kernel<<<grid, 256, 0, s>>>(X.p, F, didx.p, len, dm->X.p);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
+  auto take = [&](const std::vector<float>& src, size_t per_row) { std::vector<float> o; if (src.empty()) return o; o.resize(len * per_row);
+    for (int64_t i = 0; i < len; ++i) for (size_t k = 0; k < per_row; ++k) o[i * per_row + k] = src[(size_t)idx[i] * per_row + k]; return o; };
+  if (!labels.empty()) { auto v = take(labels, 1); dm->set_float_info("label", v.data(), v.size()); }
+  if (!weights.empty()) { auto v = take(weights, 1); dm->set_float_info("weight", v.data(), v.size()); }
+  if (!base_margin.empty() && n > 0) { size_t per = base_margin.size() / n; auto v = take(base_margin, per); dm->set_float_info("base_margin", v.data(), v.size()); }
+  return dm;
+}
+
+void DMatrix::set_float_info(const std::string& field, const float* v, size_t len) {
+  cudaStream_t s = engine_stream();
+  auto put = [&](std::vector<float>& h, DevBuf<float>& d) {
+    h.assign(v, v + len); d.alloc(len);
+    if (len) { CUDA_OK(cudaMemcpyAsync(d.p, h.data(), sizeof(float) * len, cudaMemcpyHostToDevice, s)); CUDA_OK(cudaStreamSynchronize(s)); }
+  };
+  if (field == "label") put(labels, d_labels);
+  else if (field == "weight") {
+    for (size_t i = 0; i < len; ++i) B200_CHECK(v[i] >= 0 && !std::isnan(v[i]), "Weights must be positive values.");
+    put(weights, d_weights);
+    binned = false;      // weighted quantiles depend on the weights
+  }
+  else if (field == "base_margin") put(base_margin, d_base_margin);
+  else throw Error("Unknown float field name: " + field);
+}
+
+const std::vector<float>& DMatrix::get_float_info(const std::string& field) const {
+  if (field == "label") return labels;
+  if (field == "weight") return weights;
+  if (field == "base_margin") return base_margin;
+  throw Error("Unknown float field name: " + field);
+}
+
+void DMatrix::bin_with_cuts() {
+  cudaStream_t s = engine_stream();
+  ngroups = std::max(1, (F + kSlots - 1) / kSlots);
+  fpg = F > 0 ? (F + ngroups - 1) / ngroups : 1;
+  d_cut_ptrs.alloc(cuts.ptrs.size()); d_cut_vals.alloc(cuts.vals.size()); d_min_vals.alloc(cuts.mins.size());
+  CUDA_OK(cudaMemcpyAsync(d_cut_ptrs.p, cuts.ptrs.data(), sizeof(int) * cuts.ptrs.size(), cudaMemcpyHostToDevice, s));
+  if (!cuts.vals.empty()) CUDA_OK(cudaMemcpyAsync(d_cut_vals.p, cuts.vals.data(), sizeof(float) * cuts.vals.size(), cudaMemcpyHostToDevice, s));
+  if (!cuts.mins.empty()) CUDA_OK(cudaMemcpyAsync(d_min_vals.p, cuts.mins.data(), sizeof(float) * cuts.mins.size(), cudaMemcpyHostToDevice, s));
+  bins.alloc((size_t)ngroups * n * kSlots);
+  launch_bin(X.p, n, 0, n, F, fpg, ngroups, d_cut_ptrs.p, d_cut_vals.p, bins.p, s);
+  CUDA_OK(cudaStreamSynchronize(s));
+  binned = true;
+}
+
+void DMatrix::set_cuts(const HostCuts& c) {
+  B200_CHECK((int)c.ptrs.size() == F + 1 && (int)c.mins.size() == F, "SetCuts: cut_ptrs/min_vals do not match the number of features");
+  for (int f = 0; f < F; ++f) B200_CHECK(c.ptrs[f + 1] - c.ptrs[f] >= 1 && c.ptrs[f + 1] - c.ptrs[f] <= (has_missing ? 255 : 256), "SetCuts: 1..256 cuts per feature (255 with missing values)");
+  cuts = c; binned_max_bin = -1;
+  bin_with_cuts();
+}
+
+void DMatrix::ensure_binned(int max_bin) {
+  if (binned && (binned_max_bin == max_bin || binned_max_bin == -1)) return;
+  B200_CHECK(max_bin >= 2, "max_bin must be >= 2");
+  cudaStream_t s = engine_stream();
+  Comm& comm = Comm::get();
+  if (!comm.distributed()) {
+    compute_cuts_device(X.p, n, F, weights.empty() ? nullptr : d_weights.p, max_bin, has_missing, &cuts, s);
+  } else {
+    // every rank summarises its shard (exact when a feature has <= cap distinct values), the summaries are
+    // all-gathered and merged, and every rank derives the same cuts.
+    const int cap = 2048;
+    int hm = has_missing ? 1 : 0;
+    {   // has_missing must agree across ranks (bin code 255 reservation)
+      DevBuf<unsigned> flag; flag.alloc(1); unsigned v = (unsigned)hm;
+      CUDA_OK(cudaMemcpyAsync(flag.p, &v, 4, cudaMemcpyHostToDevice, s));
+      comm.allreduce_max_u32(flag.p, 1, s);
+      CUDA_OK(cudaMemcpyAsync(&v, flag.p, 4, cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
+      has_missing = v != 0;
+    }
+    std::vector<FeatureSummary> local;
+    compute_summaries_device(X.p, n, F, weights.empty() ? nullptr : d_weights.p, cap, &local, s);
+    const size_t per_feat = (size_t)(cap + 2);
+    const size_t rec = per_feat * (sizeof(float) + sizeof(double)) + sizeof(double);   // vals, weights, count
+    std::vector<unsigned char> sendbuf((size_t)F * rec, 0);
+    for (int f = 0; f < F; ++f) {
+      unsigned char* p = sendbuf.data() + (size_t)f * rec;
+      double cntd = (double)local[f].vals.size(); memcpy(p, &cntd, 8);
+      memcpy(p + 8, local[f].vals.data(), sizeof(float) * local[f].vals.size());
+      memcpy(p + 8 + per_feat * sizeof(float), local[f].weights.data(), sizeof(double) * local[f].weights.size());
+    }
+    const int W = comm.world();
+    DevBuf<unsigned char> dsend, drecv; dsend.alloc(sendbuf.size()); drecv.alloc(sendbuf.size() * W);
+    CUDA_OK(cudaMemcpyAsync(dsend.p, sendbuf.data(), sendbuf.size(), cudaMemcpyHostToDevice, s));
+    comm.allgather_bytes(dsend.p, drecv.p, sendbuf.size(), s);
+    std::vector<unsigned char> all(sendbuf.size() * W);
+    CUDA_OK(cudaMemcpyAsync(all.data(), drecv.p, all.size(), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    std::vector<FeatureSummary> merged(F);
+    for (int f = 0; f < F; ++f) {
+      std::vector<std::pair<float, double>> pts;
+      for (int r = 0; r < W; ++r) {
+        const unsigned char* p = all.data() + (size_t)r * sendbuf.size() + (size_t)f * rec;
+        double cntd; memcpy(&cntd, p, 8); size_t c = (size_t)cntd;
+        const float* v = reinterpret_cast<const float*>(p + 8);
+        std::vector<double> w(c); memcpy(w.data(), p + 8 + per_feat * sizeof(float), sizeof(double) * c);
+        for (size_t i = 0; i < c; ++i) pts.emplace_back(v[i], w[i]);
+      }
+      std::stable_sort(pts.begin(), pts.end(), [](const std::pair<float, double>& a, const std::pair<float, double>& b) { return a.first < b.first; });
+      for (auto& pw : pts) {
+        if (!merged[f].vals.empty() && merged[f].vals.back() == pw.first) merged[f].weights.back() += pw.second;
+        else { merged[f].vals.push_back(pw.first); merged[f].weights.push_back(pw.second); }
+      }
+    }
+    cuts_from_summaries(merged, max_bin, has_missing, &cuts);
+  }
+  binned_max_bin = max_bin;
+  bin_with_cuts();
+}
+
+// ---------------------------------------------------------------------------------------------
+// tree builder: device buffers + the per-tree launch sequence
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_tree_kernel(TreeArrays t, const int* n_nodes, DevNode* out, int cap) {
+  const int nn = *n_nodes;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    DevNode d;
+    if (i < nn) { d.cond = t.split_cond[i]; d.left = t.left[i]; d.right = t.right[i]; d.fidx_dl = (unsigned)t.split_index[i] | ((unsigned)t.default_left[i] << 31); }
+    else { d.cond = 0.f; d.left = -1; d.right = -1; d.fidx_dl = 0; }
+    out[i] = d;
+  }
+}
+
+struct PinnedPool {
+  std::vector<std::pair<char*, size_t>> chunks; size_t cur = 0, off = 0;
+  ~PinnedPool() { for (auto& c : chunks) cudaFreeHost(c.first); }
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    while (cur < chunks.size() && off + bytes > chunks[cur].second) { ++cur; off = 0; }
+    if (cur >= chunks.size()) { size_t sz = std::max<size_t>(bytes, 4u << 20); char* p = nullptr; CUDA_OK(cudaMallocHost(&p, sz)); chunks.emplace_back(p, sz); off = 0; }
+    void* r = chunks[cur].first + off; off += bytes; return r;
+  }
+  void reset() { cur = 0; off = 0; }
+};
+
+struct GrowerImpl {
+  int64_t n = 0; int ngroups = 0, max_depth = 0, max_nodes = 0, cap_nodes = 0, max_level_nodes = 0, region = 0;
+  size_t slot_stride = 0;                  // GH64 entries per histogram slot
+  GrowState gs{}; TreeArrays ta{};
+  DevBuf<unsigned char> state_block;       // all GrowState arrays
+  DevBuf<unsigned char> tree_block;        // header + TreeArrays, copied to the host in one piece
+  size_t tree_block_bytes = 0;
+  DevBuf<GH64> hist_pool; DevBuf<unsigned> ridx0, ridx1, scratch;
+  DevBuf<float2> gpair; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
+  DevBuf<double> dsum;
+  PinnedPool pinned; std::vector<cudaEvent_t> free_events;
+  int hist_grid_x = 1;
+
+  void ensure(int64_t n_, int ngroups_, int max_depth_, int K) {
+    if (n == n_ && ngroups == ngroups_ && max_depth == max_depth_ && gpair.n >= (size_t)n_ * K) return;
+    B200_CHECK(max_depth_ >= 1 && max_depth_ <= kMaxDepth, "max_depth must be in [1, 16] for the B200 depth-wise hist builder");
+    n = n_; ngroups = ngroups_; max_depth = max_depth_;
+    max_nodes = (1 << (max_depth + 1)) - 1;
+    cap_nodes = (max_nodes + 15) & ~15;
+    max_level_nodes = 1 << (max_depth - 1);
+    region = max_level_nodes;
+    slot_stride = (size_t)ngroups * kGroupEntries;
+    const size_t pool_bytes = 2 * (size_t)region * slot_stride * sizeof(GH64);
+    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+    B200_CHECK(pool_bytes < free_b / 2 + hist_pool.n * sizeof(GH64), "histogram pool for this max_depth / feature count does not fit in device memory");
+    hist_pool.alloc(2 * (size_t)region * slot_stride);
+    ridx0.alloc(n); ridx1.alloc(n);
+    gpair.alloc((size_t)n * K); err.alloc(1); dsum.alloc(4);
+    const unsigned max_tiles = (unsigned)((n + kPartTile - 1) / kPartTile) + max_level_nodes + 1;
+    scratch.alloc(3 * (size_t)max_level_nodes + 8);
+    // ---- GrowState block
+    size_t off = 0; auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t N = cap_nodes, L = max_level_nodes;
+    size_t o_seg_begin = take(4 * N), o_seg_count = take(4 * N), o_slot = take(4 * N), o_sum = take(16 * N), o_rg = take(4 * N), o_w = take(4 * N);
+    size_t o_best = take(sizeof(SplitCand) * N), o_bestg = take(sizeof(SplitCand) * N * ngroups);
+    size_t o_lnodes = take(4 * (size_t)(kMaxDepth + 1) * L), o_lcount = take(4 * (kMaxDepth + 2));
+    size_t o_bnid = take(4 * L), o_bsub = take(4 * L), o_bps = take(4 * L), o_bcount = take(4), o_bprefix = take(4 * (L + 1));
+    size_t o_action = take(4 * L), o_tprefix = take(4 * (L + 1)), o_tleft = take(4 * (size_t)max_tiles), o_toff = take(4 * (size_t)max_tiles);
+    size_t o_flags = take((size_t)n + 16), o_nleaves = take(4), o_scales = take(16), o_absmax = take(8);
+    state_block.alloc(off); state_block.zero(engine_stream());
+    unsigned char* b = state_block.p;
+    gs.seg_begin = (unsigned*)(b + o_seg_begin); gs.seg_count = (unsigned*)(b + o_seg_count); gs.hist_slot = (int*)(b + o_slot);
+    gs.node_sum = (GH64*)(b + o_sum); gs.root_gain = (float*)(b + o_rg); gs.weight = (float*)(b + o_w);
+    gs.best = (SplitCand*)(b + o_best); gs.best_group = (SplitCand*)(b + o_bestg);
+    gs.level_nodes = (int*)(b + o_lnodes); gs.level_count = (int*)(b + o_lcount);
+    gs.build_nid = (int*)(b + o_bnid); gs.build_sub_nid = (int*)(b + o_bsub); gs.build_parent_slot = (int*)(b + o_bps);
+    gs.build_count = (int*)(b + o_bcount); gs.build_prefix = (unsigned*)(b + o_bprefix);
+    gs.part_action = (int*)(b + o_action); gs.tile_prefix = (unsigned*)(b + o_tprefix); gs.tile_left = (unsigned*)(b + o_tleft); gs.tile_off = (unsigned*)(b + o_toff);
+    gs.flags = b + o_flags; gs.n_leaves = (int*)(b + o_nleaves); gs.scales = (float*)(b + o_scales); gs.absmax = (unsigned*)(b + o_absmax);
+    // ---- tree block: [n_nodes + pad to 64][5 int arrays][4 float arrays][u8 array]
+    tree_block_bytes = 64 + 9 * 4 * N + N;
+    tree_block.alloc(tree_block_bytes);
+    unsigned char* t = tree_block.p;
+    gs.n_nodes = (int*)t;
+    int* ip = (int*)(t + 64);
+    ta.left = ip; ta.right = ip + N; ta.parent = ip + 2 * N; ta.split_index = ip + 3 * N; ta.split_bin = ip + 4 * N;
+    float* fp = (float*)(ip + 5 * N);
+    ta.split_cond = fp; ta.base_weight = fp + N; ta.loss_chg = fp + 2 * N; ta.sum_hess = fp + 3 * N;
+    ta.default_left = (unsigned char*)(fp + 4 * N);
+    hist_grid_x = std::max(1, (engine_num_sms() * 3 + ngroups - 1) / ngroups);
+  }
+};
+
+static TrainParamDev to_dev(const TrainParam& p) {
+  TrainParamDev d; d.eta = p.eta; d.lambda = p.lambda; d.alpha = p.alpha; d.gamma = p.gamma; d.min_child_weight = p.min_child_weight;
+  d.max_delta_step = p.max_delta_step; d.max_depth = p.max_depth; d.max_leaves = p.max_leaves; return d;
+}
+
+// counter-based RNG shared with the oracle (splitmix64 on (seed, stream, index))
+static inline uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL; x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL; return x ^ (x >> 31);
+}
+static inline float rng_uniform(uint32_t seed, uint64_t stream, uint64_t idx) {
+  uint64_t h = splitmix64(splitmix64(((uint64_t)seed << 32) ^ stream) ^ idx);
+  return (float)(h >> 40) * (1.0f / 16777216.0f);
+}
+std::string colsample_mask(unsigned seed, int tree_index, int F, float frac) {
+  std::string m((size_t)F, (char)1);
+  if (frac >= 1.0f) return m;
+  int keep = (int)std::max(1.0f, std::floor(frac * F + 0.5f));
+  std::vector<float> u(F);
+  for (int f = 0; f < F; ++f) u[f] = rng_uniform(seed, 0x1000 + (uint64_t)tree_index, (uint64_t)f);
+  for (int f = 0; f < F; ++f) { int rank = 0; for (int g = 0; g < F; ++g) if (u[g] < u[f] || (u[g] == u[f] && g < f)) ++rank; m[f] = rank < keep ? 1 : 0; }
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Booster
+// ---------------------------------------------------------------------------------------------
+Booster::Booster() {}
+Booster::~Booster() {
+  if (grower_) { for (auto e : grower_->free_events) cudaEventDestroy(e); delete grower_; }
+  for (auto& p : pending_) if (p.ready) cudaEventDestroy(p.ready);
+}
+
+static const std::map<std::string, int>& objective_table() {
+  static const std::map<std::string, int> t = {{"reg:squarederror", kSquaredError}, {"reg:linear", kSquaredError}, {"binary:logistic", kBinaryLogistic},
+    {"reg:logistic", kRegLogistic}, {"binary:logitraw", kLogitRaw}, {"multi:softprob", kSoftprob}, {"multi:softmax", kSoftmax}};
+  return t;
+}
+
+void Booster::set_param(const std::string& k, const std::string& v) {
+  if (k == "eval_metric") { if (std::find(eval_metrics_.begin(), eval_metrics_.end(), v) == eval_metrics_.end()) eval_metrics_.push_back(v); }
+  else raw_params_[k] = v;
+  configured_ = false;
+}
+
+void Booster::configure() {
+  if (configured_) return;
+  auto getf = [&](const char* a, const char* b, float def) { auto it = raw_params_.find(a); if (it == raw_params_.end() && b) it = raw_params_.find(b);
+    if (it == raw_params_.end()) return def; try { return std::stof(it->second); } catch (...) { throw Error(std::string("Invalid value for parameter ") + a + ": " + it->second); } };
+  auto geti = [&](const char* a, int def) { auto it = raw_params_.find(a); if (it == raw_params_.end()) return def;
+    try { return (int)std::stod(it->second); } catch (...) { throw Error(std::string("Invalid value for parameter ") + a + ": " + it->second); } };
+  TrainParam p;
+  auto ito = raw_params_.find("objective");
+  if (ito != raw_params_.end()) objective_name_ = ito->second;
+  auto ot = objective_table().find(objective_name_);
+  B200_CHECK(ot != objective_table().end(), "Unknown objective function: `" + objective_name_ + "` (supported on the B200 hist path: reg:squarederror, reg:linear, reg:logistic, binary:logistic, binary:logitraw, multi:softprob, multi:softmax)");
+  p.objective = ot->second;
+  if (objective_name_ == "reg:linear") objective_name_ = "reg:squarederror";
+  p.num_class = (p.objective == kSoftprob || p.objective == kSoftmax) ? geti("num_class", 0) : 1;
+  if (p.objective == kSoftprob || p.objective == kSoftmax) B200_CHECK(p.num_class >= 1, "num_class must be set (>= 1) for multi:softprob / multi:softmax");
+  p.max_depth = geti("max_depth", 6); p.max_leaves = geti("max_leaves", 0); p.max_bin = geti("max_bin", 256);
+  p.eta = getf("eta", "learning_rate", 0.3f); p.lambda = getf("lambda", "reg_lambda", 1.0f); p.alpha = getf("alpha", "reg_alpha", 0.0f);
+  p.gamma = getf("gamma", "min_split_loss", 0.0f); p.min_child_weight = getf("min_child_weight", nullptr, 1.0f);
+  p.max_delta_step = getf("max_delta_step", nullptr, 0.0f); p.scale_pos_weight = getf("scale_pos_weight", nullptr, 1.0f);
+  p.subsample = getf("subsample", nullptr, 1.0f); p.colsample_bytree = getf("colsample_bytree", nullptr, 1.0f);
+  p.colsample_bylevel = getf("colsample_bylevel", nullptr, 1.0f); p.colsample_bynode = getf("colsample_bynode", nullptr, 1.0f);
+  p.seed = (unsigned)geti("seed", 0);
+  B200_CHECK(p.lambda >= 0.0f, "Parameter reg_lambda should be greater equal to 0");
+  B200_CHECK(p.subsample > 0.0f && p.subsample <= 1.0f, "Parameter subsample should be in (0, 1]");
+  auto tm = raw_params_.find("tree_method");
+  if (tm != raw_params_.end()) {
+    const std::string& t = tm->second;
+    B200_CHECK(t == "hist" || t == "auto" || t == "gpu_hist" || t == "approx" || t == "exact",
+               "Unknown tree_method: " + t);
+    // every method maps onto the device hist builder; exact/approx are accepted for hyperparameter compatibility
+  }
+  auto bo = raw_params_.find("booster");
+  if (bo != raw_params_.end()) B200_CHECK(bo->second == "gbtree", "Only booster=gbtree is implemented on the B200 hist path (got " + bo->second + ")");
+  auto gp = raw_params_.find("grow_policy");
+  if (gp != raw_params_.end()) B200_CHECK(gp->second == "depthwise", "grow_policy=" + gp->second + " is not implemented on the B200 hist path yet (depthwise only)");
+  auto bs = raw_params_.find("base_score");
+  if (bs != raw_params_.end() && !bs->second.empty()) {
+    base_score_ = std::stof(bs->second); base_score_set_ = true;
+    if (p.objective == kBinaryLogistic || p.objective == kRegLogistic || p.objective == kLogitRaw)
+      B200_CHECK(base_score_ > 0.0f && base_score_ < 1.0f, "Check failed: base_score > 0.0f && base_score < 1.0f base_score must be in (0,1) for logistic loss");
+  }
+  if (p.max_depth <= 0) p.max_depth = 6;
+  param_ = p;
+  configured_ = true;
+}
+
+float Booster::base_margin() const {
+  if (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic || param_.objective == kLogitRaw)
+    return -std::log(1.0f / base_score_ - 1.0f);
+  return base_score_;
+}
+
+// One Newton stump at margin 0, then PredTransform (upstream src/objective/init_estimation.cc, src/tree/fit_stump.cc)
+void Booster::estimate_base_score(DMatrix* dtrain) {
+  if (base_score_set_ || base_score_estimated_ || !trees_.empty()) { base_score_estimated_ = true; return; }
+  base_score_estimated_ = true;
+  if (param_.objective == kSoftprob || param_.objective == kSoftmax) { base_score_ = 0.5f; return; }
+  cudaStream_t s = engine_stream();
+  GrowerImpl& g = *grower_;
+  GradArgs ga{}; ga.margin = nullptr; ga.label = dtrain->d_labels.p; ga.weight = dtrain->weights.empty() ? nullptr : dtrain->d_weights.p;
+  ga.gpair = g.gpair.p; ga.absmax = nullptr; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = 1; ga.objective = param_.objective;
+  ga.scale_pos_weight = param_.scale_pos_weight; ga.subsample = 1.0f; ga.seed = 0; ga.iter = 0;
+  CUDA_OK(cudaMemsetAsync(g.dsum.p, 0, 4 * sizeof(double), s));
+  launch_gradient(ga, s);
+  launch_sum_gpair(g.gpair.p, dtrain->n, g.dsum.p, s);
+  Comm::get().allreduce_sum_f64(g.dsum.p, 2, s);
+  double h[2];
+  CUDA_OK(cudaMemcpyAsync(h, g.dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  float w = h[1] <= 0.0 ? 0.0f : (float)(-h[0] / h[1]);
+  if (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic) {
+    float x = std::min(-w, 88.7f); base_score_ = 1.0f / (std::exp(x) + 1.0f + 1e-16f);
+  } else base_score_ = w;
+}
+
+void Booster::append_device_tree(int class_id, size_t device_offset, int max_nodes, PendingTree pt) {
+  trees_.emplace_back(); tree_info_.push_back(class_id); pending_.push_back(pt); on_device_.push_back(1);
+  h_tree_offset.resize(trees_.size() + 1);
+  h_tree_offset[trees_.size() - 1] = (int64_t)device_offset;
+  h_tree_offset[trees_.size()] = (int64_t)device_offset + max_nodes;
+  ++model_version_;
+}
+
+void Booster::sync_model() {
+  bool any = false;
+  for (auto& p : pending_) if (p.staging) { any = true; break; }
+  if (!any) return;
+  for (size_t t = 0; t < pending_.size(); ++t) {
+    PendingTree& p = pending_[t];
+    if (!p.staging) continue;
+    CUDA_OK(cudaEventSynchronize(p.ready));
+    const unsigned char* b = (const unsigned char*)p.staging;
+    const int nn = *(const int*)b; const size_t N = p.cap_nodes;
+    const int* ip = (const int*)(b + 64); const float* fp = (const float*)(ip + 5 * N); const unsigned char* up = (const unsigned char*)(fp + 4 * N);
+    HostTree& h = trees_[t];
+    h.left.assign(ip, ip + nn); h.right.assign(ip + N, ip + N + nn); h.parent.assign(ip + 2 * N, ip + 2 * N + nn);
+    h.split_index.assign(ip + 3 * N, ip + 3 * N + nn); h.split_bin.assign(ip + 4 * N, ip + 4 * N + nn);
+    h.split_cond.assign(fp, fp + nn); h.base_weight.assign(fp + N, fp + N + nn); h.loss_chg.assign(fp + 2 * N, fp + 2 * N + nn); h.sum_hess.assign(fp + 3 * N, fp + 3 * N + nn);
+    h.default_left.assign(up, up + nn);
+    if (grower_) grower_->free_events.push_back(p.ready); else cudaEventDestroy(p.ready);
+    p.ready = nullptr; p.staging = nullptr;
+  }
+  if (grower_) grower_->pinned.reset();
+}
+
+// make sure every tree is present in the device model (trees loaded from a file are uploaded here)
+void Booster::upload_model() {
+  cudaStream_t s = engine_stream();
+  const int nt = (int)trees_.size();
+  if ((int)h_tree_offset.size() != nt + 1) h_tree_offset.resize(nt + 1, 0);
+  pending_.resize(nt); on_device_.resize(nt, 0);
+  for (int t = 0; t < nt; ++t) {
+    if (on_device_[t]) continue;
+    const HostTree& h = trees_[t];
+    const int nn = h.num_nodes();
+    std::vector<DevNode> nodes(nn);
+    for (int i = 0; i < nn; ++i) { nodes[i].cond = h.split_cond[i]; nodes[i].left = h.left[i]; nodes[i].right = h.right[i]; nodes[i].fidx_dl = (unsigned)h.split_index[i] | ((unsigned)h.default_left[i] << 31); }
+    if (d_nodes_used + nn > d_nodes.n) {
+      size_t cap = std::max<size_t>(d_nodes.n * 2, d_nodes_used + nn + 4096);
+      DevBuf<DevNode> nb; nb.alloc(cap);
+      if (d_nodes_used) CUDA_OK(cudaMemcpyAsync(nb.p, d_nodes.p, sizeof(DevNode) * d_nodes_used, cudaMemcpyDeviceToDevice, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      std::swap(nb.p, d_nodes.p); std::swap(nb.n, d_nodes.n);
+    }
+    CUDA_OK(cudaMemcpyAsync(d_nodes.p + d_nodes_used, nodes.data(), sizeof(DevNode) * nn, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    h_tree_offset[t] = (int64_t)d_nodes_used; h_tree_offset[t + 1] = (int64_t)d_nodes_used + nn;
+    d_nodes_used += nn; on_device_[t] = 1; d_trees_uploaded = 0;
+  }
+  if (d_trees_uploaded != nt || d_tree_offset.n < (size_t)nt + 1) {
+    d_tree_offset.ensure(std::max<size_t>(nt + 1, 64)); d_tree_info.ensure(std::max<size_t>(nt, 64));
+    // offsets are per-tree starts (trees trained on the device have fixed-capacity slots, so starts are not cumulative)
+    CUDA_OK(cudaMemcpyAsync(d_tree_offset.p, h_tree_offset.data(), sizeof(int64_t) * (nt + 1), cudaMemcpyHostToDevice, s));
+    if (nt) CUDA_OK(cudaMemcpyAsync(d_tree_info.p, tree_info_.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    d_trees_uploaded = nt;
+  }
+}
+
+PredCache& Booster::cache_for(DMatrix* dm) {
+  PredCache& c = caches_[dm->uid];
+  const int K = param_.num_class;
+  if (c.n != dm->n || c.margin.n != (size_t)dm->n * K) {
+    c.n = dm->n; c.margin.alloc((size_t)dm->n * K); c.trees_applied = -1;
+  }
+  return c;
+}
+
+void Booster::bring_cache_up_to_date(DMatrix* dm, PredCache& c) {
+  cudaStream_t s = engine_stream();
+  const int K = param_.num_class;
+  const int nt = (int)trees_.size();
+  if (c.trees_applied < 0) {
+    if (!dm->base_margin.empty()) {
+      B200_CHECK(dm->base_margin.size() == (size_t)dm->n * K, "base_margin size does not match rows x groups");
+      CUDA_OK(cudaMemcpyAsync(c.margin.p, dm->d_base_margin.p, sizeof(float) * dm->n * K, cudaMemcpyDeviceToDevice, s));
+    } else launch_fill(c.margin.p, dm->n * K, base_margin(), s);
+    c.trees_applied = 0;
+  }
+  if (c.trees_applied < nt) {
+    upload_model();
+    PredictArgs pa{}; pa.X = dm->X.p; pa.n = dm->n; pa.F = dm->F; pa.nodes = d_nodes.p; pa.tree_offset = d_tree_offset.p; pa.tree_info = d_tree_info.p;
+    pa.tree_begin = c.trees_applied; pa.tree_end = nt; pa.K = K; pa.margin = c.margin.p; pa.leaf = nullptr;
+    launch_predict(pa, s);
+    c.trees_applied = nt;
+  }
+}
+
+static void check_labels(const DMatrix* dm) {
+  B200_CHECK(dm->labels.size() == (size_t)dm->n, "Check failed: preds.size() == info.labels_.size() (" + std::to_string(dm->n) + " vs. " +
+             std::to_string(dm->labels.size()) + ") : labels are not correctly provided");
+}
+
+void Booster::update_one_iter(int iter, DMatrix* dtrain) {
+  configure();
+  (void)iter;
+  cudaStream_t s = engine_stream();
+  check_labels(dtrain);
+  if (num_feature_ == 0) num_feature_ = dtrain->F;
+  B200_CHECK(num_feature_ == dtrain->F, "Check failed: learner_model_param_.num_feature == p_fmat->Info().num_col_ (" + std::to_string(num_feature_) +
+             " vs. " + std::to_string(dtrain->F) + ") : Number of columns does not match number of features in booster.");
+  B200_CHECK(dtrain->n > 0 || Comm::get().distributed(), "Empty dataset at worker: 0");
+  dtrain->ensure_binned(param_.max_bin);
+  const int K = param_.num_class;
+  if (!grower_) grower_ = new GrowerImpl();
+  GrowerImpl& g = *grower_;
+  g.ensure(dtrain->n, dtrain->ngroups, param_.max_depth, K);
+  if (!labels_checked_) {
+    // label-range errors must surface from update() (the container maps them to UserError, train.py:461-467)
+    const std::vector<float>& y = dtrain->labels;
+    if (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic || param_.objective == kLogitRaw)
+      for (float v : y) B200_CHECK(v >= 0.0f && v <= 1.0f, "Check failed: label must be in [0,1] for logistic regression");
+    if (param_.objective == kSoftprob || param_.objective == kSoftmax)
+      for (float v : y) B200_CHECK(v >= 0.0f && (int)v < K, "SoftmaxMultiClassObj: label must be in [0, num_class).");
+    labels_checked_ = true;
+  }
+  estimate_base_score(dtrain);
+  PredCache& cache = cache_for(dtrain);
+  bring_cache_up_to_date(dtrain, cache);
+
+  const int round = (int)trees_.size() / K;
+  // ---- gradients + fixed-point scales
+  CUDA_OK(cudaMemsetAsync(g.gs.absmax, 0, 8, s));
+  GradArgs ga{}; ga.margin = cache.margin.p; ga.label = dtrain->d_labels.p; ga.weight = dtrain->weights.empty() ? nullptr : dtrain->d_weights.p;
+  ga.gpair = g.gpair.p; ga.absmax = g.gs.absmax; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = K; ga.objective = param_.objective;
+  ga.scale_pos_weight = param_.scale_pos_weight; ga.subsample = param_.subsample; ga.seed = param_.seed; ga.iter = (unsigned long long)round;
+  ga.row_offset = (int64_t)Comm::get().rank() << 40;
+  launch_gradient(ga, s);
+  Comm::get().allreduce_max_u32(g.gs.absmax, 2, s);
+  launch_scales(g.gs, s);
+
+  for (int k = 0; k < K; ++k) grow_one_tree(dtrain, cache, k, round * K + k);
+}
+
+
+// One tree of class k: the whole level loop is a fixed sequence of launches; every data-dependent decision
+// (which nodes split, which child is built, segment sizes) lives in device memory.
+void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_index) {
+  cudaStream_t s = engine_stream();
+  GrowerImpl& g = *grower_;
+  Comm& comm = Comm::get();
+  const int K = param_.num_class;
+  const int D = param_.max_depth;
+  const TrainParamDev pd = to_dev(param_);
+  const BinnedMatrix bm = dtrain->binned_view();
+  const unsigned char* mask = nullptr;
+  if (param_.colsample_bytree < 1.0f) {
+    std::string m = colsample_mask(param_.seed, tree_index, dtrain->F, param_.colsample_bytree);
+    g.feat_mask.ensure(m.size());
+    CUDA_OK(cudaMemcpyAsync(g.feat_mask.p, m.data(), m.size(), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    mask = g.feat_mask.p;
+  }
+  const unsigned max_tiles = (unsigned)((dtrain->n + kPartTile - 1) / kPartTile) + g.max_level_nodes + 1;
+
+  launch_init_tree(g.gs, g.ta, (unsigned)dtrain->n, 0, g.max_level_nodes, s);
+  CUDA_OK(cudaMemsetAsync(g.hist_pool.p, 0, g.slot_stride * sizeof(GH64), s));
+
+  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.gpair = g.gpair.p + (size_t)k * dtrain->n; ha.ridx = nullptr;
+  ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
+  ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups;
+  ha.accumulate_sum = 1;
+  launch_hist_build(ha, g.hist_grid_x, s);
+  if (comm.distributed()) {
+    comm.allreduce_sum_i64(g.hist_pool.p, g.slot_stride * 2, s);
+    comm.allreduce_sum_i64(g.gs.node_sum, 2, s);
+  }
+  EvalArgs ea{}; ea.hist_pool = g.hist_pool.p; ea.gs = g.gs; ea.cut_ptrs = dtrain->d_cut_ptrs.p; ea.feat_mask = mask; ea.p = pd; ea.F = bm.F;
+  ea.ngroups = bm.ngroups; ea.fpg = bm.fpg; ea.has_missing = bm.has_missing; ea.level = 0; ea.max_level_nodes = g.max_level_nodes;
+  launch_eval(ea, 1, s);
+
+  for (int L = 0; L < D; ++L) {
+    const bool final_level = (L == D - 1);
+    const int next_base = ((L + 1) & 1) * g.region, next_half = 1 << L;
+    ApplyArgs aa{}; aa.gs = g.gs; aa.tree = g.ta; aa.cut_ptrs = dtrain->d_cut_ptrs.p; aa.cut_vals = dtrain->d_cut_vals.p; aa.min_vals = dtrain->d_min_vals.p;
+    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups; aa.level = L; aa.max_level_nodes = g.max_level_nodes; aa.next_base = next_base; aa.next_half = next_half;
+    launch_apply(aa, s);
+    PartArgs pa{}; pa.gs = g.gs; pa.tree = g.ta; pa.bins = bm.bins; pa.n = bm.n;
+    pa.ridx_cur = L == 0 ? nullptr : ((L & 1) ? g.ridx0.p : g.ridx1.p);
+    pa.ridx_next = (L & 1) ? g.ridx1.p : g.ridx0.p;
+    pa.margin = cache.margin.p; pa.K = K; pa.k = k; pa.fpg = bm.fpg; pa.has_missing = bm.has_missing; pa.level = L; pa.max_level_nodes = g.max_level_nodes;
+    pa.final_level = final_level ? 1 : 0;
+    launch_partition(pa, max_tiles, 1 << L, s);
+    if (final_level) break;
+    // histograms of the next level: build the smaller children, all-reduce, subtract for the siblings
+    CUDA_OK(cudaMemsetAsync(g.hist_pool.p + (size_t)next_base * g.slot_stride, 0, (size_t)next_half * g.slot_stride * sizeof(GH64), s));
+    ha.ridx = pa.ridx_next; ha.accumulate_sum = 0;
+    launch_hist_build(ha, g.hist_grid_x, s);
+    if (comm.distributed()) comm.allreduce_sum_i64(g.hist_pool.p + (size_t)next_base * g.slot_stride, (size_t)next_half * g.slot_stride * 2, s);
+    launch_subtract(g.gs, g.hist_pool.p, bm.ngroups, next_half, s);
+    ea.level = L + 1;
+    launch_eval(ea, 1 << (L + 1), s);
+  }
+
+  // ---- hand the finished tree to the model: device copy for prediction, async host copy for model IO
+  const size_t need = d_nodes_used + (size_t)g.cap_nodes;
+  if (need > d_nodes.n) {
+    size_t cap = std::max<size_t>(d_nodes.n * 2, need + 64 * (size_t)g.cap_nodes);
+    DevBuf<DevNode> nb; nb.alloc(cap);
+    if (d_nodes_used) CUDA_OK(cudaMemcpyAsync(nb.p, d_nodes.p, sizeof(DevNode) * d_nodes_used, cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    std::swap(nb.p, d_nodes.p); std::swap(nb.n, d_nodes.n);
+  }
+  pack_tree_kernel<<<(g.cap_nodes + 255) / 256, 256, 0, s>>>(g.ta, g.gs.n_nodes, d_nodes.p + d_nodes_used, g.cap_nodes);
+  CUDA_OK(cudaGetLastError());
+  if (pending_.size() - (size_t)std::count_if(pending_.begin(), pending_.end(), [](const PendingTree& p) { return p.staging == nullptr; }) >= 512) sync_model();
+  PendingTree pt; pt.cap_nodes = (size_t)g.cap_nodes;
+  pt.staging = g.pinned.take(g.tree_block_bytes);
+  if (!g.free_events.empty()) { pt.ready = g.free_events.back(); g.free_events.pop_back(); }
+  else CUDA_OK(cudaEventCreateWithFlags(&pt.ready, cudaEventDisableTiming));
+  CUDA_OK(cudaMemcpyAsync(pt.staging, g.tree_block.p, g.tree_block_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaEventRecord(pt.ready, s));
+  append_device_tree(k, d_nodes_used, g.cap_nodes, pt);
+  d_nodes_used += (size_t)g.cap_nodes;
+  d_trees_uploaded = 0;                      // offsets/info arrays need a refresh before the next predict
+  cache.trees_applied = (int)trees_.size();  // the partition passes already added this tree's leaves to the cache
+}
+
+void Booster::boost_one_iter(DMatrix*, const float*, const float*, size_t) {
+  throw Error("custom objective (BoostOneIter) is not implemented on the B200 hist path");
+}
+
+int Booster::boosted_rounds() { configure(); return (int)trees_.size() / std::max(1, param_.num_class); }
+
+// ---------------------------------------------------------------------------------------------
+// evaluation  (upstream src/learner.cc EvalOneIter: "[iter]\t<name>-<metric>:<value>")
+// ---------------------------------------------------------------------------------------------
+static std::string default_metric(int objective) {
+  switch (objective) { case kSquaredError: case kRegLogistic: return "rmse"; case kBinaryLogistic: case kLogitRaw: return "logloss"; default: return "mlogloss"; }
+}
+
+std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, const std::vector<std::string>& names) {
+  configure();
+  cudaStream_t s = engine_stream();
+  std::vector<std::string> metrics = eval_metrics_;
+  if (metrics.empty()) metrics.push_back(default_metric(param_.objective));
+  if (!grower_) grower_ = new GrowerImpl();
+  grower_->dsum.ensure(4);
+  std::string out = "[" + std::to_string(iter) + "]";
+  for (size_t i = 0; i < dms.size(); ++i) {
+    DMatrix* dm = dms[i];
+    check_labels(dm);
+    PredCache& c = cache_for(dm);
+    bring_cache_up_to_date(dm, c);
+    for (const std::string& mname : metrics) {
+      MetricArgs ma{}; ma.margin = c.margin.p; ma.label = dm->d_labels.p; ma.weight = dm->weights.empty() ? nullptr : dm->d_weights.p;
+      ma.out = grower_->dsum.p; ma.n = dm->n; ma.K = param_.num_class; ma.threshold = 0.5f;
+      ma.is_logistic = (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic) ? 1 : 0;
+      std::string base = mname;
+      if (mname.rfind("error@", 0) == 0) { base = "error"; ma.threshold = std::stof(mname.substr(6)); }
+      if (base == "rmse") ma.metric = kMetricRmse; else if (base == "mse") ma.metric = kMetricRmse; else if (base == "mae") ma.metric = kMetricMae;
+      else if (base == "logloss") ma.metric = kMetricLogloss; else if (base == "error") ma.metric = kMetricError;
+      else if (base == "merror") ma.metric = kMetricMerror; else if (base == "mlogloss") ma.metric = kMetricMlogloss;
+      else throw Error("Unknown metric function " + mname + " (B200 hist path implements rmse, mae, logloss, error, error@t, merror, mlogloss)");
+      if (param_.objective == kLogitRaw && (ma.metric == kMetricLogloss || ma.metric == kMetricError)) ma.is_logistic = 1;
+      if ((ma.metric == kMetricMerror || ma.metric == kMetricMlogloss)) B200_CHECK(param_.num_class > 1, "Check failed: preds.size() == info.labels_.size() : label and prediction size not match, hint: use merror or mlogloss for multi-class classification");
+      CUDA_OK(cudaMemsetAsync(grower_->dsum.p, 0, 2 * sizeof(double), s));
+      launch_metric(ma, s);
+      Comm::get().allreduce_sum_f64(grower_->dsum.p, 2, s);
+      double h[2];
+      CUDA_OK(cudaMemcpyAsync(h, grower_->dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaStreamSynchronize(s));
+      double v = h[1] == 0.0 ? h[0] : h[0] / h[1];
+      if (mname == "rmse") v = std::sqrt(v);
+      char buf[64]; snprintf(buf, sizeof buf, "%.17g", v);
+      out += "\t" + names[i] + "-" + mname + ":" + buf;
+    }
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prediction (upstream Booster.predict -> XGBoosterPredictFromDMatrix; cpu_predictor.cc semantics)
+// type: 0 value, 1 margin, 6 leaf
+// ---------------------------------------------------------------------------------------------
+void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int iter_end, bool strict_shape,
+                      std::vector<float>* out, std::vector<uint64_t>* shape) {
+  configure();
+  (void)training;
+  cudaStream_t s = engine_stream();
+  const int K = param_.num_class;
+  const int rounds = (int)trees_.size() / K;
+  if (iter_end == 0) iter_end = rounds;
+  B200_CHECK(iter_begin >= 0 && iter_begin <= iter_end && iter_end <= rounds, "Invalid iteration range: [" + std::to_string(iter_begin) + ", " + std::to_string(iter_end) + ") for a model with " + std::to_string(rounds) + " rounds");
+  if (num_feature_ > 0 && !trees_.empty())
+    B200_CHECK(dm->F <= num_feature_ || true, "feature count mismatch");
+  B200_CHECK(type == 0 || type == 1 || type == 6, "predict type " + std::to_string(type) + " (contributions / interactions) is not implemented on the B200 path");
+  upload_model();
+  const int tb = iter_begin * K, te = iter_end * K;
+  const int64_t n = dm->n;
+  PredictArgs pa{}; pa.X = dm->X.p; pa.n = n; pa.F = dm->F; pa.nodes = d_nodes.p; pa.tree_offset = d_tree_offset.p; pa.tree_info = d_tree_info.p;
+  pa.tree_begin = tb; pa.tree_end = te; pa.K = K;
+  if (type == 6) {
+    const int nt = te - tb;
+    DevBuf<int> leaf; leaf.alloc((size_t)n * std::max(nt, 1));
+    pa.margin = nullptr; pa.leaf = leaf.p;
+    launch_predict(pa, s);
+    std::vector<int> h((size_t)n * nt);
+    if (!h.empty()) CUDA_OK(cudaMemcpyAsync(h.data(), leaf.p, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    out->resize(h.size());
+    for (size_t i = 0; i < h.size(); ++i) (*out)[i] = (float)h[i];
+    shape->assign({(uint64_t)n, (uint64_t)nt});
+    return;
+  }
+  DevBuf<float> margin; margin.alloc((size_t)n * K);
+  if (!dm->base_margin.empty()) {
+    B200_CHECK(dm->base_margin.size() == (size_t)n * K, "base_margin size does not match rows x groups");
+    CUDA_OK(cudaMemcpyAsync(margin.p, dm->d_base_margin.p, sizeof(float) * n * K, cudaMemcpyDeviceToDevice, s));
+  } else launch_fill(margin.p, n * K, base_margin(), s);
+  pa.margin = margin.p; pa.leaf = nullptr;
+  launch_predict(pa, s);
+  int out_cols = K;
+  DevBuf<float> cls;
+  if (type == 0) {
+    if (param_.objective == kSoftmax) { cls.alloc(n); launch_transform(margin.p, n, K, param_.objective, cls.p, s); out_cols = 1; }
+    else launch_transform(margin.p, n, K, param_.objective, nullptr, s);
+  }
+  out->resize((size_t)n * out_cols);
+  if (!out->empty()) CUDA_OK(cudaMemcpyAsync(out->data(), (type == 0 && param_.objective == kSoftmax) ? cls.p : margin.p, sizeof(float) * out->size(), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  if (out_cols == 1 && !strict_shape) shape->assign({(uint64_t)n});
+  else shape->assign({(uint64_t)n, (uint64_t)out_cols});
+}
+
+// Kernel-level entry point for parity tests and the roofline bench: build the root histogram of `dm` from host
+// gradient pairs `repeats` times; returns the int64 histogram [ngroups][256][32][2] and the fixed-point scales.
+void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::vector<long long>* hist_out, float* scales_out,
+                                    int repeats, float* ms_out) {
+  configure();
+  cudaStream_t s = engine_stream();
+  dm->ensure_binned(param_.max_bin);
+  if (!grower_) grower_ = new GrowerImpl();
+  GrowerImpl& g = *grower_;
+  g.ensure(dm->n, dm->ngroups, param_.max_depth, param_.num_class);
+  CUDA_OK(cudaMemcpyAsync(g.gpair.p, gpair_host, sizeof(float2) * dm->n, cudaMemcpyHostToDevice, s));
+  // scales from max|g|, max h of the supplied pairs
+  float mg = 0.f, mh = 0.f;
+  for (int64_t i = 0; i < dm->n; ++i) { mg = std::max(mg, std::fabs(gpair_host[2 * i])); mh = std::max(mh, gpair_host[2 * i + 1]); }
+  unsigned am[2]; memcpy(&am[0], &mg, 4); memcpy(&am[1], &mh, 4);
+  CUDA_OK(cudaMemcpyAsync(g.gs.absmax, am, 8, cudaMemcpyHostToDevice, s));
+  launch_scales(g.gs, s);
+  const BinnedMatrix bm = dm->binned_view();
+  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.gpair = g.gpair.p; ha.ridx = nullptr;
+  ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
+  ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups; ha.accumulate_sum = 1;
+  cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  float total = 0.f;
+  for (int r = 0; r < std::max(1, repeats); ++r) {
+    launch_init_tree(g.gs, g.ta, (unsigned)dm->n, 0, g.max_level_nodes, s);
+    CUDA_OK(cudaMemsetAsync(g.hist_pool.p, 0, g.slot_stride * sizeof(GH64), s));
+    CUDA_OK(cudaEventRecord(e0, s));
+    launch_hist_build(ha, g.hist_grid_x, s);
+    CUDA_OK(cudaEventRecord(e1, s));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, e0, e1)); total += ms;
+  }
+  if (ms_out) *ms_out = total / std::max(1, repeats);
+  hist_out->resize(g.slot_stride * 2);
+  CUDA_OK(cudaMemcpyAsync(hist_out->data(), g.hist_pool.p, sizeof(GH64) * g.slot_stride, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(scales_out, g.gs.scales, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+void Booster::cached_margin(DMatrix* dm, std::vector<float>* out) {
+  configure();
+  cudaStream_t s = engine_stream();
+  PredCache& c = cache_for(dm);
+  bring_cache_up_to_date(dm, c);
+  out->resize((size_t)dm->n * param_.num_class);
+  if (!out->empty()) CUDA_OK(cudaMemcpyAsync(out->data(), c.margin.p, sizeof(float) * out->size(), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+}
+
+}  // namespace b200

@@ -1,0 +1,141 @@
+// booster.h -- host-side objects behind the C-ABI handles (DMatrixHandle / BoosterHandle).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "engine.h"
+#include "json.h"
+#include "misc.h"
+#include "tree.h"
+
+namespace b200 {
+
+cudaStream_t engine_stream();
+int engine_num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// DMatrix: features resident on the device (raw float row-major + lazily the binned feature blocks)
+// ---------------------------------------------------------------------------------------------
+class DMatrix {
+ public:
+  int64_t n = 0; int F = 0;
+  bool has_missing = false;
+  DevBuf<float> X;                                    // n x F, NaN = missing
+  std::vector<float> labels, weights, base_margin;    // host copies (returned by GetFloatInfo)
+  DevBuf<float> d_labels, d_weights, d_base_margin;
+  std::vector<std::string> feature_names, feature_types;
+  // binned representation (built on first use as a training matrix)
+  bool binned = false; int binned_max_bin = 0;
+  HostCuts cuts; DevBuf<int> d_cut_ptrs; DevBuf<float> d_cut_vals, d_min_vals;
+  DevBuf<uint8_t> bins; int ngroups = 0, fpg = 0;
+  uint64_t uid;                                       // identity for prediction caches
+
+  DMatrix();
+  static std::unique_ptr<DMatrix> from_dense(const float* data, int64_t nrow, int ncol, float missing);
+  static std::unique_ptr<DMatrix> from_csr(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr, size_t nelem, size_t ncol);
+  std::unique_ptr<DMatrix> slice(const int* idx, int64_t len) const;
+  void set_float_info(const std::string& field, const float* v, size_t len);
+  const std::vector<float>& get_float_info(const std::string& field) const;
+  void ensure_binned(int max_bin);
+  void set_cuts(const HostCuts& c);                   // external cuts (shared with the oracle in tests)
+  BinnedMatrix binned_view() const { BinnedMatrix b; b.bins = bins.p; b.n = n; b.F = F; b.ngroups = ngroups; b.fpg = fpg; b.has_missing = has_missing; return b; }
+ private:
+  void finish_upload(float missing);
+  void bin_with_cuts();
+};
+
+// ---------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------
+struct HostTree {
+  std::vector<int> left, right, parent, split_index, split_bin;
+  std::vector<uint8_t> default_left;
+  std::vector<float> split_cond, base_weight, loss_chg, sum_hess;
+  int num_nodes() const { return (int)left.size(); }
+};
+
+struct PendingTree {            // a tree still on its way from the device (async copy into pinned memory)
+  void* staging = nullptr; size_t cap_nodes = 0; cudaEvent_t ready = nullptr;
+};
+
+struct PredCache { DevBuf<float> margin; int trees_applied = 0; int64_t n = 0; uint64_t model_version = 0; };
+
+class Booster {
+ public:
+  Booster();
+  ~Booster();
+  // configuration
+  void set_param(const std::string& k, const std::string& v);
+  std::string save_config();
+  void load_config(const std::string& json);
+  // training
+  void update_one_iter(int iter, DMatrix* dtrain);
+  void boost_one_iter(DMatrix* dtrain, const float* grad, const float* hess, size_t len);
+  std::string eval_one_iter(int iter, const std::vector<DMatrix*>& dms, const std::vector<std::string>& names);
+  // inference; returns host buffer + shape
+  void predict(DMatrix* dm, int type, bool training, int iter_begin, int iter_end, bool strict_shape,
+               std::vector<float>* out, std::vector<uint64_t>* shape);
+  // model IO
+  std::string save_model_buffer(const std::string& format);      // "ubj" | "json"
+  void load_model_buffer(const char* buf, size_t len);
+  std::string serialize();                                         // model + config (pickle)
+  void unserialize(const char* buf, size_t len);
+  std::unique_ptr<Booster> slice(int begin, int end, int step);
+  int boosted_rounds();
+  int num_features() const { return num_feature_; }
+  std::map<std::string, std::string> attrs;
+  std::vector<std::string> feature_names, feature_types;
+
+  // introspection used by tests/bench (build-specific C-ABI entry points)
+  void sync_model();                              // materialise pending trees on the host
+  void cached_margin(DMatrix* dm, std::vector<float>* out);   // the trainer's prediction cache for dm
+  const std::vector<HostTree>& trees() { sync_model(); return trees_; }
+  const std::vector<int>& tree_info() const { return tree_info_; }
+  float base_score() const { return base_score_; }
+  int num_class() const { return param_.num_class; }
+  const TrainParam& param() { configure(); return param_; }
+  std::map<std::string, double> timers;           // accumulated device milliseconds per phase (when profiling)
+  bool profile = false;
+  // histogram of one node for kernel-level parity tests / the roofline bench
+  void debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::vector<long long>* hist_out, float* scales_out,
+                             int repeats, float* ms_out);
+
+ private:
+  friend struct GrowerImpl;
+  std::map<std::string, std::string> raw_params_;
+  std::vector<std::string> eval_metrics_;
+  bool configured_ = false;
+  TrainParam param_;
+  std::string objective_name_ = "reg:squarederror";
+  bool base_score_set_ = false; float base_score_ = 0.5f; bool base_score_estimated_ = false;
+  int num_feature_ = 0;
+  std::vector<HostTree> trees_; std::vector<int> tree_info_;
+  std::vector<PendingTree> pending_;            // parallel to trees_ (nullptr staging once materialised)
+  std::vector<char> on_device_;                 // parallel to trees_: nodes already in d_nodes
+  uint64_t model_version_ = 0;
+  // device model for prediction
+  DevBuf<DevNode> d_nodes; std::vector<int64_t> h_tree_offset; DevBuf<int64_t> d_tree_offset; DevBuf<int> d_tree_info;
+  size_t d_nodes_used = 0; int d_trees_uploaded = 0;
+  std::map<uint64_t, PredCache> caches_;
+  struct GrowerImpl* grower_ = nullptr;
+  bool labels_checked_ = false;
+
+  void configure();
+  float base_margin() const;
+  void estimate_base_score(DMatrix* dtrain);
+  void upload_model();
+  PredCache& cache_for(DMatrix* dm);
+  void bring_cache_up_to_date(DMatrix* dm, PredCache& c);
+  void append_device_tree(int class_id, size_t device_offset, int max_nodes, PendingTree pt);
+  void grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_index);
+  JPtr model_to_json();
+  void model_from_json(const JValue& doc);
+  JPtr config_to_json();
+  void config_from_json(const JValue& doc);
+  void reset_model();
+};
+
+std::string colsample_mask(unsigned seed, int tree_index, int F, float frac);   // bytes, 1 = feature usable
+
+}  // namespace b200

@@ -1,0 +1,314 @@
+// capi.cc -- extern "C" surface of libb200xgb.so (declared in include/b200xgb.h).
+// Same conventions as libxgboost's c_api.cc: int return code, thread-local last error, handle-owned buffers.
+#include "../../include/b200xgb.h"
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <vector>
+#include "booster.h"
+#include "comm.h"
+
+using namespace b200;
+
+namespace {
+thread_local std::string g_last_error;
+struct DMatrixBox {
+  std::unique_ptr<DMatrix> dm;
+  std::vector<const char*> str_ptrs; std::vector<std::string> strs;
+  std::vector<uint8_t> scratch_u8;
+};
+struct BoosterBox {
+  std::unique_ptr<Booster> bst;
+  std::string ret_str; std::vector<float> ret_vec; std::vector<uint64_t> ret_shape;
+  std::vector<const char*> str_ptrs; std::vector<std::string> strs;
+};
+thread_local std::string g_ret_str;
+
+int fail(const std::exception& e) { g_last_error = e.what(); return -1; }
+DMatrix* DM(DMatrixHandle h) { if (!h) throw Error("DMatrix handle is NULL"); return static_cast<DMatrixBox*>(h)->dm.get(); }
+Booster* BST(BoosterHandle h) { if (!h) throw Error("Booster handle is NULL"); return static_cast<BoosterBox*>(h)->bst.get(); }
+#define API_BEGIN() try {
+#define API_END() } catch (const std::exception& e) { return fail(e); } return 0;
+
+std::string hex_encode(const std::string& s) { static const char* d = "0123456789abcdef"; std::string o; for (unsigned char c : s) { o.push_back(d[c >> 4]); o.push_back(d[c & 15]); } return o; }
+std::string hex_decode(const std::string& s) { std::string o; auto v = [](char c) { return c <= '9' ? c - '0' : (c | 32) - 'a' + 10; };
+  for (size_t i = 0; i + 1 < s.size(); i += 2) o.push_back((char)((v(s[i]) << 4) | v(s[i + 1]))); return o; }
+}  // namespace
+
+extern "C" {
+
+const char* XGBGetLastError(void) { return g_last_error.c_str(); }
+void XGBoostVersion(int* major, int* minor, int* patch) { if (major) *major = 3; if (minor) *minor = 0; if (patch) *patch = 5; }
+int XGBuildInfo(const char** out) {
+  API_BEGIN();
+  g_ret_str = "{\"USE_CUDA\":true,\"USE_NCCL\":true,\"arch\":\"sm_100a\",\"library\":\"b200xgb\",\"CPU_FALLBACK\":false}";
+  *out = g_ret_str.c_str();
+  API_END();
+}
+
+// ------------------------------------------------------------------------------------------- DMatrix
+int XGDMatrixCreateFromMat(const float* data, bst_ulong nrow, bst_ulong ncol, float missing, DMatrixHandle* out) {
+  API_BEGIN();
+  auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
+  box->dm = DMatrix::from_dense(data, (int64_t)nrow, (int)ncol, missing);
+  *out = guard.release();
+  API_END();
+}
+int XGDMatrixCreateFromCSREx(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr, size_t nelem,
+                             size_t num_col, DMatrixHandle* out) {
+  API_BEGIN();
+  auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
+  box->dm = DMatrix::from_csr(indptr, indices, data, nindptr, nelem, num_col);
+  *out = guard.release();
+  API_END();
+}
+int XGDMatrixFree(DMatrixHandle handle) { API_BEGIN(); delete static_cast<DMatrixBox*>(handle); API_END(); }
+int XGDMatrixNumRow(DMatrixHandle handle, bst_ulong* out) { API_BEGIN(); *out = (bst_ulong)DM(handle)->n; API_END(); }
+int XGDMatrixNumCol(DMatrixHandle handle, bst_ulong* out) { API_BEGIN(); *out = (bst_ulong)DM(handle)->F; API_END(); }
+int XGDMatrixSetFloatInfo(DMatrixHandle handle, const char* field, const float* array, bst_ulong len) {
+  API_BEGIN(); DM(handle)->set_float_info(field, array, (size_t)len); API_END();
+}
+int XGDMatrixGetFloatInfo(DMatrixHandle handle, const char* field, bst_ulong* out_len, const float** out_dptr) {
+  API_BEGIN(); const std::vector<float>& v = DM(handle)->get_float_info(field); *out_len = v.size(); *out_dptr = v.data(); API_END();
+}
+int XGDMatrixSliceDMatrix(DMatrixHandle handle, const int* idxset, bst_ulong len, DMatrixHandle* out) {
+  API_BEGIN();
+  auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
+  box->dm = DM(handle)->slice(idxset, (int64_t)len);
+  *out = guard.release();
+  API_END();
+}
+int XGDMatrixSetStrFeatureInfo(DMatrixHandle handle, const char* field, const char** features, bst_ulong size) {
+  API_BEGIN();
+  DMatrix* dm = DM(handle);
+  std::vector<std::string>& dst = std::string(field) == "feature_name" ? dm->feature_names : dm->feature_types;
+  if (std::string(field) != "feature_name" && std::string(field) != "feature_type") throw Error(std::string("Unknown feature info name: ") + field);
+  if (size != 0 && (int64_t)size != dm->F) throw Error("Length of " + std::string(field) + " must be equal to the number of columns");
+  dst.clear(); for (bst_ulong i = 0; i < size; ++i) dst.emplace_back(features[i]);
+  API_END();
+}
+int XGDMatrixGetStrFeatureInfo(DMatrixHandle handle, const char* field, bst_ulong* size, const char*** out_features) {
+  API_BEGIN();
+  DMatrixBox* box = static_cast<DMatrixBox*>(handle); DMatrix* dm = DM(handle);
+  const std::vector<std::string>& src = std::string(field) == "feature_name" ? dm->feature_names : dm->feature_types;
+  box->strs = src; box->str_ptrs.clear(); for (auto& s : box->strs) box->str_ptrs.push_back(s.c_str());
+  *size = box->str_ptrs.size(); *out_features = box->str_ptrs.data();
+  API_END();
+}
+
+// ------------------------------------------------------------------------------------------- Booster
+int XGBoosterCreate(const DMatrixHandle dmats[], bst_ulong len, BoosterHandle* out) {
+  API_BEGIN();
+  (void)dmats; (void)len;      // prediction caches are created lazily per DMatrix
+  auto box = new BoosterBox(); box->bst = std::make_unique<Booster>(); *out = box;
+  API_END();
+}
+int XGBoosterFree(BoosterHandle handle) { API_BEGIN(); delete static_cast<BoosterBox*>(handle); API_END(); }
+int XGBoosterSetParam(BoosterHandle handle, const char* name, const char* value) { API_BEGIN(); BST(handle)->set_param(name, value ? value : ""); API_END(); }
+int XGBoosterUpdateOneIter(BoosterHandle handle, int iter, DMatrixHandle dtrain) { API_BEGIN(); BST(handle)->update_one_iter(iter, DM(dtrain)); API_END(); }
+int XGBoosterBoostOneIter(BoosterHandle handle, DMatrixHandle dtrain, float* grad, float* hess, bst_ulong len) {
+  API_BEGIN(); BST(handle)->boost_one_iter(DM(dtrain), grad, hess, (size_t)len); API_END();
+}
+int XGBoosterEvalOneIter(BoosterHandle handle, int iter, DMatrixHandle dmats[], const char* evnames[], bst_ulong len, const char** out_result) {
+  API_BEGIN();
+  BoosterBox* box = static_cast<BoosterBox*>(handle);
+  std::vector<DMatrix*> dms; std::vector<std::string> names;
+  for (bst_ulong i = 0; i < len; ++i) { dms.push_back(DM(dmats[i])); names.emplace_back(evnames[i]); }
+  box->ret_str = BST(handle)->eval_one_iter(iter, dms, names);
+  *out_result = box->ret_str.c_str();
+  API_END();
+}
+int XGBoosterPredictFromDMatrix(BoosterHandle handle, DMatrixHandle dmat, const char* config, bst_ulong const** out_shape,
+                                bst_ulong* out_dim, float const** out_result) {
+  API_BEGIN();
+  BoosterBox* box = static_cast<BoosterBox*>(handle);
+  JPtr cfg = parse_json(config ? config : "{}");
+  auto geti = [&](const char* k, int64_t def) { auto v = cfg->get(k); return v ? v->as_int() : def; };
+  auto getb = [&](const char* k, bool def) { auto v = cfg->get(k); if (!v) return def; return v->type == JValue::kBool ? v->b : v->as_int() != 0; };
+  BST(handle)->predict(DM(dmat), (int)geti("type", 0), getb("training", false), (int)geti("iteration_begin", 0), (int)geti("iteration_end", 0),
+                       getb("strict_shape", false), &box->ret_vec, &box->ret_shape);
+  *out_shape = box->ret_shape.data(); *out_dim = box->ret_shape.size(); *out_result = box->ret_vec.data();
+  API_END();
+}
+static bool ends_with(const std::string& s, const char* suf) { size_t n = strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; }
+int XGBoosterSaveModel(BoosterHandle handle, const char* fname) {
+  API_BEGIN();
+  std::string f(fname);
+  std::string buf = BST(handle)->save_model_buffer(ends_with(f, ".json") ? "json" : "ubj");
+  std::ofstream os(f, std::ios::binary);
+  if (!os) throw Error("Opening " + f + " failed: cannot write the model file");
+  os.write(buf.data(), (std::streamsize)buf.size());
+  if (!os) throw Error("Writing " + f + " failed");
+  API_END();
+}
+int XGBoosterLoadModel(BoosterHandle handle, const char* fname) {
+  API_BEGIN();
+  std::ifstream is(fname, std::ios::binary);
+  if (!is) throw Error(std::string("Opening ") + fname + " failed: No such file or directory");
+  std::string buf((std::istreambuf_iterator<char>(is)), std::istreambuf_iterator<char>());
+  BST(handle)->load_model_buffer(buf.data(), buf.size());
+  API_END();
+}
+int XGBoosterSaveModelToBuffer(BoosterHandle handle, const char* config, bst_ulong* out_len, const char** out_dptr) {
+  API_BEGIN();
+  BoosterBox* box = static_cast<BoosterBox*>(handle);
+  JPtr cfg = parse_json(config ? config : "{}");
+  std::string fmt = cfg->has("format") ? cfg->at("format").s : "ubj";
+  if (fmt != "json" && fmt != "ubj") throw Error("Unknown model format: " + fmt + " (expected json or ubj)");
+  box->ret_str = BST(handle)->save_model_buffer(fmt);
+  *out_len = box->ret_str.size(); *out_dptr = box->ret_str.data();
+  API_END();
+}
+int XGBoosterLoadModelFromBuffer(BoosterHandle handle, const void* buf, bst_ulong len) { API_BEGIN(); BST(handle)->load_model_buffer((const char*)buf, (size_t)len); API_END(); }
+int XGBoosterSerializeToBuffer(BoosterHandle handle, bst_ulong* out_len, const char** out_dptr) {
+  API_BEGIN(); BoosterBox* box = static_cast<BoosterBox*>(handle); box->ret_str = BST(handle)->serialize(); *out_len = box->ret_str.size(); *out_dptr = box->ret_str.data(); API_END();
+}
+int XGBoosterUnserializeFromBuffer(BoosterHandle handle, const void* buf, bst_ulong len) { API_BEGIN(); BST(handle)->unserialize((const char*)buf, (size_t)len); API_END(); }
+int XGBoosterSaveJsonConfig(BoosterHandle handle, bst_ulong* out_len, const char** out_str) {
+  API_BEGIN(); BoosterBox* box = static_cast<BoosterBox*>(handle); box->ret_str = BST(handle)->save_config(); *out_len = box->ret_str.size(); *out_str = box->ret_str.c_str(); API_END();
+}
+int XGBoosterLoadJsonConfig(BoosterHandle handle, const char* config) { API_BEGIN(); BST(handle)->load_config(config); API_END(); }
+int XGBoosterGetNumFeature(BoosterHandle handle, bst_ulong* out) { API_BEGIN(); *out = (bst_ulong)BST(handle)->num_features(); API_END(); }
+int XGBoosterBoostedRounds(BoosterHandle handle, int* out) { API_BEGIN(); *out = BST(handle)->boosted_rounds(); API_END(); }
+int XGBoosterSlice(BoosterHandle handle, int begin_layer, int end_layer, int step, BoosterHandle* out) {
+  API_BEGIN();
+  auto box = new BoosterBox(); std::unique_ptr<BoosterBox> guard(box);
+  box->bst = BST(handle)->slice(begin_layer, end_layer, step);
+  *out = guard.release();
+  API_END();
+}
+int XGBoosterGetAttr(BoosterHandle handle, const char* key, const char** out, int* success) {
+  API_BEGIN();
+  BoosterBox* box = static_cast<BoosterBox*>(handle);
+  auto it = BST(handle)->attrs.find(key);
+  if (it == BST(handle)->attrs.end()) { *out = nullptr; *success = 0; }
+  else { box->ret_str = it->second; *out = box->ret_str.c_str(); *success = 1; }
+  API_END();
+}
+int XGBoosterSetAttr(BoosterHandle handle, const char* key, const char* value) {
+  API_BEGIN(); if (value) BST(handle)->attrs[key] = value; else BST(handle)->attrs.erase(key); API_END();
+}
+int XGBoosterGetAttrNames(BoosterHandle handle, bst_ulong* out_len, const char*** out) {
+  API_BEGIN();
+  BoosterBox* box = static_cast<BoosterBox*>(handle);
+  box->strs.clear(); for (auto& kv : BST(handle)->attrs) box->strs.push_back(kv.first);
+  box->str_ptrs.clear(); for (auto& s : box->strs) box->str_ptrs.push_back(s.c_str());
+  *out_len = box->str_ptrs.size(); *out = box->str_ptrs.data();
+  API_END();
+}
+int XGBoosterSetStrFeatureInfo(BoosterHandle handle, const char* field, const char** features, bst_ulong size) {
+  API_BEGIN();
+  Booster* b = BST(handle);
+  if (std::string(field) != "feature_name" && std::string(field) != "feature_type") throw Error(std::string("Unknown feature info name: ") + field);
+  std::vector<std::string>& dst = std::string(field) == "feature_name" ? b->feature_names : b->feature_types;
+  dst.clear(); for (bst_ulong i = 0; i < size; ++i) dst.emplace_back(features[i]);
+  API_END();
+}
+int XGBoosterGetStrFeatureInfo(BoosterHandle handle, const char* field, bst_ulong* len, const char*** out_features) {
+  API_BEGIN();
+  BoosterBox* box = static_cast<BoosterBox*>(handle); Booster* b = BST(handle);
+  box->strs = std::string(field) == "feature_name" ? b->feature_names : b->feature_types;
+  box->str_ptrs.clear(); for (auto& s : box->strs) box->str_ptrs.push_back(s.c_str());
+  *len = box->str_ptrs.size(); *out_features = box->str_ptrs.data();
+  API_END();
+}
+
+// ------------------------------------------------------------------------------------------- collective
+int XGCommunicatorInit(const char* config) {
+  API_BEGIN();
+  JPtr cfg = parse_json(config ? config : "{}");
+  int rank = cfg->has("rank") ? (int)cfg->at("rank").as_int() : 0;
+  int world = cfg->has("world_size") ? (int)cfg->at("world_size").as_int() : 1;
+  std::string id = cfg->has("nccl_unique_id") ? hex_decode(cfg->at("nccl_unique_id").s) : std::string();
+  engine_stream();            // binds this process to its GPU (LOCAL_RANK) before NCCL initialises
+  Comm::get().init(id, rank, world);
+  API_END();
+}
+int XGCommunicatorFinalize(void) { API_BEGIN(); Comm::get().finalize(); API_END(); }
+int XGCommunicatorGetRank(void) { return Comm::get().rank(); }
+int XGCommunicatorGetWorldSize(void) { return Comm::get().world(); }
+int XGCommunicatorGetUniqueId(const char** out_hex) {
+  API_BEGIN(); engine_stream(); g_ret_str = hex_encode(Comm::create_unique_id()); *out_hex = g_ret_str.c_str(); API_END();
+}
+
+// ------------------------------------------------------------------------------------------- introspection
+int XGB200DMatrixGetCuts(DMatrixHandle handle, int max_bin, bst_ulong* n_ptrs, const int** ptrs, bst_ulong* n_vals, const float** vals,
+                         const float** mins, int* has_missing) {
+  API_BEGIN();
+  DMatrix* dm = DM(handle); dm->ensure_binned(max_bin);
+  *n_ptrs = dm->cuts.ptrs.size(); *ptrs = dm->cuts.ptrs.data(); *n_vals = dm->cuts.vals.size(); *vals = dm->cuts.vals.data(); *mins = dm->cuts.mins.data();
+  if (has_missing) *has_missing = dm->has_missing ? 1 : 0;
+  API_END();
+}
+int XGB200DMatrixSetCuts(DMatrixHandle handle, const int* ptrs, bst_ulong n_ptrs, const float* vals, const float* mins) {
+  API_BEGIN();
+  HostCuts c; c.ptrs.assign(ptrs, ptrs + n_ptrs); c.vals.assign(vals, vals + (n_ptrs ? ptrs[n_ptrs - 1] : 0)); c.mins.assign(mins, mins + (n_ptrs ? n_ptrs - 1 : 0));
+  DM(handle)->set_cuts(c);
+  API_END();
+}
+int XGB200DMatrixGetBins(DMatrixHandle handle, int max_bin, uint8_t* out_row_major) {
+  API_BEGIN();
+  DMatrix* dm = DM(handle); dm->ensure_binned(max_bin);
+  std::vector<uint8_t> h((size_t)dm->ngroups * dm->n * kSlots);
+  if (!h.empty()) { CUDA_OK(cudaMemcpy(h.data(), dm->bins.p, h.size(), cudaMemcpyDeviceToHost)); }
+  for (int64_t r = 0; r < dm->n; ++r) for (int f = 0; f < dm->F; ++f) {
+    int g = f / dm->fpg, s = f % dm->fpg;
+    out_row_major[r * dm->F + f] = h[((size_t)g * dm->n + r) * kSlots + s];
+  }
+  API_END();
+}
+int XGB200BoosterModelShape(BoosterHandle handle, bst_ulong* num_trees, bst_ulong* num_nodes, float* base_score, int* num_class) {
+  API_BEGIN();
+  Booster* b = BST(handle); const auto& trees = b->trees();
+  size_t nn = 0; for (auto& t : trees) nn += t.left.size();
+  if (num_trees) *num_trees = trees.size(); if (num_nodes) *num_nodes = nn; if (base_score) *base_score = b->base_score();
+  if (num_class) *num_class = b->param().num_class;
+  API_END();
+}
+int XGB200BoosterExportModel(BoosterHandle handle, int64_t* tree_offset, int32_t* tree_info, int32_t* left, int32_t* right, int32_t* parent,
+                             int32_t* split_index, int32_t* split_bin, uint8_t* default_left, float* split_cond, float* base_weight,
+                             float* loss_chg, float* sum_hess) {
+  API_BEGIN();
+  Booster* b = BST(handle); const auto& trees = b->trees(); const auto& info = b->tree_info();
+  size_t off = 0;
+  for (size_t t = 0; t < trees.size(); ++t) {
+    const HostTree& h = trees[t]; const size_t nn = h.left.size();
+    if (tree_offset) tree_offset[t] = (int64_t)off;
+    if (tree_info) tree_info[t] = info[t];
+#define CP(dst, src) if (dst) memcpy(dst + off, src.data(), sizeof(src[0]) * nn)
+    CP(left, h.left); CP(right, h.right); CP(parent, h.parent); CP(split_index, h.split_index); CP(split_bin, h.split_bin);
+    CP(default_left, h.default_left); CP(split_cond, h.split_cond); CP(base_weight, h.base_weight); CP(loss_chg, h.loss_chg); CP(sum_hess, h.sum_hess);
+#undef CP
+    off += nn;
+  }
+  if (tree_offset) tree_offset[trees.size()] = (int64_t)off;
+  API_END();
+}
+int XGB200BuildRootHistogram(BoosterHandle handle, DMatrixHandle dmat, const float* gpair, int repeats, int64_t* out_hist, float* scales, float* out_ms) {
+  API_BEGIN();
+  DMatrix* dm = DM(dmat);
+  std::vector<long long> h; float sc[4];
+  BST(handle)->debug_build_root_hist(dm, gpair, &h, sc, repeats, out_ms);
+  // device layout [group][bin][slot]{g,h} -> [F][256]{g,h}
+  for (int f = 0; f < dm->F; ++f) {
+    int g = f / dm->fpg, s = f % dm->fpg;
+    for (int b = 0; b < kBins; ++b) {
+      size_t src = (((size_t)g * kBins + b) * kSlots + s) * 2, dst = ((size_t)f * kBins + b) * 2;
+      out_hist[dst] = h[src]; out_hist[dst + 1] = h[src + 1];
+    }
+  }
+  if (scales) memcpy(scales, sc, sizeof sc);
+  API_END();
+}
+int XGB200BoosterGetCachedMargin(BoosterHandle handle, DMatrixHandle dmat, float* out) {
+  API_BEGIN();
+  std::vector<float> v;
+  BST(handle)->cached_margin(DM(dmat), &v);
+  memcpy(out, v.data(), sizeof(float) * v.size());
+  API_END();
+}
+int XGB200Synchronize(void) { API_BEGIN(); CUDA_OK(cudaStreamSynchronize(engine_stream())); API_END(); }
+
+}  // extern "C"

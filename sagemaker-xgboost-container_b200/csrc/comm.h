@@ -1,0 +1,35 @@
+// comm.h -- in-engine collective used by the tree builder: NCCL over NVLink, one process per GPU.
+// Replaces the histogram AllReduce that upstream xgboost performs inside libxgboost (src/collective/*),
+// which the container reaches through distributed.py:42-109 (rabit_run) / distributed_gpu_training.py:184-192.
+// libnccl is resolved with dlopen at first use so the library also loads on hosts without NCCL / without a GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+class Comm {
+ public:
+  static Comm& get();
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  bool distributed() const { return world_ > 1; }
+  // rank 0 creates the id (128 bytes) and ships it to the others through the Python-side bootstrap
+  // (torch.distributed / tracker); every rank then calls init.
+  static std::string create_unique_id();
+  void init(const std::string& unique_id, int rank, int world);
+  void finalize();
+  void allreduce_sum_i64(void* buf, size_t count, cudaStream_t s);
+  void allreduce_sum_f64(void* buf, size_t count, cudaStream_t s);
+  void allreduce_max_u32(void* buf, size_t count, cudaStream_t s);
+  void allgather_bytes(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
+  void broadcast_bytes(void* buf, size_t bytes, int root, cudaStream_t s);
+ private:
+  int rank_ = 0, world_ = 1;
+  void* comm_ = nullptr;
+};
+
+}  // namespace b200

@@ -1,0 +1,108 @@
+// engine.h -- internal declarations shared by the CUDA translation units of libb200xgb.so.
+// Product code: B200 (sm_100a) gradient-boosted-tree trainer/predictor behind the xgboost C API
+// surface that the SageMaker XGBoost container reaches through `import xgboost`.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+#define B200_CHECK(cond, msg) do { if (!(cond)) throw ::b200::Error(std::string(msg)); } while (0)
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw ::b200::Error( \
+    std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); } while (0)
+
+template <typename T> struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count) { if (count == n && p) return; release(); if (count) { CUDA_OK(cudaMalloc(&p, count * sizeof(T))); } n = count; }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  void zero(cudaStream_t s) { if (n) CUDA_OK(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// layout constants (DESIGN.md "data layout in HBM")
+// ---------------------------------------------------------------------------------------------
+constexpr int kSlots = 32;            // feature slots per group == bytes per row slice == one 32 B sector
+constexpr int kBins = 256;            // bins per feature (uint8 codes); code 255 = missing when has_missing
+constexpr int kGroupEntries = kBins * kSlots;          // (bin, slot) accumulators per feature group
+constexpr int kMissingBin = 255;
+constexpr int kGradBits = 18;         // |g_q| <= 2^18, h_q <= 2^19: one 4096-row window cannot overflow int32
+constexpr int kHessBits = 19;
+constexpr int kMaxDepth = 16;
+
+struct GH64 { long long g, h; };      // exact fixed-point gradient/hessian sums
+
+// One feature group of the binned matrix: rows x 32 B, row-major ("row-major binned feature block").
+struct BinnedMatrix {
+  const uint8_t* bins = nullptr;      // [ngroups][n][32]
+  int64_t n = 0;
+  int F = 0, ngroups = 0, fpg = 0;    // feature f -> group f / fpg, slot f % fpg
+  int has_missing = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// training parameters (names follow the container's hyperparameter schema,
+// reference: src/sagemaker_xgboost_container/algorithm_mode/hyperparameter_validation.py:141-346)
+// ---------------------------------------------------------------------------------------------
+enum Objective : int { kSquaredError = 0, kBinaryLogistic = 1, kRegLogistic = 2, kLogitRaw = 3, kSoftprob = 4, kSoftmax = 5 };
+
+struct TrainParam {
+  int objective = kSquaredError;
+  int num_class = 1;
+  int max_depth = 6, max_leaves = 0, max_bin = 256;
+  float eta = 0.3f, lambda = 1.0f, alpha = 0.0f, gamma = 0.0f, min_child_weight = 1.0f, max_delta_step = 0.0f;
+  float scale_pos_weight = 1.0f, subsample = 1.0f, colsample_bytree = 1.0f, colsample_bylevel = 1.0f, colsample_bynode = 1.0f;
+  unsigned seed = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// device-side tree-growing state (one per Booster; all control decisions stay on the device so a
+// whole tree is one stream of launches with no host synchronisation)
+// ---------------------------------------------------------------------------------------------
+struct SplitCand {
+  float loss_chg; int feature; int bin; int dleft; int ord;
+  long long GL, HL;                   // fixed-point left sums (right = node - left)
+};
+
+struct TreeArrays {                   // capacity max_nodes each; the layout the model file stores
+  int *left, *right, *parent, *split_index, *split_bin;
+  unsigned char* default_left;
+  float *split_cond, *base_weight, *loss_chg, *sum_hess;
+};
+
+struct GrowState {
+  // per tree-node (indexed by nid)
+  unsigned* seg_begin; unsigned* seg_count;     // row segment in the row-index buffer
+  int* hist_slot;                               // slot in the histogram pool
+  GH64* node_sum;                               // exact node totals
+  float* root_gain; float* weight;
+  SplitCand* best;                              // reduced over groups
+  SplitCand* best_group;                        // [nid][ngroups]
+  // per level
+  int* level_nodes;                             // [kMaxDepth+1][max_level_nodes] nids alive at each depth
+  int* level_count;                             // [kMaxDepth+2]
+  // build list of the level being built
+  int* build_nid; int* build_sub_nid; int* build_parent_slot; int* build_count;   // build_count[0]
+  unsigned* build_prefix;                       // exclusive prefix of seg_count over the build list (+ total)
+  // partition plan of the level being split
+  int* part_action;                             // per alive node index at level: 0 leaf, 1 split
+  unsigned* tile_prefix;                        // per alive node: exclusive prefix of tile counts (+ total)
+  unsigned* tile_left; unsigned* tile_off;      // per tile
+  unsigned char* flags;                         // per row position: goes left
+  int* n_nodes; int* n_leaves;
+  float* scales;                                // [0]=sg [1]=sh [2]=1/sg [3]=1/sh
+  unsigned* absmax;                             // [0]=max|g| bits [1]=max h bits
+};
+
+}  // namespace b200

@@ -1,0 +1,270 @@
+// misc.cu -- objective gradients, feature binning, tree-traversal predictor and evaluation metrics.
+// SURVEY.md section 8a rows A5, A5b, A6 (binning half), A11, A12.  Formulas restate upstream xgboost
+// (src/objective/regression_loss.h, multiclass_obj.cu, src/data/gradient_index.cc, src/predictor/cpu_predictor.cc,
+// src/metric/elementwise_metric.cu, multiclass_metric.cu) as written down in oracle/gbt_oracle.c.
+#include "engine.h"
+#include "misc.h"
+
+namespace b200 {
+
+__device__ __forceinline__ float sigmoidf_xgb(float x) {
+  const float kEps = 1e-16f;
+  x = fminf(-x, 88.7f);
+  float denom = expf(x) + 1.0f + kEps;
+  return 1.0f / denom;
+}
+
+__device__ __forceinline__ unsigned long long splitmix64_dev(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL; return x ^ (x >> 31);
+}
+__device__ __forceinline__ float rng_uniform_dev(unsigned seed, unsigned long long stream, unsigned long long idx) {
+  unsigned long long h = splitmix64_dev(splitmix64_dev(((unsigned long long)seed << 32) ^ stream) ^ idx);
+  return (float)(h >> 40) * (1.0f / 16777216.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient pairs: one thread per row, all K classes; also the running max|g|, max h of the round
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gradient_kernel(GradArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float mg = 0.f, mh = 0.f;
+  if (r < a.n) {
+    const float y = a.label[r];
+    float w = a.weight ? a.weight[r] : 1.0f;
+    bool dropped = false;
+    if (a.subsample < 1.0f) dropped = !(rng_uniform_dev(a.seed, 0x2000ull + a.iter, (unsigned long long)(r + a.row_offset)) < a.subsample);
+    if (a.objective == kSoftprob || a.objective == kSoftmax) {
+      const int K = a.K;
+      const float* m = a.margin ? a.margin + r * K : nullptr;
+      float wmax = m ? m[0] : 0.f;
+      for (int k = 1; k < K; ++k) wmax = fmaxf(wmax, m ? m[k] : 0.f);
+      float wsum = 0.f;
+      for (int k = 0; k < K; ++k) wsum += expf((m ? m[k] : 0.f) - wmax);
+      int label = (int)y;
+      if (label < 0 || label >= K) { *a.err = 2; label = 0; }
+      for (int k = 0; k < K; ++k) {
+        float pk = expf((m ? m[k] : 0.f) - wmax) / wsum;
+        float h = fmaxf(2.0f * pk * (1.0f - pk) * w, 1e-16f);
+        float g = (label == k ? pk - 1.0f : pk) * w;
+        if (dropped) { g = 0.f; h = 0.f; }
+        a.gpair[(int64_t)k * a.n + r] = make_float2(g, h);
+        mg = fmaxf(mg, fabsf(g)); mh = fmaxf(mh, h);
+      }
+    } else {
+      if (y == 1.0f) w *= a.scale_pos_weight;
+      float p = a.margin ? a.margin[r] : 0.f, g, h;
+      if (a.objective == kSquaredError) { g = p - y; h = 1.0f; }
+      else {
+        if (y < 0.0f || y > 1.0f) *a.err = 1;
+        p = sigmoidf_xgb(p); g = p - y; h = fmaxf(p * (1.0f - p), 1e-16f);
+      }
+      g *= w; h *= w;
+      if (dropped) { g = 0.f; h = 0.f; }
+      a.gpair[r] = make_float2(g, h);
+      mg = fabsf(g); mh = h;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o)); mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o)); }
+  __shared__ float sg[8], sh[8];
+  if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = mg; sh[threadIdx.x >> 5] = mh; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mg = fmaxf(mg, sg[w]); mh = fmaxf(mh, sh[w]); }
+    if (a.absmax) { atomicMax(a.absmax, __float_as_uint(mg)); atomicMax(a.absmax + 1, __float_as_uint(mh)); }
+  }
+}
+
+// sum of (g,h) over rows in double (base-score stump)
+__global__ void __launch_bounds__(256) sum_gpair_kernel(const float2* gp, int64_t n, double* out) {
+  double g = 0, h = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) { float2 v = gp[r]; g += v.x; h += v.y; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); h += __shfl_xor_sync(0xffffffffu, h, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, g); atomicAdd(out + 1, h); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// binning: float matrix (row-major, NaN = missing) -> uint8 feature-group blocks [g][n][32]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bin_kernel(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups,
+                                                  const int* cut_ptrs, const float* cut_vals, uint8_t* bins) {
+  const int64_t total = n_chunk * ngroups * kSlots;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(idx % kSlots);
+    const int64_t t = idx / kSlots;
+    const int64_t r = t % n_chunk;
+    const int g = (int)(t / n_chunk);
+    const int f = g * fpg + s;
+    uint8_t b = 0;
+    if (s < fpg && f < F) {
+      float v = X[r * F + f];
+      if (isnan(v)) b = kMissingBin;
+      else {
+        const float* c = cut_vals + cut_ptrs[f];
+        int nc = cut_ptrs[f + 1] - cut_ptrs[f];
+        int lo = 0, hi = nc;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (c[mid] > v) hi = mid; else lo = mid + 1; }
+        if (lo >= nc) lo = nc - 1;
+        b = (uint8_t)lo;
+      }
+    }
+    bins[((int64_t)g * n_total + row0 + r) * kSlots + s] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256) count_nan_kernel(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = X[i];
+    c += (isnan(v) || (use_missing && v == missing)) ? 1ull : 0ull;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void __launch_bounds__(256) replace_missing_kernel(float* X, int64_t count, float missing) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    if (X[i] == missing) X[i] = __int_as_float(0x7fc00000);
+}
+
+// ---------------------------------------------------------------------------------------------
+// predictor: one thread per row, trees in model order, fp32 accumulation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n) return;
+  const float* x = a.X + r * a.F;
+  const int nt = a.tree_end - a.tree_begin;
+  float acc = (a.K == 1 && a.margin) ? a.margin[r] : 0.f;
+  for (int t = a.tree_begin; t < a.tree_end; ++t) {
+    const DevNode* nodes = a.nodes + a.tree_offset[t];
+    int nid = 0;
+    DevNode nd = nodes[0];
+    while (nd.left != -1) {
+      const unsigned f = nd.fidx_dl & 0x7fffffffu;
+      const float v = f < (unsigned)a.F ? __ldg(x + f) : __int_as_float(0x7fc00000);
+      if (isnan(v)) nid = (nd.fidx_dl >> 31) ? nd.left : nd.right;
+      else nid = v < nd.cond ? nd.left : nd.right;
+      nd = nodes[nid];
+    }
+    if (a.margin) { if (a.K == 1) acc += nd.cond; else a.margin[r * a.K + a.tree_info[t]] += nd.cond; }
+    if (a.leaf) a.leaf[r * nt + (t - a.tree_begin)] = nid;
+  }
+  if (a.K == 1 && a.margin) a.margin[r] = acc;
+}
+
+// margins -> predictions (PredTransform), in place
+__global__ void __launch_bounds__(256) transform_kernel(float* m, int64_t n, int K, int objective, float* out_class) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  if (objective == kBinaryLogistic || objective == kRegLogistic) m[r] = sigmoidf_xgb(m[r]);
+  else if (objective == kSoftprob || objective == kSoftmax) {
+    float* p = m + r * K;
+    float wmax = p[0]; int arg = 0;
+    for (int k = 1; k < K; ++k) if (p[k] > wmax) { wmax = p[k]; arg = k; }
+    if (objective == kSoftmax) { out_class[r] = (float)arg; return; }
+    float wsum = 0.f;
+    for (int k = 0; k < K; ++k) { p[k] = expf(p[k] - wmax); wsum += p[k]; }
+    for (int k = 0; k < K; ++k) p[k] /= wsum;
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void __launch_bounds__(256) add_base_margin_kernel(float* p, const float* bm, int64_t count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) p[i] = bm[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise evaluation metrics on raw margins: out[0] += sum(w * loss), out[1] += sum(w)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) metric_kernel(MetricArgs a) {
+  double s = 0, ws = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
+    const float y = a.label[r];
+    const float w = a.weight ? a.weight[r] : 1.0f;
+    float loss = 0.f;
+    if (a.metric == kMetricMlogloss || a.metric == kMetricMerror) {
+      const float* m = a.margin + r * a.K;
+      float wmax = m[0]; int arg = 0;
+      for (int k = 1; k < a.K; ++k) if (m[k] > wmax) { wmax = m[k]; arg = k; }
+      int label = (int)y;
+      if (a.metric == kMetricMerror) loss = (arg != label) ? 1.f : 0.f;
+      else {
+        float wsum = 0.f;
+        for (int k = 0; k < a.K; ++k) wsum += expf(m[k] - wmax);
+        float p = (label >= 0 && label < a.K) ? expf(m[label] - wmax) / wsum : 0.f;
+        const float eps = 1e-16f;
+        loss = p > eps ? -logf(p) : -logf(eps);
+      }
+    } else {
+      float p = a.margin[r];
+      if (a.is_logistic) p = sigmoidf_xgb(p);
+      switch (a.metric) {
+        case kMetricRmse: { float d = p - y; loss = d * d; break; }
+        case kMetricMae: loss = fabsf(p - y); break;
+        case kMetricLogloss: {
+          const float eps = 1e-16f;
+          float pneg = 1.0f - p;
+          if (p < eps) loss = -y * logf(eps) - (1.0f - y) * logf(1.0f - eps);
+          else if (pneg < eps) loss = -y * logf(1.0f - eps) - (1.0f - y) * logf(eps);
+          else loss = -y * logf(p) - (1.0f - y) * logf(pneg);
+          break; }
+        case kMetricError: loss = (p > a.threshold) ? (1.0f - y) : y; break;
+        default: break;
+      }
+    }
+    s += (double)(loss * w); ws += (double)w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ws += __shfl_xor_sync(0xffffffffu, ws, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(a.out, s); atomicAdd(a.out + 1, ws); }
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline int grid_for(int64_t n, int block = 256, int cap = 148 * 16) {
+  int64_t g = (n + block - 1) / block; if (g < 1) g = 1; if (g > cap) g = cap; return (int)g;
+}
+void launch_gradient(const GradArgs& a, cudaStream_t s) {
+  if (a.n == 0) return;
+  gradient_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+}
+void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s) {
+  sum_gpair_kernel<<<grid_for(n), 256, 0, s>>>(gp, n, out); CUDA_OK(cudaGetLastError());
+}
+void launch_bin(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups, const int* cut_ptrs,
+                const float* cut_vals, uint8_t* bins, cudaStream_t s) {
+  if (n_chunk == 0) return;
+  bin_kernel<<<grid_for(n_chunk * ngroups * kSlots, 256, 148 * 32), 256, 0, s>>>(X, n_chunk, row0, n_total, F, fpg, ngroups, cut_ptrs, cut_vals, bins);
+  CUDA_OK(cudaGetLastError());
+}
+void launch_count_nan(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out, cudaStream_t s) {
+  if (count == 0) return;
+  count_nan_kernel<<<grid_for(count), 256, 0, s>>>(X, count, missing, use_missing, out); CUDA_OK(cudaGetLastError());
+}
+void launch_replace_missing(float* X, int64_t count, float missing, cudaStream_t s) {
+  if (count == 0) return;
+  replace_missing_kernel<<<grid_for(count), 256, 0, s>>>(X, count, missing); CUDA_OK(cudaGetLastError());
+}
+void launch_predict(const PredictArgs& a, cudaStream_t s) {
+  if (a.n == 0 || a.tree_end <= a.tree_begin) return;
+  predict_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+}
+void launch_transform(float* m, int64_t n, int K, int objective, float* out_class, cudaStream_t s) {
+  if (n == 0) return;
+  transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, n, K, objective, out_class); CUDA_OK(cudaGetLastError());
+}
+void launch_fill(float* p, int64_t n, float v, cudaStream_t s) {
+  if (n == 0) return;
+  fill_kernel<<<grid_for(n), 256, 0, s>>>(p, n, v); CUDA_OK(cudaGetLastError());
+}
+void launch_metric(const MetricArgs& a, cudaStream_t s) {
+  if (a.n == 0) return;
+  metric_kernel<<<grid_for(a.n), 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace b200

@@ -1,0 +1,61 @@
+// misc.h -- argument blocks and launchers for misc.cu / quantile.cu
+#pragma once
+#include "engine.h"
+
+namespace b200 {
+
+struct GradArgs {
+  const float* margin;      // n x K row-major, nullptr = all zero (base-score stump)
+  const float* label; const float* weight;
+  float2* gpair;            // [K][n]
+  unsigned* absmax;         // max|g|, max h as float bits (atomicMax), may be nullptr
+  int* err;                 // 1 = logistic label range, 2 = multiclass label range
+  int64_t n, row_offset;    // row_offset: global index of local row 0 (multi-GPU subsampling stream)
+  int K, objective;
+  float scale_pos_weight, subsample;
+  unsigned seed; unsigned long long iter;
+};
+
+struct DevNode { float cond; int left; int right; unsigned fidx_dl; };   // 16 B, leaf: left == -1, cond = leaf value
+
+struct PredictArgs {
+  const float* X; int64_t n; int F;
+  const DevNode* nodes; const int64_t* tree_offset; const int* tree_info;
+  int tree_begin, tree_end, K;
+  float* margin;            // n x K, pre-initialised with the base margin; may be nullptr
+  int* leaf;                // n x (tree_end - tree_begin); may be nullptr
+};
+
+enum Metric : int { kMetricRmse = 0, kMetricMae = 1, kMetricLogloss = 2, kMetricError = 3, kMetricMerror = 4, kMetricMlogloss = 5,
+                    kMetricAuc = 6, kMetricMse = 7 };
+
+struct MetricArgs {
+  const float* margin; const float* label; const float* weight; double* out;
+  int64_t n; int K, metric, is_logistic; float threshold;
+};
+
+void launch_gradient(const GradArgs& a, cudaStream_t s);
+void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s);
+void launch_bin(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups, const int* cut_ptrs,
+                const float* cut_vals, uint8_t* bins, cudaStream_t s);
+void launch_count_nan(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out, cudaStream_t s);
+void launch_replace_missing(float* X, int64_t count, float missing, cudaStream_t s);
+void launch_predict(const PredictArgs& a, cudaStream_t s);
+void launch_transform(float* m, int64_t n, int K, int objective, float* out_class, cudaStream_t s);
+void launch_fill(float* p, int64_t n, float v, cudaStream_t s);
+void launch_metric(const MetricArgs& a, cudaStream_t s);
+
+// quantile.cu: exact weighted-quantile cuts per feature (same definition as oracle/gbt_oracle.c cuts_from_distinct).
+// X: device, row-major n x F. Returns host vectors.
+struct HostCuts { std::vector<int> ptrs; std::vector<float> vals; std::vector<float> mins; };
+// Per-feature summary for distributed merging: distinct values + weights (host), capped.
+void compute_cuts_device(const float* dX, int64_t n, int F, const float* dweights, int max_bin, bool has_missing,
+                         HostCuts* out, cudaStream_t s);
+// Distinct-value summary of one rank (for merging cuts across ranks): per feature the sorted distinct values and
+// their weights, exact when a feature has <= cap distinct values, else a cap-point weighted-quantile summary.
+struct FeatureSummary { std::vector<float> vals; std::vector<double> weights; };
+void compute_summaries_device(const float* dX, int64_t n, int F, const float* dweights, int cap,
+                              std::vector<FeatureSummary>* out, cudaStream_t s);
+void cuts_from_summaries(const std::vector<FeatureSummary>& sums, int max_bin, bool has_missing, HostCuts* out);
+
+}  // namespace b200

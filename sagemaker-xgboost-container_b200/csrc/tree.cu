@@ -1,0 +1,430 @@
+// tree.cu -- split evaluation, node expansion, sibling subtraction and row partition kernels of the
+// depth-wise hist tree builder.  Mirrors the behaviour of upstream
+// xgboost's src/tree/hist/evaluate_splits.h, src/tree/driver.h, src/tree/updater_quantile_hist.cc and
+// src/common/partition_builder.h as restated in oracle/gbt_oracle.c; all control flow stays on the device.
+#include "engine.h"
+#include "tree.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// split arithmetic (float/double mix follows upstream src/tree/param.h + split_evaluator.h)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double threshold_l1(double w, double alpha) {
+  if (w > +alpha) return w - alpha;
+  if (w < -alpha) return w + alpha;
+  return 0.0;
+}
+__device__ __forceinline__ float calc_weight(const TrainParamDev& p, double G, double H) {
+  if (H < p.min_child_weight || H <= 0.0) return 0.0f;
+  double dw = -threshold_l1(G, p.alpha) / (H + p.lambda);
+  if (p.max_delta_step != 0.0f && fabs(dw) > p.max_delta_step) dw = copysign((double)p.max_delta_step, dw);
+  return (float)dw;
+}
+__device__ __forceinline__ float calc_gain_given_weight(const TrainParamDev& p, double G, double H, float w) {
+  if (H <= 0.0) return 0.0f;
+  if (p.max_delta_step == 0.0f) { double t = threshold_l1(G, p.alpha); return (float)(t * t / (H + p.lambda)); }
+  float g = (float)G, h = (float)H;
+  return -(2.0f * g * w + (h + p.lambda) * w * w);
+}
+__device__ __forceinline__ float calc_gain(const TrainParamDev& p, double G, double H) {
+  return calc_gain_given_weight(p, G, H, calc_weight(p, G, H));
+}
+__device__ __forceinline__ float calc_split_gain(const TrainParamDev& p, double GL, double HL, double GR, double HR) {
+  float wl = calc_weight(p, GL, HL), wr = calc_weight(p, GR, HR);
+  return calc_gain_given_weight(p, GL, HL, wl) + calc_gain_given_weight(p, GR, HR, wr);
+}
+
+// Total order of candidates == upstream SplitEntry::NeedReplace: larger loss_chg, then lower feature,
+// then earlier position in scan order (forward bins ascending, then backward bins descending).
+__device__ __forceinline__ unsigned long long cand_key(float loss, int f, int ord) {
+  if (!(loss > 0.0f) || isinf(loss)) return 0ull;
+  return ((unsigned long long)__float_as_uint(loss) << 32) | ((unsigned long long)(0xFFFFu - (unsigned)f) << 16) |
+         (unsigned long long)(0xFFFFu - (unsigned)ord);
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void init_tree_kernel(GrowState gs, TreeArrays t, unsigned n, int root_slot, int max_level_nodes) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  *gs.n_nodes = 1; *gs.n_leaves = 1;
+  for (int d = 0; d < kMaxDepth + 2; ++d) gs.level_count[d] = 0;
+  gs.level_count[0] = 1; gs.level_nodes[0] = 0;
+  gs.seg_begin[0] = 0; gs.seg_count[0] = n; gs.hist_slot[0] = root_slot;
+  gs.node_sum[0].g = 0; gs.node_sum[0].h = 0;
+  *gs.build_count = 1; gs.build_nid[0] = 0; gs.build_sub_nid[0] = -1; gs.build_parent_slot[0] = -1;
+  gs.build_prefix[0] = 0; gs.build_prefix[1] = n;
+  t.left[0] = -1; t.right[0] = -1; t.parent[0] = 2147483647; t.split_index[0] = 0; t.split_bin[0] = -1;
+  t.default_left[0] = 0; t.split_cond[0] = 0.f; t.base_weight[0] = 0.f; t.loss_chg[0] = 0.f; t.sum_hess[0] = 0.f;
+  (void)max_level_nodes;
+}
+
+// Fixed-point scales from the all-reduced max|g|, max h of this round: power-of-two so that
+// quantisation is pure rounding to a binary grid and the inverse scaling is exact.
+__global__ void scales_kernel(GrowState gs) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float mg = __uint_as_float(gs.absmax[0]), mh = __uint_as_float(gs.absmax[1]);
+  int eg = 0, eh = 0;
+  if (mg > 0.f && isfinite(mg)) frexpf(mg, &eg);     // mg < 2^eg
+  if (mh > 0.f && isfinite(mh)) frexpf(mh, &eh);
+  float sg = ldexpf(1.0f, kGradBits - eg), sh = ldexpf(1.0f, kHessBits - eh);
+  gs.scales[0] = sg; gs.scales[1] = sh; gs.scales[2] = 1.0f / sg; gs.scales[3] = 1.0f / sh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// split evaluation: one block per (alive node of the level, feature group); thread = (slot, 32-bin segment)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eval_kernel(EvalArgs a) {
+  const int li = blockIdx.x;
+  if (li >= a.gs.level_count[a.level]) return;
+  const int nid = a.gs.level_nodes[(size_t)a.level * a.max_level_nodes + li];
+  const int group = blockIdx.y;
+  const GH64* hist = a.hist_pool + ((int64_t)a.gs.hist_slot[nid] * a.ngroups + group) * kGroupEntries;
+  const int slot = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int f = group * a.fpg + slot;
+  const bool active = slot < a.fpg && f < a.F && (a.feat_mask == nullptr || a.feat_mask[f] != 0);
+  const int nbf = active ? a.cut_ptrs[f + 1] - a.cut_ptrs[f] : 0;
+  const double isg = (double)a.gs.scales[2], ish = (double)a.gs.scales[3];
+  const GH64 tot = a.gs.node_sum[nid];
+  const double G = (double)tot.g * isg, H = (double)tot.h * ish;
+  const float root_gain = calc_gain(a.p, G, H);
+  if (threadIdx.x == 0 && group == 0) { a.gs.root_gain[nid] = root_gain; a.gs.weight[nid] = calc_weight(a.p, G, H); }
+
+  __shared__ long long segG[8][32], segH[8][32];
+  __shared__ unsigned long long wkey[8];
+  const int b0 = seg * 32;
+  long long sG = 0, sH = 0;
+  for (int i = 0; i < 32; ++i) { int b = b0 + i; if (b < nbf) { GH64 v = hist[b * kSlots + slot]; sG += v.g; sH += v.h; } }
+  segG[seg][slot] = sG; segH[seg][slot] = sH;
+  __syncthreads();
+  long long pG = 0, pH = 0, tG = 0, tH = 0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) { long long x = segG[s][slot], y = segH[s][slot]; if (s < seg) { pG += x; pH += y; } tG += x; tH += y; }
+  const bool fmiss = a.has_missing && (tG != tot.g || tH != tot.h);
+
+  SplitCand best; best.loss_chg = 0.f; best.feature = 0; best.bin = -1; best.dleft = 0; best.ord = 0; best.GL = 0; best.HL = 0;
+  unsigned long long bkey = 0ull;
+  const double mcw = (double)a.p.min_child_weight;
+  long long cG = pG, cH = pH;
+  for (int i = 0; i < 32; ++i) {          // forward scan: missing goes right, threshold = cut[b]
+    int b = b0 + i;
+    if (b < nbf) {
+      GH64 v = hist[b * kSlots + slot]; cG += v.g; cH += v.h;
+      double GL = (double)cG * isg, HL = (double)cH * ish;
+      double GR = (double)(tot.g - cG) * isg, HR = (double)(tot.h - cH) * ish;
+      if (HL >= mcw && HR >= mcw) {
+        float lc = calc_split_gain(a.p, GL, HL, GR, HR) - root_gain;
+        unsigned long long k = cand_key(lc, f, b);
+        if (k > bkey) { bkey = k; best.loss_chg = lc; best.feature = f; best.bin = b; best.dleft = 0; best.ord = b; best.GL = cG; best.HL = cH; }
+      }
+    }
+  }
+  if (fmiss) {                            // backward scan: missing goes left, threshold below bin b
+    long long rG = tG - pG, rH = tH - pH;  // non-missing sum of bins >= b0
+    for (int i = 0; i < 32; ++i) {
+      int b = b0 + i;
+      if (b < nbf) {
+        long long lG = tot.g - rG, lH = tot.h - rH;       // left = everything else incl. missing
+        double GL = (double)lG * isg, HL = (double)lH * ish, GR = (double)rG * isg, HR = (double)rH * ish;
+        if (HR >= mcw && HL >= mcw) {
+          float lc = calc_split_gain(a.p, GL, HL, GR, HR) - root_gain;
+          int ord = 256 + (255 - b);
+          unsigned long long k = cand_key(lc, f, ord);
+          if (k > bkey) { bkey = k; best.loss_chg = lc; best.feature = f; best.bin = b - 1; best.dleft = 1; best.ord = ord; best.GL = lG; best.HL = lH; }
+        }
+        GH64 v = hist[b * kSlots + slot]; rG -= v.g; rH -= v.h;
+      }
+    }
+  }
+  // block arg-max of the key
+  unsigned long long k = bkey;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long x = __shfl_xor_sync(0xffffffffu, k, o); k = x > k ? x : k; }
+  if ((threadIdx.x & 31) == 0) wkey[seg] = k;
+  __syncthreads();
+  unsigned long long m = 0ull;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) m = wkey[s] > m ? wkey[s] : m;
+  SplitCand* out = a.gs.best_group + (size_t)nid * a.ngroups + group;
+  if (m == 0ull) { if (threadIdx.x == 0) { SplitCand z; z.loss_chg = 0.f; z.feature = 0; z.bin = -1; z.dleft = 0; z.ord = 0; z.GL = 0; z.HL = 0; *out = z; } }
+  else if (bkey == m) *out = best;        // keys are unique per (feature, ord)
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide exclusive scan over a global int array (single block), returns the total
+// ---------------------------------------------------------------------------------------------
+__device__ unsigned block_exclusive_scan(const unsigned* in, unsigned* out, int n, unsigned* s_tmp /*>=33*/) {
+  unsigned carry = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    unsigned v = i < n ? in[i] : 0u, x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_tmp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = lane < nw ? s_tmp[lane] : 0u, z = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, z, o); if (lane >= o) z += y; }
+      s_tmp[lane] = z - w;                       // exclusive warp offsets
+      if (lane == 31) s_tmp[32] = z;             // chunk total
+    }
+    __syncthreads();
+    if (i < n) out[i] = carry + s_tmp[warp] + x - v;
+    carry += s_tmp[32];
+    __syncthreads();
+  }
+  return carry;
+}
+
+// ---------------------------------------------------------------------------------------------
+// node expansion for one level (single block): validity, child ids, tree arrays, build list, partition plan
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
+  __shared__ unsigned s_tmp[33];
+  GrowState& gs = a.gs; TreeArrays& t = a.tree;
+  const int L = a.level;
+  const int cnt = gs.level_count[L];
+  const int* nodes = gs.level_nodes + (size_t)L * a.max_level_nodes;
+  unsigned* valid = a.scratch;                       // [max_level_nodes]
+  unsigned* rank = a.scratch + a.max_level_nodes;    // [max_level_nodes]
+  unsigned* tiles = a.scratch + 2 * (size_t)a.max_level_nodes;
+  const double isg = (double)gs.scales[2], ish = (double)gs.scales[3];
+  if (L == 0 && threadIdx.x == 0 && cnt > 0) {      // the root was created without a parent: finish it here
+    t.base_weight[0] = gs.weight[0]; t.sum_hess[0] = (float)((double)gs.node_sum[0].h * ish);
+    t.split_cond[0] = a.p.eta * gs.weight[0];
+  }
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int nid = nodes[i];
+    SplitCand best = gs.best_group[(size_t)nid * a.ngroups];
+    unsigned long long bk = cand_key(best.loss_chg, best.feature, best.ord);
+    for (int g = 1; g < a.ngroups; ++g) {
+      SplitCand c = gs.best_group[(size_t)nid * a.ngroups + g];
+      unsigned long long k = cand_key(c.loss_chg, c.feature, c.ord);
+      if (k > bk) { bk = k; best = c; }
+    }
+    gs.best[nid] = best;
+    const GH64 tot = gs.node_sum[nid];
+    bool ok = best.loss_chg > 1e-6f;
+    if (ok && (best.HL == 0 || tot.h - best.HL == 0)) ok = false;
+    if (ok && best.loss_chg < a.p.gamma) ok = false;
+    if (ok && a.p.max_depth > 0 && L >= a.p.max_depth) ok = false;
+    valid[i] = ok ? 1u : 0u;
+  }
+  __syncthreads();
+  if (a.p.max_leaves > 0 && threadIdx.x == 0) {     // Driver::Pop order: increasing nid, stop at max_leaves
+    int leaves = *gs.n_leaves;
+    for (int i = 0; i < cnt; ++i) { if (valid[i]) { if (leaves >= a.p.max_leaves) valid[i] = 0; else ++leaves; } }
+  }
+  __syncthreads();
+  const unsigned nvalid = block_exclusive_scan(valid, rank, cnt, s_tmp);
+  const int n0 = *gs.n_nodes;
+  const bool children_evaluated = (L + 1 < a.p.max_depth) || a.p.max_depth == 0;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int nid = nodes[i];
+    tiles[i] = (gs.seg_count[nid] + kPartTile - 1) / kPartTile;
+    gs.part_action[i] = (int)valid[i];
+    if (!valid[i]) continue;
+    const SplitCand best = gs.best[nid];
+    const GH64 tot = gs.node_sum[nid];
+    const int r = (int)rank[i];
+    const int Lc = n0 + 2 * r, Rc = Lc + 1;
+    const long long GLq = best.GL, HLq = best.HL, GRq = tot.g - best.GL, HRq = tot.h - best.HL;
+    const double GL = (double)GLq * isg, HL = (double)HLq * ish, GR = (double)GRq * isg, HR = (double)HRq * ish;
+    const float wl = calc_weight(a.p, GL, HL), wr = calc_weight(a.p, GR, HR);
+    const int cb = a.cut_ptrs[best.feature];
+    float thr = best.dleft ? (best.bin < 0 ? a.min_vals[best.feature] : a.cut_vals[cb + best.bin]) : a.cut_vals[cb + best.bin];
+    t.left[nid] = Lc; t.right[nid] = Rc; t.split_index[nid] = best.feature; t.split_cond[nid] = thr;
+    t.split_bin[nid] = best.bin; t.default_left[nid] = (unsigned char)best.dleft;
+    t.base_weight[nid] = gs.weight[nid]; t.loss_chg[nid] = best.loss_chg; t.sum_hess[nid] = (float)((double)tot.h * ish);
+    const int ch[2] = {Lc, Rc}; const float cw[2] = {wl, wr}; const double chh[2] = {HL, HR};
+    for (int s = 0; s < 2; ++s) {
+      int c = ch[s];
+      t.left[c] = -1; t.right[c] = -1; t.parent[c] = nid; t.split_index[c] = 0; t.split_bin[c] = -1; t.default_left[c] = 0;
+      t.split_cond[c] = a.p.eta * cw[s]; t.base_weight[c] = a.p.eta * cw[s]; t.loss_chg[c] = 0.f; t.sum_hess[c] = (float)chh[s];
+    }
+    gs.node_sum[Lc].g = GLq; gs.node_sum[Lc].h = HLq; gs.node_sum[Rc].g = GRq; gs.node_sum[Rc].h = HRq;
+    gs.seg_begin[Lc] = 0; gs.seg_count[Lc] = 0; gs.seg_begin[Rc] = 0; gs.seg_count[Rc] = 0;   // set by part_scan
+    if (children_evaluated) {               // build the child with the smaller hessian sum, subtract the sibling
+      int* nxt = gs.level_nodes + (size_t)(L + 1) * a.max_level_nodes;
+      nxt[2 * r] = Lc; nxt[2 * r + 1] = Rc;
+      const bool fewer_right = HRq < HLq;
+      const int bld = fewer_right ? Rc : Lc, sub = fewer_right ? Lc : Rc;
+      gs.hist_slot[bld] = a.next_base + r; gs.hist_slot[sub] = a.next_base + a.next_half + r;
+      gs.build_nid[r] = bld; gs.build_sub_nid[r] = sub; gs.build_parent_slot[r] = gs.hist_slot[nid];
+    }
+  }
+  __syncthreads();
+  const unsigned total_tiles = block_exclusive_scan(tiles, gs.tile_prefix, cnt, s_tmp);
+  if (threadIdx.x == 0) {
+    gs.tile_prefix[cnt] = total_tiles;
+    *gs.n_nodes = n0 + 2 * (int)nvalid;
+    *gs.n_leaves += (int)nvalid;
+    gs.level_count[L + 1] = children_evaluated ? 2 * (int)nvalid : 0;
+    *gs.build_count = children_evaluated ? (int)nvalid : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row partition (stable), fused with the prediction-cache update for rows whose node became a leaf
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_node_of_tile(const unsigned* tile_prefix, int cnt, unsigned tile) {
+  int lo = 0, hi = cnt;        // largest i with tile_prefix[i] <= tile
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (tile_prefix[mid] <= tile) lo = mid; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) part_count_kernel(PartArgs a) {
+  const GrowState& gs = a.gs;
+  const int cnt = gs.level_count[a.level];
+  if (cnt <= 0) return;
+  const unsigned tile = blockIdx.x;
+  if (tile >= gs.tile_prefix[cnt]) return;
+  const int i = find_node_of_tile(gs.tile_prefix, cnt, tile);
+  const int nid = gs.level_nodes[(size_t)a.level * a.max_level_nodes + i];
+  const unsigned lt = tile - gs.tile_prefix[i];
+  const unsigned b = gs.seg_begin[nid], c = gs.seg_count[nid];
+  const unsigned p0 = b + lt * kPartTile, p1 = (b + c < p0 + kPartTile) ? b + c : p0 + kPartTile;
+  float* margin = a.margin;
+  if (!gs.part_action[i]) {                 // node stays a leaf: apply its value to the prediction cache
+    const float v = a.tree.split_cond[nid];
+    for (unsigned p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+      unsigned r = a.ridx_cur ? a.ridx_cur[p] : p;
+      margin[(size_t)r * a.K + a.k] += v;
+    }
+    return;
+  }
+  const int f = a.tree.split_index[nid];
+  const int g = f / a.fpg, s = f % a.fpg;
+  const int sb = a.tree.split_bin[nid], dl = a.tree.default_left[nid];
+  const uint8_t* col = a.bins + (int64_t)g * a.n * kSlots + s;
+  const float lv = a.tree.split_cond[a.tree.left[nid]], rv = a.tree.split_cond[a.tree.right[nid]];
+  unsigned nleft = 0;
+  const unsigned pt = p0 + threadIdx.x * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    unsigned p = pt + j;
+    if (p < p1) {
+      unsigned r = a.ridx_cur ? a.ridx_cur[p] : p;
+      int byte = col[(int64_t)r * kSlots];
+      bool left = (a.has_missing && byte == kMissingBin) ? (dl != 0) : (byte <= sb);
+      if (a.final_level) margin[(size_t)r * a.K + a.k] += left ? lv : rv;
+      else { gs.flags[p] = left ? 1 : 0; nleft += left ? 1u : 0u; }
+    }
+  }
+  if (a.final_level) return;
+  __shared__ unsigned s_cnt[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nleft += __shfl_xor_sync(0xffffffffu, nleft, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = nleft;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned tsum = 0; for (int w = 0; w < 8; ++w) tsum += s_cnt[w]; gs.tile_left[tile] = tsum; }
+}
+
+__global__ void __launch_bounds__(256) part_scan_kernel(PartArgs a) {
+  __shared__ unsigned s_tmp[33];
+  const GrowState& gs = a.gs;
+  const int cnt = gs.level_count[a.level];
+  const int i = blockIdx.x;
+  if (i >= cnt || !gs.part_action[i]) return;
+  const int nid = gs.level_nodes[(size_t)a.level * a.max_level_nodes + i];
+  const unsigned t0 = gs.tile_prefix[i], t1 = gs.tile_prefix[i + 1];
+  const unsigned nl = block_exclusive_scan(gs.tile_left + t0, gs.tile_off + t0, (int)(t1 - t0), s_tmp);
+  if (threadIdx.x == 0) {
+    const unsigned b = gs.seg_begin[nid], c = gs.seg_count[nid];
+    const int Lc = a.tree.left[nid], Rc = a.tree.right[nid];
+    gs.seg_begin[Lc] = b; gs.seg_count[Lc] = nl; gs.seg_begin[Rc] = b + nl; gs.seg_count[Rc] = c - nl;
+  }
+}
+
+__global__ void __launch_bounds__(256) part_scatter_kernel(PartArgs a) {
+  const GrowState& gs = a.gs;
+  const int cnt = gs.level_count[a.level];
+  if (cnt <= 0) return;
+  const unsigned tile = blockIdx.x;
+  if (tile >= gs.tile_prefix[cnt]) return;
+  const int i = find_node_of_tile(gs.tile_prefix, cnt, tile);
+  if (!gs.part_action[i]) return;
+  const int nid = gs.level_nodes[(size_t)a.level * a.max_level_nodes + i];
+  const unsigned lt = tile - gs.tile_prefix[i];
+  const unsigned b = gs.seg_begin[nid], c = gs.seg_count[nid];
+  const unsigned p0 = b + lt * kPartTile, p1 = (b + c < p0 + kPartTile) ? b + c : p0 + kPartTile;
+  const unsigned nl = gs.seg_count[a.tree.left[nid]];
+  const unsigned toff = gs.tile_off[tile];
+  const unsigned pt = p0 + threadIdx.x * 8;
+  unsigned rows[8]; unsigned char fl[8]; unsigned mine = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    unsigned p = pt + j;
+    if (p < p1) { rows[j] = a.ridx_cur ? a.ridx_cur[p] : p; fl[j] = gs.flags[p]; mine += fl[j]; } else { rows[j] = 0; fl[j] = 2; }
+  }
+  __shared__ unsigned s_w[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned x = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  unsigned woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_w[w];
+  unsigned lbefore = woff + x - mine;               // lefts before my first position inside the tile
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (fl[j] == 2) continue;
+    unsigned jj = threadIdx.x * 8 + j;              // position inside the tile
+    unsigned dest;
+    if (fl[j]) { dest = b + toff + lbefore; ++lbefore; }
+    else dest = b + nl + (lt * kPartTile + jj - toff - lbefore);
+    a.ridx_next[dest] = rows[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) build_prefix_kernel(GrowState gs) {
+  __shared__ unsigned s_tmp[33];
+  const int nb = *gs.build_count;
+  if (nb <= 0) { if (threadIdx.x == 0) gs.build_prefix[0] = 0; return; }
+  // counts of the build nodes -> tile_left is free at this point; reuse tile_off as temp input
+  unsigned* tmp = gs.tile_left;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) tmp[i] = gs.seg_count[gs.build_nid[i]];
+  __syncthreads();
+  unsigned total = block_exclusive_scan(tmp, gs.build_prefix, nb, s_tmp);
+  if (threadIdx.x == 0) gs.build_prefix[nb] = total;
+}
+
+// sibling = parent - built child (exact int64)
+__global__ void __launch_bounds__(256) subtract_kernel(GrowState gs, GH64* pool, int ngroups) {
+  const int r = blockIdx.x;
+  if (r >= *gs.build_count) return;
+  const int bld = gs.build_nid[r], sub = gs.build_sub_nid[r];
+  const size_t stride = (size_t)ngroups * kGroupEntries;
+  const GH64* hb = pool + (size_t)gs.hist_slot[bld] * stride;
+  const GH64* hp = pool + (size_t)gs.build_parent_slot[r] * stride;
+  GH64* hs = pool + (size_t)gs.hist_slot[sub] * stride;
+  for (size_t e = (size_t)blockIdx.y * blockDim.x + threadIdx.x; e < stride; e += (size_t)gridDim.y * blockDim.x) {
+    GH64 p = hp[e], b = hb[e]; GH64 o; o.g = p.g - b.g; o.h = p.h - b.h; hs[e] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s) {
+  init_tree_kernel<<<1, 32, 0, s>>>(gs, t, n, root_slot, max_level_nodes); CUDA_OK(cudaGetLastError());
+}
+void launch_scales(const GrowState& gs, cudaStream_t s) { scales_kernel<<<1, 32, 0, s>>>(gs); CUDA_OK(cudaGetLastError()); }
+void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s) {
+  dim3 grid(max_nodes_level, a.ngroups); eval_kernel<<<grid, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+}
+void launch_apply(const ApplyArgs& a, cudaStream_t s) { apply_kernel<<<1, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError()); }
+void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s) {
+  part_count_kernel<<<max_tiles, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  if (a.final_level) return;
+  part_scan_kernel<<<max_nodes_level, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  part_scatter_kernel<<<max_tiles, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  build_prefix_kernel<<<1, 256, 0, s>>>(a.gs); CUDA_OK(cudaGetLastError());
+}
+void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s) {
+  dim3 grid(max_build, 8 * ngroups); subtract_kernel<<<grid, 256, 0, s>>>(gs, pool, ngroups); CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace b200

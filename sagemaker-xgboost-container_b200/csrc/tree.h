@@ -1,0 +1,54 @@
+// tree.h -- kernel argument blocks and launchers of the tree builder (see tree.cu, hist.cu, misc.cu).
+#pragma once
+#include "engine.h"
+
+namespace b200 {
+
+constexpr unsigned kPartTile = 2048;       // rows per partition tile (256 threads x 8 consecutive rows)
+
+struct TrainParamDev {
+  float eta, lambda, alpha, gamma, min_child_weight, max_delta_step;
+  int max_depth, max_leaves;
+};
+
+struct EvalArgs {
+  const GH64* hist_pool; GrowState gs; const int* cut_ptrs; const unsigned char* feat_mask;
+  TrainParamDev p; int F, ngroups, fpg, has_missing, level, max_level_nodes;
+};
+
+struct ApplyArgs {
+  GrowState gs; TreeArrays tree; const int* cut_ptrs; const float* cut_vals; const float* min_vals;
+  TrainParamDev p; unsigned* scratch; int ngroups, level, max_level_nodes, next_base, next_half;
+};
+
+struct PartArgs {
+  GrowState gs; TreeArrays tree; const uint8_t* bins; int64_t n; const unsigned* ridx_cur; unsigned* ridx_next;
+  float* margin; int K, k, fpg, has_missing, level, max_level_nodes, final_level;
+};
+
+struct HistArgs {
+  const uint8_t* bins;          // [ngroups][n][32]
+  int64_t n;
+  const float2* gpair;          // (g, h) per row of the class being grown
+  const unsigned* ridx;         // row ids by segment position; nullptr = identity (root)
+  const int* build_count;       // number of nodes to build
+  const int* build_nid;         // their node ids
+  const unsigned* build_prefix; // exclusive prefix of their row counts, [count] = total
+  const unsigned* seg_begin;    // per nid
+  const int* hist_slot;         // per nid
+  const float* scales;          // sg, sh
+  GH64* hist_pool;              // slot stride = ngroups * kGroupEntries
+  GH64* node_sum;               // per nid, accumulated only when accumulate_sum
+  int ngroups;
+  int accumulate_sum;
+};
+
+void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream);
+void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s);
+void launch_scales(const GrowState& gs, cudaStream_t s);
+void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s);
+void launch_apply(const ApplyArgs& a, cudaStream_t s);
+void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s);
+void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s);
+
+}  // namespace b200

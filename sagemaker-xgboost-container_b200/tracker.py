@@ -1,0 +1,165 @@
+"""`xgboost.tracker.RabitTracker` replacement (distributed.py:183-190,247-257) plus the worker-side client.
+
+The tracker is a tiny TCP hub: workers connect, announce their task id, receive (rank, world) -- ranks follow the
+sorted task ids when sortby="task", as the container requests -- and later relay host-side object broadcasts
+(the container's RabitHelper.synchronize) through it.  Bulk numeric traffic never goes here: histograms travel
+over NCCL inside the engine.
+"""
+import pickle
+import socket
+import struct
+import threading
+import time
+
+
+def _send(sock, obj):
+    data = pickle.dumps(obj)
+    sock.sendall(struct.pack("!Q", len(data)) + data)
+
+
+def _recv(sock):
+    hdr = b""
+    while len(hdr) < 8:
+        chunk = sock.recv(8 - len(hdr))
+        if not chunk:
+            raise ConnectionError("tracker connection closed")
+        hdr += chunk
+    (n,) = struct.unpack("!Q", hdr)
+    buf = bytearray()
+    while len(buf) < n:
+        chunk = sock.recv(min(1 << 20, n - len(buf)))
+        if not chunk:
+            raise ConnectionError("tracker connection closed")
+        buf += chunk
+    return pickle.loads(bytes(buf))
+
+
+class RabitTracker:
+    def __init__(self, n_workers, host_ip="127.0.0.1", port=0, sortby="host", timeout=0):
+        self.n_workers = int(n_workers)
+        self.host_ip = host_ip
+        self.sortby = sortby
+        self.timeout = timeout
+        self._sock = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        self._sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        self._sock.bind(("" if host_ip in ("0.0.0.0", "") else host_ip, int(port)))
+        self.port = self._sock.getsockname()[1]
+        self._sock.listen(max(16, self.n_workers * 2))
+        self._thread = None
+        self._done = threading.Event()
+        self._error = None
+
+    def worker_args(self):
+        return {"dmlc_tracker_uri": self.host_ip, "dmlc_tracker_port": self.port}
+
+    def start(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        try:
+            conns = []
+            while len(conns) < self.n_workers:
+                c, addr = self._sock.accept()
+                c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                hello = _recv(c)
+                conns.append((str(hello.get("task_id", "")), addr[0], len(conns), c))
+            if self.sortby == "task":
+                conns.sort(key=lambda t: (t[0], t[2]))
+            else:
+                conns.sort(key=lambda t: (t[1], t[2]))
+            socks = [c for *_, c in conns]
+            for rank, s in enumerate(socks):
+                _send(s, {"rank": rank, "world": self.n_workers})
+            alive = set(range(self.n_workers))
+            while alive:
+                msgs = {}
+                for r in sorted(alive):
+                    try:
+                        msgs[r] = _recv(socks[r])
+                    except (ConnectionError, OSError):
+                        msgs[r] = {"op": "bye"}
+                ops = {m["op"] for m in msgs.values()}
+                if ops == {"bye"} or "bye" in ops:
+                    for r in list(alive):
+                        if msgs[r]["op"] == "bye":
+                            alive.discard(r)
+                            try:
+                                socks[r].close()
+                            except OSError:
+                                pass
+                    if not alive:
+                        break
+                    continue
+                if ops == {"bcast"}:
+                    root = next(iter(msgs.values()))["root"]
+                    payload = msgs[root]["data"]
+                    for r in alive:
+                        _send(socks[r], {"data": payload})
+                elif ops == {"barrier"}:
+                    for r in alive:
+                        _send(socks[r], {"ok": True})
+                else:
+                    raise RuntimeError("tracker: mismatched collective ops %s" % ops)
+        except Exception as e:  # surfaced by wait_for
+            self._error = e
+        finally:
+            self._done.set()
+
+    def wait_for(self, timeout=None):
+        ok = self._done.wait(timeout if timeout and timeout > 0 else None)
+        if self._error is not None:
+            raise RuntimeError("tracker failed: %s" % self._error)
+        if not ok:
+            raise TimeoutError("tracker timed out")
+
+    def join(self):
+        self.wait_for()
+
+    def free(self):
+        try:
+            self._sock.close()
+        except OSError:
+            pass
+
+
+class TrackerClient:
+    def __init__(self, uri, port, task_id, timeout=300.0):
+        self.uri, self.port, self.task_id, self.timeout = uri, int(port), task_id, timeout
+        self.sock = None
+        self.rank, self.world = 0, 1
+
+    def connect(self):
+        deadline = time.time() + max(self.timeout, 1.0)
+        last = None
+        while True:
+            try:
+                self.sock = socket.create_connection((self.uri, self.port), timeout=10.0)
+                break
+            except OSError as e:
+                last = e
+                if time.time() > deadline:
+                    raise ConnectionError("cannot reach the tracker at %s:%d: %s" % (self.uri, self.port, last))
+                time.sleep(0.2)
+        self.sock.settimeout(None)
+        self.sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+        _send(self.sock, {"task_id": self.task_id})
+        info = _recv(self.sock)
+        self.rank, self.world = info["rank"], info["world"]
+
+    def broadcast(self, data, root):
+        _send(self.sock, {"op": "bcast", "root": root, "data": data if self.rank == root else None})
+        return _recv(self.sock)["data"]
+
+    def barrier(self):
+        _send(self.sock, {"op": "barrier"})
+        _recv(self.sock)
+
+    def close(self):
+        if self.sock is not None:
+            try:
+                _send(self.sock, {"op": "bye"})
+                self.sock.close()
+            except OSError:
+                pass
+            self.sock = None

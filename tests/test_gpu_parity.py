@@ -1,0 +1,194 @@
+"""GPU parity tests (run with `pytest -m gpu` on a B200): the CUDA path through the C-ABI against the CPU oracle.
+
+Bar (BASELINE.json north_star): integer work bit-exact (bins, fixed-point histograms, leaf indices, tree structure);
+leaf weights within 1e-5 of the CPU reference.
+"""
+import numpy as np
+import pytest
+
+from util import assert_same_structure, first_structural_difference, max_leaf_diff, synth
+
+pytestmark = pytest.mark.gpu
+
+LEAF_TOL = 1e-5       # absolute, stated by BASELINE.json north_star
+MARGIN_TOL = 2e-5
+
+
+def _be():
+    from sagemaker_xgboost_container_b200.backend import get_backend
+    return get_backend()
+
+
+@pytest.mark.parametrize("n,F,max_bin,quantised", [(5000, 7, 256, True), (20000, 28, 256, True), (3000, 5, 64, False), (4000, 40, 256, False)])
+def test_cuts_and_bins_match_oracle(xgb, oracle, n, F, max_bin, quantised):
+    X, y = synth(n, F, 11, "reg", quantised=quantised)
+    d = xgb.DMatrix(X, label=y)
+    ptrs, vals, mins, hm = _be().dmatrix_get_cuts(d.handle, max_bin)
+    optrs, ovals, omins, ohm = oracle.make_cuts(X, max_bin)
+    np.testing.assert_array_equal(ptrs, optrs)
+    np.testing.assert_array_equal(vals, ovals)
+    np.testing.assert_array_equal(mins, omins)
+    assert hm == ohm
+    bins = _be().dmatrix_get_bins(d.handle, max_bin)
+    np.testing.assert_array_equal(bins, oracle.bin_matrix(X, optrs, ovals))      # bit-exact integer work
+
+
+def test_bins_with_missing_values(xgb, oracle):
+    X, y = synth(6000, 9, 12, "reg", quantised=False, missing_frac=0.1)
+    d = xgb.DMatrix(X, label=y)
+    ptrs, vals, mins, hm = _be().dmatrix_get_cuts(d.handle, 256)
+    optrs, ovals, omins, ohm = oracle.make_cuts(X, 256)
+    assert hm and ohm
+    np.testing.assert_array_equal(ptrs, optrs)
+    np.testing.assert_array_equal(vals, ovals)
+    np.testing.assert_array_equal(_be().dmatrix_get_bins(d.handle, 256), oracle.bin_matrix(X, optrs, ovals))
+
+
+@pytest.mark.parametrize("n,F", [(1, 3), (17, 5), (4096, 28), (4097, 33), (100003, 50), (300000, 100)])
+def test_root_histogram_bit_exact(xgb, oracle, n, F):
+    """Histogram kernel vs the fixed-point mirror in the oracle: exact int64 equality for ragged sizes."""
+    X, y = synth(n, F, 21, "reg")
+    rng = np.random.default_rng(5)
+    gpair = np.stack([rng.standard_normal(n).astype(np.float32) * 3, rng.random(n).astype(np.float32) + 0.01], axis=1)
+    d = xgb.DMatrix(X, label=y)
+    b = xgb.Booster({"max_bin": 256}, [d])
+    hist, scales, ms = _be().build_root_histogram(b.handle, d.handle, gpair, repeats=1)
+    gq = np.rint(gpair[:, 0] * scales[0]).astype(np.int32)
+    hq = np.rint(gpair[:, 1] * scales[1]).astype(np.int32)
+    bins = _be().dmatrix_get_bins(d.handle, 256)
+    ref = oracle.build_hist_fixed(bins, gq, hq)
+    np.testing.assert_array_equal(hist, ref)
+    # and close to the reference-faithful double histogram (same bins, float gradients)
+    optrs, ovals, _, _ = oracle.make_cuts(X, 256)
+    dref = oracle.build_hist(bins, optrs, gpair)
+    for f in range(F):
+        nb = optrs[f + 1] - optrs[f]
+        got = hist[f, :nb, 0] / scales[0]
+        np.testing.assert_allclose(got, dref[optrs[f]:optrs[f + 1], 0], rtol=0, atol=2e-5 * max(1.0, np.abs(gpair[:, 0]).max()) * np.sqrt(n))
+
+
+CASES = [
+    ("reg:squarederror", "reg", 1, dict(max_depth=6, eta=0.3), 20000, 28, 12),
+    ("reg:squarederror", "reg", 1, dict(max_depth=5, eta=0.2, gamma=4, min_child_weight=6), 3000, 8, 20),
+    ("binary:logistic", "bin", 1, dict(max_depth=6, eta=0.3), 30000, 28, 12),
+    ("binary:logistic", "bin", 1, dict(max_depth=4, eta=0.1, alpha=0.5, scale_pos_weight=2.0), 10000, 40, 10),
+    ("multi:softprob", "multi", 4, dict(max_depth=4, eta=0.3), 12000, 20, 5),
+    ("reg:squarederror", "reg", 1, dict(max_depth=3, eta=0.5, max_delta_step=0.7), 5000, 100, 6),
+]
+
+
+@pytest.mark.parametrize("objective,kind,K,hp,n,F,rounds", CASES)
+def test_training_matches_oracle(xgb, oracle, objective, kind, K, hp, n, F, rounds):
+    X, y = synth(n, F, 31, kind, K=max(K, 1))
+    params = dict(objective=objective, tree_method="hist", max_bin=256, **hp)
+    if K > 1:
+        params["num_class"] = K
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=rounds, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    ref = oracle.train(params, X, y, rounds)
+    mr = ref.model()
+    assert abs(m["base_score"] - mr["base_score"]) <= 1e-6 * max(1.0, abs(mr["base_score"]))
+    assert first_structural_difference(m, mr) is None, "tree structure differs first at tree %s" % first_structural_difference(m, mr)
+    assert_same_structure(m, mr)
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    # prediction cache kept by the trainer == oracle margins
+    cache = _be().booster_cached_margin(bst.handle, d.handle, max(K, 1))
+    np.testing.assert_allclose(cache, ref.margins(), rtol=0, atol=MARGIN_TOL)
+    # predict(): leaf indices are integer work -> bit-exact against the oracle walking ITS model
+    leaves = bst.predict(d, pred_leaf=True)
+    np.testing.assert_array_equal(leaves.astype(np.int32), oracle.predict_leaf(mr, X))
+    margin = bst.predict(d, output_margin=True).reshape(n, -1)
+    np.testing.assert_allclose(margin, oracle.predict_margin(mr, X), rtol=0, atol=MARGIN_TOL)
+
+
+def test_training_with_missing_values(xgb, oracle):
+    X, y = synth(15000, 12, 41, "reg", quantised=False, missing_frac=0.15)
+    params = dict(objective="reg:squarederror", max_depth=5, eta=0.3, max_bin=64)
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=8, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, 8).model()
+    assert_same_structure(m, mr)
+    assert m["default_left"].sum() > 0          # the backward scan was exercised
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    np.testing.assert_array_equal(bst.predict(d, pred_leaf=True).astype(np.int32), oracle.predict_leaf(mr, X))
+
+
+def test_fixture_model_predict_leaf_bit_exact(xgb, oracle):
+    """The reference's own UBJSON fixture through the C++ loader + GPU predictor vs the oracle walking the same file."""
+    import os
+    from oracle import ubjson
+    path = os.path.join(os.path.dirname(__file__), "golden", "abalone_xgboost-model.ubj")
+    bst = xgb.Booster(model_file=path)
+    mr = ubjson.model_from_xgb_json(ubjson.load(path))
+    rng = np.random.default_rng(3)
+    X = rng.random((2000, 8)).astype(np.float32) * np.array([3, 1, 1, 0.3, 3, 1.5, 0.8, 1], np.float32)
+    X[0] = [2, 0.645, 0.515, 0.15, 1.212, 0.515, 0.2055, 0.385]      # LIBSVM_SAMPLE of test/integration/local/test_abalone.py:24
+    d = xgb.DMatrix(X)
+    leaves = bst.predict(d, pred_leaf=True).astype(np.int32)
+    np.testing.assert_array_equal(leaves, oracle.predict_leaf(mr, X))
+    np.testing.assert_array_equal(leaves[0, :8], [42, 45, 40, 43, 34, 38, 38, 41])          # SURVEY.md 8(c) self-consistency vector
+    pred = bst.predict(d)
+    np.testing.assert_allclose(pred, oracle.predict_margin(mr, X)[:, 0], rtol=0, atol=1e-5)
+    assert abs(float(pred[0]) - 11.100031) < 1e-4
+
+
+def test_model_roundtrip_ubj_json_pickle(xgb, oracle, tmp_path):
+    import pickle
+    from oracle import ubjson
+    X, y = synth(4000, 10, 51, "bin")
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(dict(objective="binary:logistic", max_depth=4), d, num_boost_round=5, verbose_eval=False)
+    p0 = bst.predict(d)
+    f_ubj, f_json = str(tmp_path / "xgboost-model"), str(tmp_path / "m.json")
+    bst.save_model(f_ubj)
+    bst.save_model(f_json)
+    for f in (f_ubj, f_json):
+        b2 = xgb.Booster(model_file=f)
+        np.testing.assert_array_equal(b2.predict(d), p0)
+    b3 = pickle.loads(pickle.dumps(bst))
+    np.testing.assert_array_equal(b3.predict(d), p0)
+    # the independent Python reader understands the C++ writer's UBJSON
+    doc = ubjson.load(f_ubj)
+    mo = ubjson.model_from_xgb_json(doc)
+    assert mo["objective"] == "binary:logistic" and len(mo["tree_info"]) == 5
+    np.testing.assert_allclose(oracle.transform(mo, oracle.predict_margin(mo, X))[:, 0], p0, rtol=0, atol=1e-6)
+    cfg = __import__("json").loads(bst.save_config())
+    assert cfg["learner"]["objective"]["name"] == "binary:logistic"
+
+
+def test_continue_training_from_checkpoint(xgb, oracle, tmp_path):
+    X, y = synth(6000, 9, 61, "reg")
+    params = dict(objective="reg:squarederror", max_depth=4, eta=0.3)
+    d = xgb.DMatrix(X, label=y)
+    full = xgb.train(params, d, num_boost_round=8, verbose_eval=False)
+    part = xgb.train(params, d, num_boost_round=5, verbose_eval=False)
+    ck = str(tmp_path / "xgboost-checkpoint.4")
+    part.save_model(ck)
+    resumed = xgb.train(params, d, num_boost_round=3, xgb_model=ck, verbose_eval=False)
+    assert resumed.num_boosted_rounds() == 8
+    np.testing.assert_allclose(resumed.predict(d), full.predict(d), rtol=0, atol=1e-5)
+
+
+def test_eval_metrics_match_numpy(xgb):
+    X, y = synth(5000, 6, 71, "bin")
+    d = xgb.DMatrix(X, label=y)
+    res = {}
+    bst = xgb.train(dict(objective="binary:logistic", max_depth=3, eval_metric=["logloss", "error", "rmse"]), d, num_boost_round=3,
+                    evals=[(d, "train")], evals_result=res, verbose_eval=False)
+    p = bst.predict(d).astype(np.float64)
+    ll = -np.mean(y * np.log(p) + (1 - y) * np.log(1 - p))
+    assert abs(res["train"]["logloss"][-1] - ll) < 1e-6
+    assert abs(res["train"]["error"][-1] - np.mean((p > 0.5) != (y > 0.5))) < 1e-9
+    assert abs(res["train"]["rmse"][-1] - np.sqrt(np.mean((p - y) ** 2))) < 1e-6
+
+
+def test_label_errors_surface_as_xgboost_error(xgb):
+    X, y = synth(200, 4, 81, "reg")
+    d = xgb.DMatrix(X, label=y * 10)
+    with pytest.raises(xgb.XGBoostError, match=r"label must be in \[0,1\] for logistic regression"):
+        xgb.train(dict(objective="binary:logistic"), d, num_boost_round=1, verbose_eval=False)
+    d2 = xgb.DMatrix(X, label=np.full(200, 7, np.float32))
+    with pytest.raises(xgb.XGBoostError, match=r"label must be in \[0, num_class\)"):
+        xgb.train(dict(objective="multi:softprob", num_class=3), d2, num_boost_round=1, verbose_eval=False)
