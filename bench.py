@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the hist boosting hot path.  Contract: see the task statement ("Measurement").
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # CUDA path (default arm)
+    python bench.py --impl reference --steps 3 --warmup 1          # the reference's CPU hist path (oracle port)
+    torchrun ... bench.py --gpus N ...                             # rows sharded over N GPUs, NCCL hist all-reduce
+
+metric  : boosting rounds/sec (BASELINE.json) on synthetic 50M x 100 reg:squarederror, 256 bins, max_depth 6.
+step    : one boosting round (one tree) over the whole matrix.
+value   : K / device time of K rounds, inputs resident in HBM (CUDA events on the engine stream, max over ranks).
+e2e     : the same through the public Python API with HOST buffers: DMatrix(numpy) [H2D + quantile cuts + binning],
+          then per round Booster.update + Booster.eval_set (D2H of the metric), reported for a 200-round job:
+          200 / (ingest + 200 * step).
+roofline: histogram-build kernel, root launch (all rows): algorithmic bytes rows*(F+8) / mean launch time measured with
+          CUDA events inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+JOB_ROUNDS = 200          # rounds of the end-to-end job the ingest cost is amortised over (BASELINE config 2 uses 200)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=50_000_000)
+    ap.add_argument("--cols", type=int, default=100)
+    ap.add_argument("--objective", default="reg:squarederror")
+    ap.add_argument("--num-class", type=int, default=0)
+    ap.add_argument("--max-depth", type=int, default=6)
+    ap.add_argument("--max-bin", type=int, default=256)
+    ap.add_argument("--seed", type=int, default=43)
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def params_of(a):
+    p = {"objective": a.objective, "tree_method": "hist", "max_depth": a.max_depth, "max_bin": a.max_bin, "eta": 0.3, "lambda": 1.0,
+         "gamma": 0.0, "min_child_weight": 1.0}
+    if a.num_class > 1:
+        p["num_class"] = a.num_class
+    return p
+
+
+BLOCK = 1_000_000
+
+
+def gen_block_torch(block_id, rows, F, seed, objective, K, device):
+    """SURVEY.md 8(d) recipe: x = N(0,1) quantised to 256 levels; y = x.beta + 0.1 eps (regression), per 1M-row block."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 100003 + block_id)
+    x = torch.randn(rows, F, generator=g, device=device, dtype=torch.float32)
+    x = torch.round(torch.clamp(x, -4.0, 4.0 - 1.0 / 32) * 32) / 32
+    gb = torch.Generator(device=device)
+    gb.manual_seed(seed)
+    if objective.startswith("multi"):
+        beta = torch.randn(F, K, generator=gb, device=device) / (F ** 0.5)
+        y = torch.argmax(x @ beta + torch.randn(rows, K, generator=g, device=device), dim=1).float()
+    else:
+        beta = torch.randn(F, generator=gb, device=device) / (F ** 0.5)
+        if objective.startswith("binary") or objective == "reg:logistic":
+            z = x @ beta + 0.5 * torch.randn(rows, generator=g, device=device)
+            y = (torch.sigmoid(z) > torch.rand(rows, generator=g, device=device)).float()
+        else:
+            y = x @ beta + 0.1 * torch.randn(rows, generator=g, device=device)
+    return x, y
+
+
+def gen_shard(a, r0, r1, device):
+    import torch
+    F = a.cols
+    X = torch.empty((r1 - r0, F), device=device, dtype=torch.float32)
+    y = torch.empty((r1 - r0,), device=device, dtype=torch.float32)
+    b = r0 // BLOCK
+    pos = r0
+    while pos < r1:
+        bs, be = b * BLOCK, min((b + 1) * BLOCK, a.rows)
+        xb, yb = gen_block_torch(b, be - bs, F, a.seed, a.objective, max(a.num_class, 1), device)
+        lo, hi = max(pos, bs), min(r1, be)
+        X[lo - r0:hi - r0] = xb[lo - bs:hi - bs]
+        y[lo - r0:hi - r0] = yb[lo - bs:hi - bs]
+        pos = hi
+        b += 1
+    return X, y
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled with NVML every ~5 ms during the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception as e:       # pragma: no cover
+            self.err = str(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, reasons))
+            except Exception as e:   # pragma: no cover
+                self.err = str(e)
+                return
+            time.sleep(0.005)
+
+    def stop(self):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+        seen = set()
+        for _, r in self.samples:
+            for k, bit in names.items():
+                if r & bit:
+                    seen.add(k)
+        sm = [x for x, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(mx), "samples": len(sm), "reasons": sorted(seen)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_rounds_per_sec(a, Xs, ys, steps, warmup):
+    """Time the CPU restatement of the reference's hist path on a bounded sample (all host threads)."""
+    from oracle import gbt_oracle as O
+    t0 = time.time()
+    cuts = O.make_cuts(Xs, a.max_bin)
+    bins = O.bin_matrix(Xs, cuts[0], cuts[1])
+    ingest = time.time() - t0
+    tr = O.Trainer(params_of(a), bins=bins, cuts=cuts, y=ys)
+    for _ in range(warmup):
+        tr.update()
+    t0 = time.time()
+    for _ in range(steps):
+        tr.update()
+    dt = time.time() - t0
+    return steps / dt, ingest, O.num_threads()
+
+
+def run_reference(a):
+    """--impl reference: the reference's own CPU hist implementation.  xgboost==3.0.5 is not installable in this image
+    (no network, no wheel), so this arm times the oracle port of that path on the host cores, on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rng = np.random.default_rng(a.seed)
+    S = min(a.rows, a.cpu_sample_rows)
+    X = rng.standard_normal((S, a.cols), dtype=np.float32)
+    X = (np.round(np.clip(X, -4, 4 - 1 / 32) * 32) / 32).astype(np.float32)
+    beta = (rng.standard_normal(a.cols) / np.sqrt(a.cols)).astype(np.float32)
+    if a.objective.startswith("binary"):
+        y = (1 / (1 + np.exp(-(X @ beta + 0.5 * rng.standard_normal(S).astype(np.float32)))) > rng.random(S)).astype(np.float32)
+    elif a.objective.startswith("multi"):
+        bk = (rng.standard_normal((a.cols, a.num_class)) / np.sqrt(a.cols)).astype(np.float32)
+        y = np.argmax(X @ bk + rng.standard_normal((S, a.num_class)).astype(np.float32), axis=1).astype(np.float32)
+    else:
+        y = (X @ beta + 0.1 * rng.standard_normal(S).astype(np.float32)).astype(np.float32)
+    rps_sample, ingest_s, cores = oracle_rounds_per_sec(a, X, y, a.steps, a.warmup)
+    scale = S / a.rows
+    value = rps_sample * scale
+    sample = "%d of %d rows (oracle port of the xgboost CPU hist path, OpenMP), rounds/s scaled by %d/%d" % (S, a.rows, S, a.rows)
+    ingest_full = ingest_s / scale
+    e2e = JOB_ROUNDS / (ingest_full + JOB_ROUNDS / value)
+    print(json.dumps({
+        "impl": "reference", "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 histograms over f32 gradients", "data": "synthetic",
+        "config": {"workload": "synthetic %dx%d %s hist max_bin=%d max_depth=%d" % (a.rows, a.cols, a.objective, a.max_bin, a.max_depth)},
+        "cpu_baseline": {"value": value, "unit": "rounds/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": e2e, "unit": "rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    import sagemaker_xgboost_container_b200 as xgb
+    from sagemaker_xgboost_container_b200 import collective
+    be = xgb.get_backend()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        collective.init_from_env(backend="gloo")
+
+    def barrier():
+        torch.cuda.synchronize()
+        be.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    r0, r1 = rank * a.rows // world, (rank + 1) * a.rows // world
+    X, y = gen_shard(a, r0, r1, device)
+    y_host = y.cpu().numpy()
+    dtrain = xgb.DMatrix(X, label=y_host)
+    params = params_of(a)
+    bst = xgb.Booster(params, [dtrain])
+    it = 0
+    for _ in range(a.warmup):
+        bst.update(dtrain, it); it += 1
+    barrier()
+    be.booster_set_profile(bst.handle, True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = be.launch_count()
+    barrier()
+    be.timer_start()
+    for _ in range(a.steps):
+        bst.update(dtrain, it); it += 1
+    ms = be.timer_stop()
+    barrier()
+    launches = be.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    prof = be.booster_get_profile(bst.handle)
+    be.booster_set_profile(bst.handle, False)
+    ms = max_over_ranks(ms)
+    value = a.steps / (ms / 1000.0)
+
+    # ---- roofline of the histogram kernel (root launch = one full pass over this rank's rows)
+    peak, peak_src = hbm_peak()
+    F = a.cols
+    root_ms = prof["root_hist_ms"] / max(1, prof["root_hist_launches"])
+    root_rows = prof["root_hist_rows"] / max(1, prof["root_hist_launches"])
+    root_bytes = root_rows * (F + 8)
+    achieved = root_bytes / (root_ms * 1e-3) / 1e9 if root_ms > 0 else 0.0
+    deep_bytes = prof["deep_hist_rows"] * (F + 8 + 4)          # deeper levels also read a 4 B row id per row
+    all_gbs = (prof["root_hist_rows"] * (F + 8) + deep_bytes) / ((prof["root_hist_ms"] + prof["deep_hist_ms"]) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "hist_build_kernel (root launch, all rows of the rank)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": root_bytes, "ms_per_launch": root_ms,
+                "all_hist_launches_gbs": all_gbs, "all_hist_launches_frac": all_gbs / peak,
+                "hist_share_of_step": (prof["root_hist_ms"] + prof["deep_hist_ms"]) / ms}
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not a.no_e2e:
+        del dtrain, bst
+        Xh = torch.empty(X.shape, dtype=torch.float32, pin_memory=True)
+        Xh.copy_(X)
+        del X
+        torch.cuda.empty_cache()
+        Xn = Xh.numpy()
+        barrier()
+        t0 = time.perf_counter()
+        d2 = xgb.DMatrix(Xn, label=y_host)                       # H2D of the feature matrix happens here
+        b2 = xgb.Booster(params, [d2])
+        b2.update(d2, 0)                                         # first round: cuts + binning + round 0
+        msg = b2.eval_set([(d2, "train")], 0)
+        be.synchronize()
+        t_first = time.perf_counter() - t0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(1, a.steps + 1):
+            b2.update(d2, i)
+            msg = b2.eval_set([(d2, "train")], i)               # D2H: the metric of the round
+        be.synchronize()
+        t_steps = (time.perf_counter() - t0) / a.steps
+        t_first = max_over_ranks(t_first); t_steps = max_over_ranks(t_steps)
+        ingest = max(0.0, t_first - t_steps)
+        e2e_value = JOB_ROUNDS / (ingest + JOB_ROUNDS * t_steps)
+        e2e = {"value": e2e_value, "unit": "rounds/s", "h2d_bytes_per_step": int(Xn.nbytes + y_host.nbytes) // JOB_ROUNDS,
+               "d2h_bytes_per_step": 16, "ingest_s": ingest, "step_s": t_steps, "job_rounds": JOB_ROUNDS, "last_eval": msg,
+               "note": "DMatrix from pinned host numpy; ingest (H2D + cuts + binning) amortised over a %d-round job" % JOB_ROUNDS}
+        del d2, b2
+
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        S = min(a.rows, a.cpu_sample_rows)
+        dev_cpu = torch.device("cpu")
+        xs, ys = gen_block_torch(0, min(S, BLOCK), a.cols, a.seed, a.objective, max(a.num_class, 1), device)
+        xs, ys = xs.cpu().numpy(), ys.cpu().numpy()
+        rps, ingest_s, cores = oracle_rounds_per_sec(a, xs, ys, 3, 1)
+        cpu = {"value": rps * len(xs) / a.rows, "unit": "rounds/s", "cores": cores, "kind": "port",
+               "sample": "first %d of %d rows, 3 timed rounds after 1 warm-up, scaled linearly in rows" % (len(xs), a.rows)}
+
+    if rank == 0:
+        out = {
+            "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int64 fixed-point histograms (int32 smem partials) over f32 gradients", "data": "synthetic",
+            "config": {"workload": "synthetic %dx%d %s hist max_bin=%d max_depth=%d" % (a.rows, a.cols, a.objective, a.max_bin, a.max_depth),
+                       "rows_per_gpu": (a.rows + world - 1) // world, "parallelism": "rows sharded x%d, per-level int64 histogram NCCL all-reduce" % world,
+                       "l2": "inputs (%.1f GB of bins per GPU) exceed the 126 MB L2" % ((r1 - r0) * 32 * ((a.cols + 31) // 32) / 1e9),
+                       "params": params},
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        collective.finalize()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

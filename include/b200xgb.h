@@ -47,6 +47,10 @@ XGB_DLL int XGDMatrixCreateFromMat(const float* data, bst_ulong nrow, bst_ulong 
 /* CSR; num_col = 0 means "infer from the indices" (libsvm loader: indices kept as-is, data_utils.py:348-365) */
 XGB_DLL int XGDMatrixCreateFromCSREx(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr,
                              size_t nelem, size_t num_col, DMatrixHandle* out);
+/* device-resident input (what the reference's GPU path feeds through cupy/cudf, distributed_gpu/dask_data_utils.py:71-78):
+ * `data` is a JSON __cuda_array_interface__ {"data":[ptr,ro],"shape":[n,F],"typestr":"<f4"[,"strides":null]},
+ * config JSON {"missing": NaN} */
+XGB_DLL int XGDMatrixCreateFromCudaArrayInterface(const char* data, const char* config, DMatrixHandle* out);
 XGB_DLL int XGDMatrixFree(DMatrixHandle handle);
 XGB_DLL int XGDMatrixNumRow(DMatrixHandle handle, bst_ulong* out);                                   /* train.py:339-342 */
 XGB_DLL int XGDMatrixNumCol(DMatrixHandle handle, bst_ulong* out);
@@ -121,6 +125,15 @@ XGB_DLL int XGB200BuildRootHistogram(BoosterHandle handle, DMatrixHandle dmat, c
                              int64_t* out_hist, float* scales, float* out_ms);
 /* raw margins of the prediction cache the trainer keeps for `dmat` (n x num_class), brought up to date first */
 XGB_DLL int XGB200BoosterGetCachedMargin(BoosterHandle handle, DMatrixHandle dmat, float* out);
+/* CUDA-event stopwatch on the engine's stream: Start records an event, Stop records another, waits, returns ms */
+XGB_DLL int XGB200TimerStart(void);
+XGB_DLL int XGB200TimerStop(float* out_ms);
+/* per-kernel profile of the tree builder: enable, run rounds, then read
+ * {"hist_ms":..,"hist_launches":..,"hist_rows":..,"root_hist_ms":..,"root_hist_launches":..,"root_hist_rows":..,"launches":..} */
+XGB_DLL int XGB200BoosterSetProfile(BoosterHandle handle, int enable);
+XGB_DLL int XGB200BoosterGetProfile(BoosterHandle handle, const char** out_json);
+/* number of CUDA kernels this library has launched so far in this process */
+XGB_DLL int XGB200LaunchCount(long long* out);
 /* wait for all device work queued by this library */
 XGB_DLL int XGB200Synchronize(void);
 

@@ -76,6 +76,23 @@ class CudaBackend:
                                                       C.c_size_t(len(data)), C.c_size_t(ncol), C.byref(h)))
         return h
 
+    def dmatrix_from_cuda_array(self, obj, missing):
+        """obj exposes __cuda_array_interface__ (torch.Tensor on cuda, cupy.ndarray): float32, 2-D, C-contiguous."""
+        iface = dict(obj.__cuda_array_interface__)
+        iface["shape"] = list(iface["shape"])
+        iface["data"] = [int(iface["data"][0]), bool(iface["data"][1])]
+        iface.pop("stream", None)
+        iface["strides"] = None if iface.get("strides") is None else list(iface["strides"])
+        if iface["strides"] is not None:
+            n, F = iface["shape"]
+            if list(iface["strides"]) != [4 * F, 4]:
+                raise ValueError("device array must be C-contiguous")
+            iface["strides"] = None
+        h = C.c_void_p()
+        cfg = {} if missing is None or missing != missing else {"missing": float(missing)}
+        self._check(self.lib.XGDMatrixCreateFromCudaArrayInterface(_cstr(json.dumps(iface)), _cstr(json.dumps(cfg)), C.byref(h)))
+        return h
+
     def dmatrix_free(self, h):
         self._check(self.lib.XGDMatrixFree(h))
 
@@ -300,6 +317,27 @@ class CudaBackend:
         out = np.zeros((n, K), np.float32)
         self._check(self.lib.XGB200BoosterGetCachedMargin(bh, dh, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+    def timer_start(self):
+        self._check(self.lib.XGB200TimerStart())
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self.lib.XGB200TimerStop(C.byref(ms)))
+        return float(ms.value)
+
+    def booster_set_profile(self, bh, enable):
+        self._check(self.lib.XGB200BoosterSetProfile(bh, C.c_int(1 if enable else 0)))
+
+    def booster_get_profile(self, bh):
+        out = C.c_char_p()
+        self._check(self.lib.XGB200BoosterGetProfile(bh, C.byref(out)))
+        return json.loads(out.value.decode())
+
+    def launch_count(self):
+        out = C.c_longlong()
+        self._check(self.lib.XGB200LaunchCount(C.byref(out)))
+        return int(out.value)
 
     def synchronize(self):
         self._check(self.lib.XGB200Synchronize())

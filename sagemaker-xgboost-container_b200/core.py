@@ -51,6 +51,8 @@ class DMatrix:
                 label = y
             if weight is None and w is not None:
                 weight = w
+        elif hasattr(data, "__cuda_array_interface__"):
+            self.handle = be.dmatrix_from_cuda_array(data, missing)
         elif _is_scipy_sparse(data):
             csr = data.tocsr()
             self.handle = be.dmatrix_from_csr(csr.indptr, csr.indices, csr.data, csr.shape[1])

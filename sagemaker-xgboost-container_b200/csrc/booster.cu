@@ -11,6 +11,8 @@
 
 namespace b200 {
 
+long long g_kernel_launches = 0;
+
 // ---------------------------------------------------------------------------------------------
 // process-wide device context
 // ---------------------------------------------------------------------------------------------
@@ -69,6 +71,18 @@ std::unique_ptr<DMatrix> DMatrix::from_dense(const float* data, int64_t nrow, in
   return dm;
 }
 
+std::unique_ptr<DMatrix> DMatrix::from_device(const float* dptr, int64_t nrow, int ncol, float missing) {
+  B200_CHECK(nrow >= 0 && ncol >= 0 && nrow < (int64_t)0x7fffffff, "DMatrix: bad shape");
+  auto dm = std::make_unique<DMatrix>();
+  dm->n = nrow; dm->F = ncol;
+  cudaStream_t s = engine_stream();
+  dm->X.alloc((size_t)nrow * ncol);
+  CUDA_OK(cudaDeviceSynchronize());       // the producer (e.g. a torch stream) must be done before we read its buffer
+  if (nrow * ncol > 0) CUDA_OK(cudaMemcpyAsync(dm->X.p, dptr, sizeof(float) * (size_t)nrow * ncol, cudaMemcpyDeviceToDevice, s));
+  dm->finish_upload(missing);
+  return dm;
+}
+
 std::unique_ptr<DMatrix> DMatrix::from_csr(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr,
                                            size_t nelem, size_t ncol) {
   // densify on the host with NaN for absent entries (upstream keeps CSR; the hist path needs a dense bin matrix anyway)
@@ -101,7 +115,7 @@ std::unique_ptr<DMatrix> DMatrix::slice(const int* idx, int64_t len) const {
     DevBuf<int> didx; didx.alloc(len);
     CUDA_OK(cudaMemcpyAsync(didx.p, idx, sizeof(int) * len, cudaMemcpyHostToDevice, s));
     int grid = (int)std::min<int64_t>((len * F + 255) / 256, 148 * 16);
-    gather_rows_kernel<<<grid, 256, 0, s>>>(X.p, F, didx.p, len, dm->X.p);
+    gather_rows_kernel<<<grid, 256, 0, s>>>(X.p, F, didx.p, len, dm->X.p); ++g_kernel_launches;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(s));
   }
@@ -590,7 +604,10 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups;
   ha.accumulate_sum = 1;
+  ha.rows_counter = profile_ ? prof_rows_.p : nullptr;
+  prof_begin(0);
   launch_hist_build(ha, g.hist_grid_x, s);
+  prof_end();
   if (comm.distributed()) {
     comm.allreduce_sum_i64(g.hist_pool.p, g.slot_stride * 2, s);
     comm.allreduce_sum_i64(g.gs.node_sum, 2, s);
@@ -615,7 +632,10 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     // histograms of the next level: build the smaller children, all-reduce, subtract for the siblings
     CUDA_OK(cudaMemsetAsync(g.hist_pool.p + (size_t)next_base * g.slot_stride, 0, (size_t)next_half * g.slot_stride * sizeof(GH64), s));
     ha.ridx = pa.ridx_next; ha.accumulate_sum = 0;
+    ha.rows_counter = profile_ ? prof_rows_.p + 1 : nullptr;
+    prof_begin(L + 1);
     launch_hist_build(ha, g.hist_grid_x, s);
+    prof_end();
     if (comm.distributed()) comm.allreduce_sum_i64(g.hist_pool.p + (size_t)next_base * g.slot_stride, (size_t)next_half * g.slot_stride * 2, s);
     launch_subtract(g.gs, g.hist_pool.p, bm.ngroups, next_half, s);
     ea.level = L + 1;
@@ -631,7 +651,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     CUDA_OK(cudaStreamSynchronize(s));
     std::swap(nb.p, d_nodes.p); std::swap(nb.n, d_nodes.n);
   }
-  pack_tree_kernel<<<(g.cap_nodes + 255) / 256, 256, 0, s>>>(g.ta, g.gs.n_nodes, d_nodes.p + d_nodes_used, g.cap_nodes);
+  pack_tree_kernel<<<(g.cap_nodes + 255) / 256, 256, 0, s>>>(g.ta, g.gs.n_nodes, d_nodes.p + d_nodes_used, g.cap_nodes); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
   if (pending_.size() - (size_t)std::count_if(pending_.begin(), pending_.end(), [](const PendingTree& p) { return p.staging == nullptr; }) >= 512) sync_model();
   PendingTree pt; pt.cap_nodes = (size_t)g.cap_nodes;
@@ -801,6 +821,36 @@ void Booster::cached_margin(DMatrix* dm, std::vector<float>* out) {
   out->resize((size_t)dm->n * param_.num_class);
   if (!out->empty()) CUDA_OK(cudaMemcpyAsync(out->data(), c.margin.p, sizeof(float) * out->size(), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
+}
+
+void Booster::set_profile(bool on) {
+  profile_ = on;
+  if (on) { prof_rows_.alloc(2); prof_rows_.zero(engine_stream()); prof_launches_ = 0; }
+  for (auto& e : prof_events_) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  prof_events_.clear();
+}
+void Booster::prof_begin(int level) {
+  if (!profile_) return;
+  ProfEvent e; e.level = level;
+  CUDA_OK(cudaEventCreate(&e.a)); CUDA_OK(cudaEventCreate(&e.b));
+  CUDA_OK(cudaEventRecord(e.a, engine_stream()));
+  prof_events_.push_back(e);
+}
+void Booster::prof_end() {
+  if (!profile_) return;
+  CUDA_OK(cudaEventRecord(prof_events_.back().b, engine_stream()));
+}
+std::string Booster::get_profile() {
+  cudaStream_t s = engine_stream();
+  CUDA_OK(cudaStreamSynchronize(s));
+  double root_ms = 0, deep_ms = 0; long long root_n = 0, deep_n = 0;
+  for (auto& e : prof_events_) { float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, e.a, e.b)); if (e.level == 0) { root_ms += ms; ++root_n; } else { deep_ms += ms; ++deep_n; } }
+  unsigned long long rows[2] = {0, 0};
+  if (prof_rows_.p) CUDA_OK(cudaMemcpy(rows, prof_rows_.p, sizeof rows, cudaMemcpyDeviceToHost));
+  char buf[512];
+  snprintf(buf, sizeof buf, "{\"root_hist_ms\":%.6f,\"root_hist_launches\":%lld,\"root_hist_rows\":%llu,\"deep_hist_ms\":%.6f,\"deep_hist_launches\":%lld,\"deep_hist_rows\":%llu}",
+           root_ms, root_n, rows[0], deep_ms, deep_n, rows[1]);
+  return buf;
 }
 
 }  // namespace b200

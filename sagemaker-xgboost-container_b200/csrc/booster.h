@@ -33,6 +33,7 @@ class DMatrix {
 
   DMatrix();
   static std::unique_ptr<DMatrix> from_dense(const float* data, int64_t nrow, int ncol, float missing);
+  static std::unique_ptr<DMatrix> from_device(const float* dptr, int64_t nrow, int ncol, float missing);
   static std::unique_ptr<DMatrix> from_csr(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr, size_t nelem, size_t ncol);
   std::unique_ptr<DMatrix> slice(const int* idx, int64_t len) const;
   void set_float_info(const std::string& field, const float* v, size_t len);
@@ -95,8 +96,8 @@ class Booster {
   float base_score() const { return base_score_; }
   int num_class() const { return param_.num_class; }
   const TrainParam& param() { configure(); return param_; }
-  std::map<std::string, double> timers;           // accumulated device milliseconds per phase (when profiling)
-  bool profile = false;
+  void set_profile(bool on);
+  std::string get_profile();                      // JSON, see include/b200xgb.h
   // histogram of one node for kernel-level parity tests / the roofline bench
   void debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::vector<long long>* hist_out, float* scales_out,
                              int repeats, float* ms_out);
@@ -120,6 +121,11 @@ class Booster {
   std::map<uint64_t, PredCache> caches_;
   struct GrowerImpl* grower_ = nullptr;
   bool labels_checked_ = false;
+  bool profile_ = false;
+  struct ProfEvent { cudaEvent_t a, b; int level; };
+  std::vector<ProfEvent> prof_events_;
+  DevBuf<unsigned long long> prof_rows_;       // [0] rows through root launches, [1] rows through deeper launches
+  long long prof_launches_ = 0;
 
   void configure();
   float base_margin() const;
@@ -129,6 +135,8 @@ class Booster {
   void bring_cache_up_to_date(DMatrix* dm, PredCache& c);
   void append_device_tree(int class_id, size_t device_offset, int max_nodes, PendingTree pt);
   void grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_index);
+  void prof_begin(int level);
+  void prof_end();
   JPtr model_to_json();
   void model_from_json(const JValue& doc);
   JPtr config_to_json();

@@ -1,6 +1,7 @@
 // capi.cc -- extern "C" surface of libb200xgb.so (declared in include/b200xgb.h).
 // Same conventions as libxgboost's c_api.cc: int return code, thread-local last error, handle-owned buffers.
 #include "../../include/b200xgb.h"
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -61,6 +62,20 @@ int XGDMatrixCreateFromCSREx(const size_t* indptr, const unsigned* indices, cons
   API_BEGIN();
   auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
   box->dm = DMatrix::from_csr(indptr, indices, data, nindptr, nelem, num_col);
+  *out = guard.release();
+  API_END();
+}
+int XGDMatrixCreateFromCudaArrayInterface(const char* data, const char* config, DMatrixHandle* out) {
+  API_BEGIN();
+  JPtr a = parse_json(data); JPtr cfg = parse_json(config ? config : "{}");
+  const JValue& shape = a->at("shape");
+  if (shape.length() != 2) throw Error("cuda array interface: expecting a 2-dimensional array");
+  if (a->at("typestr").s != "<f4") throw Error("cuda array interface: only float32 (<f4) is supported, got " + a->at("typestr").s);
+  if (a->has("strides") && a->at("strides").type != JValue::kNull) throw Error("cuda array interface: only C-contiguous arrays are supported");
+  const float* ptr = reinterpret_cast<const float*>((uintptr_t)a->at("data").arr[0]->as_int());
+  float missing = cfg->has("missing") ? (float)cfg->at("missing").as_double() : std::nanf("");
+  auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
+  box->dm = DMatrix::from_device(ptr, (int64_t)shape.num_at(0), (int)shape.num_at(1), missing);
   *out = guard.release();
   API_END();
 }
@@ -309,6 +324,25 @@ int XGB200BoosterGetCachedMargin(BoosterHandle handle, DMatrixHandle dmat, float
   memcpy(out, v.data(), sizeof(float) * v.size());
   API_END();
 }
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+int XGB200TimerStart(void) {
+  API_BEGIN();
+  if (!g_t0) { CUDA_OK(cudaEventCreate(&g_t0)); CUDA_OK(cudaEventCreate(&g_t1)); }
+  CUDA_OK(cudaEventRecord(g_t0, engine_stream()));
+  API_END();
+}
+int XGB200TimerStop(float* out_ms) {
+  API_BEGIN();
+  if (!g_t0) throw Error("XGB200TimerStop without XGB200TimerStart");
+  CUDA_OK(cudaEventRecord(g_t1, engine_stream())); CUDA_OK(cudaEventSynchronize(g_t1));
+  CUDA_OK(cudaEventElapsedTime(out_ms, g_t0, g_t1));
+  API_END();
+}
+int XGB200BoosterSetProfile(BoosterHandle handle, int enable) { API_BEGIN(); BST(handle)->set_profile(enable != 0); API_END(); }
+int XGB200BoosterGetProfile(BoosterHandle handle, const char** out_json) {
+  API_BEGIN(); BoosterBox* box = static_cast<BoosterBox*>(handle); box->ret_str = BST(handle)->get_profile(); *out_json = box->ret_str.c_str(); API_END();
+}
+int XGB200LaunchCount(long long* out) { API_BEGIN(); *out = g_kernel_launches; API_END(); }
 int XGB200Synchronize(void) { API_BEGIN(); CUDA_OK(cudaStreamSynchronize(engine_stream())); API_END(); }
 
 }  // extern "C"

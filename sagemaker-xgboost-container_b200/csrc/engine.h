@@ -19,6 +19,9 @@ struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
 #define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw ::b200::Error( \
     std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); } while (0)
 
+// number of kernels this library has launched (reported by bench.py as gpu_launches)
+extern long long g_kernel_launches;
+
 template <typename T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
   DevBuf() = default;

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kHistThreads, 3) hist_build_kernel(HistArgs a)
   if (nb <= 0) return;
   const unsigned T = a.build_prefix[nb];
   if (T == 0) return;
+  if (a.rows_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.rows_counter, (unsigned long long)T);
   const unsigned C = gridDim.x;
   unsigned ceff = (T + kMinRowsPerCta - 1) / kMinRowsPerCta;
   ceff = ceff < 1 ? 1 : (ceff > C ? C : ceff);
@@ -170,7 +171,7 @@ void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid(grid_x, a.ngroups);
-  hist_build_kernel<<<grid, kHistThreads, 2 * kGroupEntries * sizeof(int), stream>>>(a);
+  hist_build_kernel<<<grid, kHistThreads, 2 * kGroupEntries * sizeof(int), stream>>>(a); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
 }
 

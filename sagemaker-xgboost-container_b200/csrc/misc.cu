@@ -231,40 +231,40 @@ static inline int grid_for(int64_t n, int block = 256, int cap = 148 * 16) {
 }
 void launch_gradient(const GradArgs& a, cudaStream_t s) {
   if (a.n == 0) return;
-  gradient_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  gradient_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s) {
-  sum_gpair_kernel<<<grid_for(n), 256, 0, s>>>(gp, n, out); CUDA_OK(cudaGetLastError());
+  sum_gpair_kernel<<<grid_for(n), 256, 0, s>>>(gp, n, out); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_bin(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups, const int* cut_ptrs,
                 const float* cut_vals, uint8_t* bins, cudaStream_t s) {
   if (n_chunk == 0) return;
-  bin_kernel<<<grid_for(n_chunk * ngroups * kSlots, 256, 148 * 32), 256, 0, s>>>(X, n_chunk, row0, n_total, F, fpg, ngroups, cut_ptrs, cut_vals, bins);
+  bin_kernel<<<grid_for(n_chunk * ngroups * kSlots, 256, 148 * 32), 256, 0, s>>>(X, n_chunk, row0, n_total, F, fpg, ngroups, cut_ptrs, cut_vals, bins); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
 }
 void launch_count_nan(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out, cudaStream_t s) {
   if (count == 0) return;
-  count_nan_kernel<<<grid_for(count), 256, 0, s>>>(X, count, missing, use_missing, out); CUDA_OK(cudaGetLastError());
+  count_nan_kernel<<<grid_for(count), 256, 0, s>>>(X, count, missing, use_missing, out); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_replace_missing(float* X, int64_t count, float missing, cudaStream_t s) {
   if (count == 0) return;
-  replace_missing_kernel<<<grid_for(count), 256, 0, s>>>(X, count, missing); CUDA_OK(cudaGetLastError());
+  replace_missing_kernel<<<grid_for(count), 256, 0, s>>>(X, count, missing); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_predict(const PredictArgs& a, cudaStream_t s) {
   if (a.n == 0 || a.tree_end <= a.tree_begin) return;
-  predict_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  predict_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_transform(float* m, int64_t n, int K, int objective, float* out_class, cudaStream_t s) {
   if (n == 0) return;
-  transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, n, K, objective, out_class); CUDA_OK(cudaGetLastError());
+  transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(m, n, K, objective, out_class); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_fill(float* p, int64_t n, float v, cudaStream_t s) {
   if (n == 0) return;
-  fill_kernel<<<grid_for(n), 256, 0, s>>>(p, n, v); CUDA_OK(cudaGetLastError());
+  fill_kernel<<<grid_for(n), 256, 0, s>>>(p, n, v); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_metric(const MetricArgs& a, cudaStream_t s) {
   if (a.n == 0) return;
-  metric_kernel<<<grid_for(a.n), 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  metric_kernel<<<grid_for(a.n), 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 
 }  // namespace b200

@@ -68,9 +68,9 @@ void compute_summaries_device(const float* dX, int64_t n, int F, const float* dw
   DevBuf<unsigned char> tmp; tmp.alloc(tmp_bytes + 16);
   const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
   for (int f = 0; f < F; ++f) {
-    extract_col_kernel<<<grid, 256, 0, s>>>(dX, n, F, f, dweights, keys.p, weighted ? wts.p : nullptr);
+    extract_col_kernel<<<grid, 256, 0, s>>>(dX, n, F, f, dweights, keys.p, weighted ? wts.p : nullptr); ++g_kernel_launches;
     CUDA_OK(cudaMemsetAsync(nvalid.p, 0, 8, s));
-    count_valid_kernel<<<grid, 256, 0, s>>>(dX, n, F, f, nvalid.p);
+    count_valid_kernel<<<grid, 256, 0, s>>>(dX, n, F, f, nvalid.p); ++g_kernel_launches;
     size_t tb = tmp_bytes;
     if (weighted) {
       CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys2.p, wts.p, wts2.p, (int64_t)n, 0, 32, s)); tb = tmp_bytes;
@@ -98,8 +98,8 @@ void compute_summaries_device(const float* dX, int64_t n, int F, const float* dw
       CUDA_OK(cudaStreamSynchronize(s));
     } else {
       // cap-point summary plus the first and last distinct values (so min/max survive)
-      pick_kernel<<<(cap + 255) / 256, 256, 0, s>>>(cum.p, m, cap, idx.p);
-      gather_kernel<<<(cap + 255) / 256, 256, 0, s>>>(uniq.p, cum.p, idx.p, cap, vsel.p, csel.p);
+      pick_kernel<<<(cap + 255) / 256, 256, 0, s>>>(cum.p, m, cap, idx.p); ++g_kernel_launches;
+      gather_kernel<<<(cap + 255) / 256, 256, 0, s>>>(uniq.p, cum.p, idx.p, cap, vsel.p, csel.p); ++g_kernel_launches;
       std::vector<float> vs(cap); std::vector<double> cs(cap); float v0; double c0;
       CUDA_OK(cudaMemcpyAsync(vs.data(), vsel.p, sizeof(float) * cap, cudaMemcpyDeviceToHost, s));
       CUDA_OK(cudaMemcpyAsync(cs.data(), csel.p, sizeof(double) * cap, cudaMemcpyDeviceToHost, s));

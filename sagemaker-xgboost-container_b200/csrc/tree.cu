@@ -409,22 +409,22 @@ __global__ void __launch_bounds__(256) subtract_kernel(GrowState gs, GH64* pool,
 // launchers
 // ---------------------------------------------------------------------------------------------
 void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s) {
-  init_tree_kernel<<<1, 32, 0, s>>>(gs, t, n, root_slot, max_level_nodes); CUDA_OK(cudaGetLastError());
+  init_tree_kernel<<<1, 32, 0, s>>>(gs, t, n, root_slot, max_level_nodes); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
-void launch_scales(const GrowState& gs, cudaStream_t s) { scales_kernel<<<1, 32, 0, s>>>(gs); CUDA_OK(cudaGetLastError()); }
+void launch_scales(const GrowState& gs, cudaStream_t s) { scales_kernel<<<1, 32, 0, s>>>(gs); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s) {
-  dim3 grid(max_nodes_level, a.ngroups); eval_kernel<<<grid, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  dim3 grid(max_nodes_level, a.ngroups); eval_kernel<<<grid, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
-void launch_apply(const ApplyArgs& a, cudaStream_t s) { apply_kernel<<<1, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError()); }
+void launch_apply(const ApplyArgs& a, cudaStream_t s) { apply_kernel<<<1, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s) {
-  part_count_kernel<<<max_tiles, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
+  part_count_kernel<<<max_tiles, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
   if (a.final_level) return;
-  part_scan_kernel<<<max_nodes_level, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
-  part_scatter_kernel<<<max_tiles, 256, 0, s>>>(a); CUDA_OK(cudaGetLastError());
-  build_prefix_kernel<<<1, 256, 0, s>>>(a.gs); CUDA_OK(cudaGetLastError());
+  part_scan_kernel<<<max_nodes_level, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+  part_scatter_kernel<<<max_tiles, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+  build_prefix_kernel<<<1, 256, 0, s>>>(a.gs); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s) {
-  dim3 grid(max_build, 8 * ngroups); subtract_kernel<<<grid, 256, 0, s>>>(gs, pool, ngroups); CUDA_OK(cudaGetLastError());
+  dim3 grid(max_build, 8 * ngroups); subtract_kernel<<<grid, 256, 0, s>>>(gs, pool, ngroups); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 
 }  // namespace b200

@@ -41,6 +41,7 @@ struct HistArgs {
   GH64* node_sum;               // per nid, accumulated only when accumulate_sum
   int ngroups;
   int accumulate_sum;
+  unsigned long long* rows_counter;   // optional: += rows processed by this launch (profiling)
 };
 
 void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream);
