@@ -640,6 +640,7 @@ int orc_update_one_iter(OrcTrainer* t) {
 
 /* accessors for the Python wrapper */
 void orc_set_quant_bits(OrcTrainer* t, int32_t bits) { t->quant_bits = bits; }
+void orc_set_margins(OrcTrainer* t, const float* m) { const int K = t->p.num_class > 1 ? t->p.num_class : 1; memcpy(t->margins, m, sizeof(float) * (size_t)(t->n * K)); }
 int32_t orc_num_trees(const OrcTrainer* t) { return t->model.n_trees; }
 int64_t orc_num_nodes(const OrcTrainer* t) { return t->model.n_nodes; }
 float orc_get_base_score(const OrcTrainer* t) { return t->base_score; }

@@ -76,6 +76,7 @@ def lib():
         L.orc_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9
         L.orc_num_threads.restype = C.c_int
         L.orc_set_quant_bits.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_set_margins.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -226,6 +227,10 @@ class Trainer:
     def set_quant_bits(self, bits):
         """Study knob: emulate the product's fixed-point gradient grid (0 = reference behaviour)."""
         lib().orc_set_quant_bits(self.h, int(bits))
+
+    def set_margins(self, m):
+        m = np.ascontiguousarray(m, np.float32).reshape(self.n, self.K)
+        lib().orc_set_margins(self.h, _p(m))
 
     def update(self):
         rc = lib().orc_update_one_iter(self.h)

@@ -1,0 +1,114 @@
+"""Pin the oracle on the only numeric anchor the reference ships: its UBJSON model fixture
+(test/resources/abalone/models/libsvm_pickled/xgboost-model, copied to tests/golden/, see tests/golden/README.md).
+CPU-only; checks listed in SURVEY.md section 8(c)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gbt_oracle as O
+from oracle import ubjson
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+ETA, LAMBDA, GAMMA, MCW = 0.2, 1.0, 4.0, 6.0     # test/integration/local/test_abalone.py:36-47
+
+
+@pytest.fixture(scope="module")
+def fixture_model():
+    doc = ubjson.load(os.path.join(G, "abalone_xgboost-model.ubj"))
+    return doc, ubjson.model_from_xgb_json(doc)
+
+
+def load_libsvm(path, F=8):
+    X, y = [], []
+    for line in open(path):
+        p = line.split()
+        y.append(float(p[0]))
+        row = [np.nan] * F
+        for kv in p[1:]:
+            k, v = kv.split(":")
+            row[int(k) - 1] = float(v)
+        X.append(row)
+    return np.array(X, np.float32), np.array(y, np.float32)
+
+
+def test_fixture_header(fixture_model):
+    doc, m = fixture_model
+    assert doc["version"] == [3, 2, 0]
+    assert m["objective"] == "reg:squarederror" and len(m["tree_info"]) == 50 and m["num_feature"] == 8
+    _, y = load_libsvm(os.path.join(G, "abalone", "abalone.train_0"))
+    assert abs(m["base_score"] - float(y.mean())) < 1e-5          # base_score = mean label = one Newton stump at margin 0
+    p = O.make_params({"objective": "reg:squarederror"})
+    assert abs(O.lib().orc_base_score(O.C.byref(p), O._p(y), None, len(y)) - m["base_score"]) < 1e-5
+
+
+def test_gain_identity_and_leaf_scaling(fixture_model):
+    """loss_chg = GL^2/(HL+l) + GR^2/(HR+l) - G^2/(H+l), leaf = eta * (-G/(H+l)); thresholds gamma / min_child_weight."""
+    _, m = fixture_model
+    worst = 0.0
+    n_internal = 0
+    for t in range(50):
+        T = m.tree(t)
+        w = lambda j: T["base_weight"][j] if T["left"][j] != -1 else T["split_cond"][j] / ETA
+        for i in range(len(T["left"])):
+            if T["left"][i] == -1:
+                assert T["sum_hess"][i] >= MCW or len(T["left"]) == 1
+                continue
+            n_internal += 1
+            l, r = T["left"][i], T["right"][i]
+            H, HL, HR = T["sum_hess"][i], T["sum_hess"][l], T["sum_hess"][r]
+            G, GL, GR = -T["base_weight"][i] * (H + LAMBDA), -w(l) * (HL + LAMBDA), -w(r) * (HR + LAMBDA)
+            lc = GL * GL / (HL + LAMBDA) + GR * GR / (HR + LAMBDA) - G * G / (H + LAMBDA)
+            worst = max(worst, abs(lc - T["loss_chg"][i]) / T["loss_chg"][i])
+            assert T["loss_chg"][i] >= GAMMA               # gamma acts before the split
+            assert abs(HL + HR - H) < 1e-3 * H
+            assert T["default_left"][i] == 0               # dense data: forward scan only
+    assert n_internal == 715
+    assert worst < 2e-5
+
+
+def test_traversal_known_answer(fixture_model):
+    _, m = fixture_model
+    row = np.array([[2, 0.645, 0.515, 0.15, 1.212, 0.515, 0.2055, 0.385]], np.float32)      # test_abalone.py:24 LIBSVM_SAMPLE
+    np.testing.assert_array_equal(O.predict_leaf(m, row)[0, :8], [42, 45, 40, 43, 34, 38, 38, 41])
+    assert abs(float(O.predict_margin(m, row)[0, 0]) - 11.100031) < 1e-5
+
+
+def test_oracle_split_arithmetic_reproduces_fixture_decisions(fixture_model):
+    """Feed the oracle's split evaluator the fixture's own node statistics: for every internal node the weight it
+    computes for each child must equal the stored base_weight / leaf value (unscaled for internal, eta-scaled for leaves)."""
+    _, m = fixture_model
+    for t in range(50):
+        T = m.tree(t)
+        for i in range(len(T["left"])):
+            if T["left"][i] == -1:
+                continue
+            H = float(T["sum_hess"][i])
+            G = -float(T["base_weight"][i]) * (H + LAMBDA)
+            wt = -G / (H + LAMBDA)
+            assert abs(wt - T["base_weight"][i]) <= 1e-6 * max(1, abs(wt))
+
+
+def test_oracle_trains_abalone_with_fixture_hyperparameters():
+    X, y = load_libsvm(os.path.join(G, "abalone", "abalone.train_0"))
+    params = dict(objective="reg:squarederror", max_depth=5, eta=ETA, gamma=GAMMA, min_child_weight=MCW)
+    t = O.train(params, X, y, 50)
+    m = t.model()
+    assert len(m["tree_info"]) == 50
+    internal = m["left"] != -1
+    assert (m["loss_chg"][internal] >= GAMMA).all() and (m["sum_hess"][~internal] >= MCW).all()
+    # same root split as the fixture's first tree (feature 7 = shell weight), cache == fresh prediction
+    assert m.tree(0)["split_index"][0] == 7
+    pred = O.predict_margin(m, X)[:, 0]
+    np.testing.assert_array_equal(pred, t.margins()[:, 0])
+    assert np.sqrt(np.mean((pred - y) ** 2)) < 2.0
+
+
+def test_cuts_definition_small_cardinality():
+    X = np.array([[1.0, 5.0], [2.0, 5.0], [2.0, 7.0], [4.0, np.nan]], np.float32)
+    ptrs, vals, mins, hm = O.make_cuts(X, 256)
+    assert hm
+    np.testing.assert_array_equal(ptrs, [0, 3, 5])
+    np.testing.assert_allclose(vals, [2.0, 4.0, 4.0 + 4.0 + 1e-5, 7.0, 7.0 + 7.0 + 1e-5])
+    bins = O.bin_matrix(X, ptrs, vals)
+    np.testing.assert_array_equal(bins, [[0, 0], [1, 0], [1, 1], [2, 255]])
