@@ -160,6 +160,8 @@ void DMatrix::bin_with_cuts() {
   if (!cuts.mins.empty()) CUDA_OK(cudaMemcpyAsync(d_min_vals.p, cuts.mins.data(), sizeof(float) * cuts.mins.size(), cudaMemcpyHostToDevice, s));
   bins.alloc((size_t)ngroups * n * kSlots);
   launch_bin(X.p, n, 0, n, F, fpg, ngroups, d_cut_ptrs.p, d_cut_vals.p, bins.p, s);
+  bins_col.alloc((size_t)std::max(F, 1) * n);
+  launch_transpose_bins(bins.p, n, F, fpg, ngroups, bins_col.p, s);
   CUDA_OK(cudaStreamSynchronize(s));
   binned = true;
 }
@@ -263,7 +265,7 @@ struct GrowerImpl {
   DevBuf<unsigned char> tree_block;        // header + TreeArrays, copied to the host in one piece
   size_t tree_block_bytes = 0;
   DevBuf<GH64> hist_pool; DevBuf<unsigned> ridx0, ridx1, scratch;
-  DevBuf<float2> gpair; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
+  DevBuf<float2> gpair, gp0, gp1; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
   int hist_grid_x = 1;
@@ -282,7 +284,7 @@ struct GrowerImpl {
     B200_CHECK(pool_bytes < free_b / 2 + hist_pool.n * sizeof(GH64), "histogram pool for this max_depth / feature count does not fit in device memory");
     hist_pool.alloc(2 * (size_t)region * slot_stride);
     ridx0.alloc(n); ridx1.alloc(n);
-    gpair.alloc((size_t)n * K); err.alloc(1); dsum.alloc(4);
+    gpair.alloc((size_t)n * K); gp0.alloc(n); gp1.alloc(n); err.alloc(1); dsum.alloc(4);
     const unsigned max_tiles = (unsigned)((n + kPartTile - 1) / kPartTile) + max_level_nodes + 1;
     scratch.alloc(3 * (size_t)max_level_nodes + 8);
     // ---- GrowState block
@@ -314,7 +316,7 @@ struct GrowerImpl {
     float* fp = (float*)(ip + 5 * N);
     ta.split_cond = fp; ta.base_weight = fp + N; ta.loss_chg = fp + 2 * N; ta.sum_hess = fp + 3 * N;
     ta.default_left = (unsigned char*)(fp + 4 * N);
-    hist_grid_x = std::max(1, (engine_num_sms() * 3 + ngroups - 1) / ngroups);
+    hist_grid_x = b200::hist_grid_x(engine_num_sms(), ngroups);
   }
 };
 
@@ -600,7 +602,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   launch_init_tree(g.gs, g.ta, (unsigned)dtrain->n, 0, g.max_level_nodes, s);
   CUDA_OK(cudaMemsetAsync(g.hist_pool.p, 0, g.slot_stride * sizeof(GH64), s));
 
-  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.gpair = g.gpair.p + (size_t)k * dtrain->n; ha.ridx = nullptr;
+  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.gpair = g.gpair.p + (size_t)k * dtrain->n; ha.ridx = nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups;
   ha.accumulate_sum = 1;
@@ -622,16 +624,17 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     ApplyArgs aa{}; aa.gs = g.gs; aa.tree = g.ta; aa.cut_ptrs = dtrain->d_cut_ptrs.p; aa.cut_vals = dtrain->d_cut_vals.p; aa.min_vals = dtrain->d_min_vals.p;
     aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups; aa.level = L; aa.max_level_nodes = g.max_level_nodes; aa.next_base = next_base; aa.next_half = next_half;
     launch_apply(aa, s);
-    PartArgs pa{}; pa.gs = g.gs; pa.tree = g.ta; pa.bins = bm.bins; pa.n = bm.n;
+    if (final_level) break;                  // children of the last level are leaves: no partition, no histograms
+    PartArgs pa{}; pa.gs = g.gs; pa.tree = g.ta; pa.bins_col = bm.bins_col; pa.n = bm.n;
     pa.ridx_cur = L == 0 ? nullptr : ((L & 1) ? g.ridx0.p : g.ridx1.p);
     pa.ridx_next = (L & 1) ? g.ridx1.p : g.ridx0.p;
-    pa.margin = cache.margin.p; pa.K = K; pa.k = k; pa.fpg = bm.fpg; pa.has_missing = bm.has_missing; pa.level = L; pa.max_level_nodes = g.max_level_nodes;
-    pa.final_level = final_level ? 1 : 0;
+    pa.gp_cur = L == 0 ? g.gpair.p + (size_t)k * dtrain->n : ((L & 1) ? g.gp0.p : g.gp1.p);
+    pa.gp_next = (L & 1) ? g.gp1.p : g.gp0.p;
+    pa.has_missing = bm.has_missing; pa.level = L; pa.max_level_nodes = g.max_level_nodes;
     launch_partition(pa, max_tiles, 1 << L, s);
-    if (final_level) break;
     // histograms of the next level: build the smaller children, all-reduce, subtract for the siblings
     CUDA_OK(cudaMemsetAsync(g.hist_pool.p + (size_t)next_base * g.slot_stride, 0, (size_t)next_half * g.slot_stride * sizeof(GH64), s));
-    ha.ridx = pa.ridx_next; ha.accumulate_sum = 0;
+    ha.ridx = pa.ridx_next; ha.gpair = pa.gp_next; ha.accumulate_sum = 0;
     ha.rows_counter = profile_ ? prof_rows_.p + 1 : nullptr;
     prof_begin(L + 1);
     launch_hist_build(ha, g.hist_grid_x, s);
@@ -641,6 +644,9 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     ea.level = L + 1;
     launch_eval(ea, 1 << (L + 1), s);
   }
+
+  // prediction cache += leaf values of this tree: one row-order pass over the column-major bins
+  launch_update_margin(g.ta, bm.bins_col, bm.n, bm.has_missing, cache.margin.p, K, k, s);
 
   // ---- hand the finished tree to the model: device copy for prediction, async host copy for model IO
   const size_t need = d_nodes_used + (size_t)g.cap_nodes;
@@ -791,7 +797,7 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   CUDA_OK(cudaMemcpyAsync(g.gs.absmax, am, 8, cudaMemcpyHostToDevice, s));
   launch_scales(g.gs, s);
   const BinnedMatrix bm = dm->binned_view();
-  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.gpair = g.gpair.p; ha.ridx = nullptr;
+  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.gpair = g.gpair.p; ha.ridx = nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups; ha.accumulate_sum = 1;
   cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));

@@ -28,7 +28,7 @@ class DMatrix {
   // binned representation (built on first use as a training matrix)
   bool binned = false; int binned_max_bin = 0;
   HostCuts cuts; DevBuf<int> d_cut_ptrs; DevBuf<float> d_cut_vals, d_min_vals;
-  DevBuf<uint8_t> bins; int ngroups = 0, fpg = 0;
+  DevBuf<uint8_t> bins, bins_col; int ngroups = 0, fpg = 0;
   uint64_t uid;                                       // identity for prediction caches
 
   DMatrix();
@@ -40,7 +40,7 @@ class DMatrix {
   const std::vector<float>& get_float_info(const std::string& field) const;
   void ensure_binned(int max_bin);
   void set_cuts(const HostCuts& c);                   // external cuts (shared with the oracle in tests)
-  BinnedMatrix binned_view() const { BinnedMatrix b; b.bins = bins.p; b.n = n; b.F = F; b.ngroups = ngroups; b.fpg = fpg; b.has_missing = has_missing; return b; }
+  BinnedMatrix binned_view() const { BinnedMatrix b; b.bins = bins.p; b.bins_col = bins_col.p; b.n = n; b.F = F; b.ngroups = ngroups; b.fpg = fpg; b.has_missing = has_missing; return b; }
  private:
   void finish_upload(float missing);
   void bin_with_cuts();

@@ -270,7 +270,7 @@ int XGB200DMatrixGetBins(DMatrixHandle handle, int max_bin, uint8_t* out_row_maj
   if (!h.empty()) { CUDA_OK(cudaMemcpy(h.data(), dm->bins.p, h.size(), cudaMemcpyDeviceToHost)); }
   for (int64_t r = 0; r < dm->n; ++r) for (int f = 0; f < dm->F; ++f) {
     int g = f / dm->fpg, s = f % dm->fpg;
-    out_row_major[r * dm->F + f] = h[((size_t)g * dm->n + r) * kSlots + s];
+    out_row_major[r * dm->F + f] = h[((size_t)r * dm->ngroups + g) * kSlots + s];
   }
   API_END();
 }

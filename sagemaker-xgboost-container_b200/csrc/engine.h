@@ -46,9 +46,10 @@ constexpr int kMaxDepth = 16;
 
 struct GH64 { long long g, h; };      // exact fixed-point gradient/hessian sums
 
-// One feature group of the binned matrix: rows x 32 B, row-major ("row-major binned feature block").
+// Binned matrix: each row is ngroups feature blocks of 32 B (one sector each); plus a column-major copy.
 struct BinnedMatrix {
-  const uint8_t* bins = nullptr;      // [ngroups][n][32]
+  const uint8_t* bins = nullptr;      // row-major [n][ngroups*32 B]: group g of row r at (r*ngroups+g)*32
+  const uint8_t* bins_col = nullptr;  // column-major [F][n]
   int64_t n = 0;
   int F = 0, ngroups = 0, fpg = 0;    // feature f -> group f / fpg, slot f % fpg
   int has_missing = 0;

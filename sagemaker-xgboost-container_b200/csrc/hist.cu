@@ -2,15 +2,20 @@
 // Replaces upstream xgboost's BuildHist (src/common/hist_util.cc / src/tree/gpu_hist/histogram.cu),
 // reached from the container at algorithm_mode/train.py:367-376 (xgb.train -> Booster.update).
 //
-// Design (DESIGN.md "histogram kernel"; measurements in profiles/microbench_r1.md):
+// Design (DESIGN.md "histogram kernel"; measurements in profiles/):
 //  * sm_100a has exactly one fast shared-memory atomic: 32-bit integer ATOMS.ADD (float and 64-bit
 //    adds compile to ATOMS.CAST.SPIN CAS loops), and it runs 2x faster when the 32 lanes of the
 //    instruction hit 32 distinct banks.  So the histogram of one 32-feature group is two int32 planes
 //    [256 bins][32 slots]: bank == slot, and every instruction below has lanes on 32 distinct slots.
-//  * A warp takes a tile of 16 rows; two lanes share a row, each holding 16 of its 32 bin bytes
-//    (one LDG.128 per lane, the row slice is exactly one 32 B sector).  Step j of 16 makes lane
-//    (row q, half h) update slot 16h + rot_q(j): the per-row rotation makes the 16 rows of an
-//    instruction touch 16 different slots of each half -> conflict-free by construction.
+//  * The binned matrix is row-major, each row = feature groups of 32 B.  A CTA owns a PAIR of adjacent
+//    groups (64 B of every row = one full DRAM burst, so gathered rows of deep levels waste nothing)
+//    or a single group when the matrix has only one.
+//  * A warp takes a tile of 16 rows; two lanes share a row, each holding 16 of a group's 32 bin bytes
+//    (one LDG.128 per lane and group).  Step j of 16 makes lane (row q, half h) update slot
+//    16h + rot_q(j): the per-row rotation makes the 16 rows of an instruction touch 16 different slots
+//    of each half -> conflict-free by construction.
+//  * (g,h) pairs are read by POSITION (they travel with the row ids through the partition), so the
+//    only gathered loads are the bin slices; row ids and pairs are prefetched two stages ahead.
 //  * Gradients are rounded to a power-of-two fixed-point grid (|g_q| <= 2^18, h_q <= 2^19) so a
 //    window of 4096 rows per CTA cannot overflow int32; between windows, accumulators above 2^24 are
 //    spilled to the global int64 histogram with RED.ADD.64 (sparse), and everything is flushed at the
@@ -21,13 +26,12 @@
 
 namespace b200 {
 
-constexpr int kHistThreads = 256;
-constexpr int kHistWarps = kHistThreads / 32;
 constexpr int kTileRows = 16;
+constexpr int kSuperRows = 2 * kTileRows;
 constexpr int kWindowRows = 4096;                 // rows per CTA between overflow checks
-constexpr int kWindowTiles = kWindowRows / kTileRows;
-constexpr int kMinRowsPerCta = 2048;              // do not pay a 16K-entry flush for fewer rows than this
+constexpr int kMinRowsPerCta = 4096;              // do not pay a flush for fewer rows than this
 constexpr int kSpillThreshold = 1 << 24;
+constexpr int kPlaneBytes = kGroupEntries * 4;    // 32 KB
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
@@ -36,75 +40,74 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 }
 __device__ __forceinline__ float2 ldg_nc_f2(const void* p) {
   float2 r;
-  asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void red_shared_s32(unsigned addr, int v) {
   asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void red_shared_u32_off(unsigned addr, unsigned v) {
+__device__ __forceinline__ void red_shared_u32_h(unsigned addr, unsigned v) {      // hessian plane = gradient plane + 32 KB
   asm volatile("red.shared.add.u32 [%0+32768], %1;" :: "r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void red_global_s64(long long* p, long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+struct LaneConst { unsigned sel[4], offb[4], offw[4]; int q, half, qw; };
 
-// Process rows [pa, pb) (segment positions) of one node into the shared-memory planes.
-__device__ __forceinline__ void hist_window(const HistArgs& a, const uint8_t* gbins, unsigned smem_g,
-                                            unsigned pa, unsigned pb, float sg, float sh,
-                                            long long& accG, long long& accH) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = lane >> 1, half = lane & 1;
-  const int qw = q >> 2, qb = q & 3;
-  // per-lane constants of the rotation: byte selectors and slot offsets (bytes) for the 4x4 steps
-  unsigned sel[4], offb[4], offw[4];
+// 16 conflict-free (g,h) atomic pairs of one lane's 16 bin bytes into the planes at smem byte offset `plane`
+__device__ __forceinline__ void accumulate16(const LaneConst& lc, const uint4& w, int gq, unsigned hq, unsigned plane) {
+  unsigned w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
+  if (lc.qw & 1) { unsigned x = w0; w0 = w1; w1 = w2; w2 = w3; w3 = x; }
+  if (lc.qw & 2) { unsigned x = w0; w0 = w2; w2 = x; x = w1; w1 = w3; w3 = x; }
+  const unsigned ww[4] = {w0, w1, w2, w3};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    sel[j] = 0x4440u | (unsigned)((j + qb) & 3);
-    offb[j] = 4u * (unsigned)((j + qb) & 3);
-    offw[j] = smem_g + 64u * (unsigned)half + 16u * (unsigned)((j + qw) & 3);
-  }
-  const unsigned ntiles = (pb - pa + kTileRows - 1) / kTileRows;
-  // software pipeline: registers of the next tile are loaded before the atomics of the current one
-  uint4 wn = make_uint4(0, 0, 0, 0); float2 ghn = make_float2(0.f, 0.f);
-  unsigned t = warp;
-  auto load_tile = [&](unsigned tile, uint4& w, float2& gh) {
-    unsigned p = pa + tile * kTileRows + q;
-    bool valid = p < pb;
-    unsigned r = valid ? (a.ridx ? __ldg(a.ridx + p) : p) : 0u;
-    if (valid) {
-      w = ldg_nc_v4(gbins + (int64_t)r * kSlots + half * 16);
-      gh = ldg_nc_f2(a.gpair + r);
-    } else { w = make_uint4(0, 0, 0, 0); gh = make_float2(0.f, 0.f); }
-  };
-  if (t < ntiles) load_tile(t, wn, ghn);
-  for (; t < ntiles; t += kHistWarps) {
-    uint4 w = wn; float2 gh = ghn;
-    if (t + kHistWarps < ntiles) load_tile(t + kHistWarps, wn, ghn);
-    const int gq = __float2int_rn(gh.x * sg);
-    const unsigned hq = (unsigned)__float2int_rn(gh.y * sh);
-    if (half == 0) { accG += gq; accH += hq; }
-    // rotate the four words by qw so that step jw reads word (jw + qw) & 3 from a fixed register
-    unsigned w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
-    if (qw & 1) { unsigned x = w0; w0 = w1; w1 = w2; w2 = w3; w3 = x; }
-    if (qw & 2) { unsigned x = w0; w0 = w2; w2 = x; x = w1; w1 = w3; w3 = x; }
-    const unsigned ww[4] = {w0, w1, w2, w3};
+  for (int jw = 0; jw < 4; ++jw) {
 #pragma unroll
-    for (int jw = 0; jw < 4; ++jw) {
-#pragma unroll
-      for (int jb = 0; jb < 4; ++jb) {
-        unsigned bin = __byte_perm(ww[jw], 0u, sel[jb]);
-        unsigned addr = (bin << 7) + offw[jw] + offb[jb];
-        red_shared_s32(addr, gq);
-        red_shared_u32_off(addr, hq);
-      }
+    for (int jb = 0; jb < 4; ++jb) {
+      unsigned bin = __byte_perm(ww[jw], 0u, lc.sel[jb]);
+      unsigned addr = (bin << 7) + lc.offw[jw] + lc.offb[jb] + plane;
+      red_shared_s32(addr, gq);
+      red_shared_u32_h(addr, hq);
     }
   }
 }
 
-__global__ void __launch_bounds__(kHistThreads, 3) hist_build_kernel(HistArgs a) {
-  extern __shared__ __align__(16) int smem[];         // LG[8192] then LH[8192]
+struct Stage { unsigned id; float2 gh; };
+struct Rows { uint4 a0, a1, b0, b1; };                      // tile A / tile B, group 0 / group 1
+
+// Spill / flush pass over the CTA's accumulators.  Between windows only accumulators that could overflow in the next
+// window leave for the global int64 histogram (sparse RED.ADD.64); `last` flushes everything that is non-zero.
+template <int NTHREADS>
+__device__ __forceinline__ void spill_pass(int* smem, int ng_here, GH64* out, bool last) {
+  const int vecs = ng_here * 2 * kGroupEntries / 4;
+  for (int v = threadIdx.x; v < vecs; v += NTHREADS) {
+    int4 x = reinterpret_cast<int4*>(smem)[v];
+    const int plane = (v * 4) / kGroupEntries;              // 0: G of group 0, 1: H of group 0, 2: G of group 1, 3: H of group 1
+    const int e0 = v * 4 - plane * kGroupEntries;
+    const bool is_h = plane & 1;
+    int vals[4] = {x.x, x.y, x.z, x.w};
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int val = vals[k];
+      bool sp = last ? (val != 0) : (is_h ? ((unsigned)val >= (unsigned)kSpillThreshold) : (val >= kSpillThreshold || val <= -kSpillThreshold));
+      if (sp) {
+        GH64* o = out + (size_t)(plane >> 1) * kGroupEntries + e0 + k;
+        red_global_s64(is_h ? &o->h : &o->g, is_h ? (long long)(unsigned)val : (long long)val);
+        vals[k] = 0; any = true;
+      }
+    }
+    if (any) reinterpret_cast<int4*>(smem)[v] = make_int4(vals[0], vals[1], vals[2], vals[3]);
+  }
+}
+
+template <int NG, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(HistArgs a) {
+  constexpr int NWARPS = NTHREADS / 32;
+  constexpr int kItersPerWindow = kWindowRows / (kSuperRows * NWARPS);     // super-tiles per warp between overflow checks
+  static_assert(kItersPerWindow >= 1, "window too small");
+  extern __shared__ __align__(16) int smem[];         // per group: LG[8192] then LH[8192]
   const int nb = *a.build_count;
   if (nb <= 0) return;
   const unsigned T = a.build_prefix[nb];
@@ -114,64 +117,120 @@ __global__ void __launch_bounds__(kHistThreads, 3) hist_build_kernel(HistArgs a)
   unsigned ceff = (T + kMinRowsPerCta - 1) / kMinRowsPerCta;
   ceff = ceff < 1 ? 1 : (ceff > C ? C : ceff);
   if (blockIdx.x >= ceff) return;
-  unsigned chunk = ((T + ceff - 1) / ceff + kTileRows - 1) & ~(unsigned)(kTileRows - 1);
+  unsigned chunk = ((T + ceff - 1) / ceff + kSuperRows - 1) & ~(unsigned)(kSuperRows - 1);
   unsigned long long r0l = (unsigned long long)blockIdx.x * chunk;
   if (r0l >= T) return;
   unsigned r0 = (unsigned)r0l;
   unsigned r1 = (unsigned long long)r0 + chunk > T ? T : r0 + chunk;
-  const int group = blockIdx.y;
-  const uint8_t* gbins = a.bins + (int64_t)group * a.n * kSlots;
+  const int g0 = blockIdx.y * NG;
+  const bool two = NG == 2 && (g0 + 1 < a.ngroups);
+  const int ng_here = two ? 2 : 1;
+  const uint8_t* gbins = a.bins + (int64_t)g0 * kSlots;
   const float sg = a.scales[0], sh = a.scales[1];
   const unsigned smem_g = (unsigned)__cvta_generic_to_shared(smem);
+  const int64_t row_stride = (int64_t)a.row_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  for (int i = threadIdx.x; i < 2 * kGroupEntries / 4; i += kHistThreads) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
+  LaneConst lc;
+  { lc.q = lane >> 1; lc.half = lane & 1; lc.qw = lc.q >> 2; const int qb = lc.q & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { lc.sel[j] = 0x4440u | (unsigned)((j + qb) & 3); lc.offb[j] = 4u * (unsigned)((j + qb) & 3);
+      lc.offw[j] = smem_g + 64u * (unsigned)lc.half + 16u * (unsigned)((j + lc.qw) & 3); } }
+
+  const int entries = ng_here * 2 * kGroupEntries;
+  for (int i = threadIdx.x; i < entries / 4; i += NTHREADS) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
   __syncthreads();
 
-  // first build node whose range contains r0
-  int b = 0;
+  int b = 0;   // first build node whose range contains r0
   { int lo = 0, hi = nb; while (lo < hi) { int mid = (lo + hi) >> 1; if (a.build_prefix[mid + 1] > r0) hi = mid; else lo = mid + 1; } b = lo; }
 
+  const Stage none{0xffffffffu, make_float2(0.f, 0.f)};
   while (r0 < r1) {
     const unsigned nbeg = a.build_prefix[b], nend_node = a.build_prefix[b + 1];
     const unsigned nend = nend_node < r1 ? nend_node : r1;
     const int nid = a.build_nid[b];
     const unsigned seg = a.seg_begin[nid];
-    GH64* out = a.hist_pool + ((int64_t)a.hist_slot[nid] * a.ngroups + group) * kGroupEntries;
+    GH64* out = a.hist_pool + ((int64_t)a.hist_slot[nid] * a.ngroups + g0) * kGroupEntries;
     long long accG = 0, accH = 0;
-    unsigned pa = seg + (r0 - nbeg), pend = seg + (nend - nbeg);
-    while (pa < pend) {
-      unsigned pb = pend - pa > (unsigned)kWindowRows ? pa + kWindowRows : pend;
-      hist_window(a, gbins, smem_g, pa, pb, sg, sh, accG, accH);
-      pa = pb;
-      __syncthreads();
-      const bool last = pa >= pend;
-      // spill (between windows: only accumulators that could overflow in the next window) / final flush
-      for (int e = threadIdx.x; e < kGroupEntries; e += kHistThreads) {
-        int g = smem[e]; unsigned h = (unsigned)smem[kGroupEntries + e];
-        bool sg_ = last ? (g != 0) : (g >= kSpillThreshold || g <= -kSpillThreshold);
-        bool sh_ = last ? (h != 0) : (h >= (unsigned)kSpillThreshold);
-        if (sg_) { red_global_s64(&out[e].g, (long long)g); smem[e] = 0; }
-        if (sh_) { red_global_s64(&out[e].h, (long long)h); smem[kGroupEntries + e] = 0; }
+    const unsigned pa = seg + (r0 - nbeg), pb = seg + (nend - nbeg);
+    const unsigned nsuper = (pb - pa + kSuperRows - 1) / kSuperRows;
+    const unsigned iters = (nsuper + NWARPS - 1) / NWARPS;          // same for every warp: barriers stay aligned
+
+    // Three-stage software pipeline per warp over super-tiles of 32 positions; it runs THROUGH the overflow-check
+    // barriers (the loads of the next super-tiles stay in flight while the CTA spills), so no window restarts cold:
+    //   stage A: row ids + (g,h) of super-tile s+2 (coalesced, one position per lane)
+    //   stage B: bin slices of super-tile s+1 (LDG.128 per lane and group, addresses from stage A via SHFL)
+    //   stage C: conflict-free ATOMS pairs of super-tile s
+    auto load_ids = [&](unsigned st) -> Stage {
+      Stage s_ = none;
+      unsigned p = pa + st * kSuperRows + lane;
+      if (st < nsuper && p < pb) { s_.id = a.ridx ? __ldg(a.ridx + p) : p; s_.gh = ldg_nc_f2(a.gpair + p); }
+      return s_;
+    };
+    auto load_rows = [&](unsigned ids, Rows& r) {
+      unsigned rA = __shfl_sync(0xffffffffu, ids, lc.q), rB = __shfl_sync(0xffffffffu, ids, 16 + lc.q);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      r.a0 = r.a1 = r.b0 = r.b1 = z;
+      if (rA != 0xffffffffu) { const uint8_t* p = gbins + (int64_t)rA * row_stride + lc.half * 16; r.a0 = ldg_nc_v4(p); if (NG == 2 && two) r.a1 = ldg_nc_v4(p + 32); }
+      if (rB != 0xffffffffu) { const uint8_t* p = gbins + (int64_t)rB * row_stride + lc.half * 16; r.b0 = ldg_nc_v4(p); if (NG == 2 && two) r.b1 = ldg_nc_v4(p + 32); }
+    };
+    Stage cur = load_ids(warp);
+    Stage nxt = load_ids(warp + NWARPS);
+    Rows rows; load_rows(cur.id, rows);
+    for (unsigned it = 0; it < iters; ++it) {
+      const unsigned s = warp + it * NWARPS;
+      Stage nn = load_ids(s + 2 * NWARPS);
+      Rows nrows; load_rows(nxt.id, nrows);
+      if (s < nsuper) {
+        const int gq_l = __float2int_rn(cur.gh.x * sg);
+        const unsigned hq_l = (unsigned)__float2int_rn(cur.gh.y * sh);
+        accG += gq_l; accH += hq_l;
+        const int gA = __shfl_sync(0xffffffffu, gq_l, lc.q), gB = __shfl_sync(0xffffffffu, gq_l, 16 + lc.q);
+        const unsigned hA = __shfl_sync(0xffffffffu, hq_l, lc.q), hB = __shfl_sync(0xffffffffu, hq_l, 16 + lc.q);
+        accumulate16(lc, rows.a0, gA, hA, 0u);
+        if (NG == 2 && two) accumulate16(lc, rows.a1, gA, hA, 2u * kPlaneBytes);
+        accumulate16(lc, rows.b0, gB, hB, 0u);
+        if (NG == 2 && two) accumulate16(lc, rows.b1, gB, hB, 2u * kPlaneBytes);
       }
-      __syncthreads();
+      rows = nrows; cur = nxt; nxt = nn;
+      if ((it + 1) % kItersPerWindow == 0 && it + 1 < iters) {       // overflow check: at most 4096 rows since the last one
+        __syncthreads();
+        spill_pass<NTHREADS>(smem, ng_here, out, false);
+        __syncthreads();
+      }
     }
-    if (a.accumulate_sum && group == 0) {
+    __syncthreads();
+    spill_pass<NTHREADS>(smem, ng_here, out, true);
+    __syncthreads();
+    if (a.accumulate_sum && blockIdx.y == 0) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { accG += __shfl_xor_sync(0xffffffffu, accG, o); accH += __shfl_xor_sync(0xffffffffu, accH, o); }
-      if ((threadIdx.x & 31) == 0 && (accG != 0 || accH != 0)) { red_global_s64(&a.node_sum[nid].g, accG); red_global_s64(&a.node_sum[nid].h, accH); }
+      if (lane == 0 && (accG != 0 || accH != 0)) { red_global_s64(&a.node_sum[nid].g, accG); red_global_s64(&a.node_sum[nid].h, accH); }
     }
     r0 = nend; ++b;
   }
 }
 
+int hist_grid_x(int num_sms, int ngroups) {
+  if (ngroups == 1) return num_sms * 3;
+  const int sets = (ngroups + 1) / 2;
+  const int x = (num_sms + sets - 1) / sets;
+  return x > 0 ? x : 1;
+}
+
 void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(hist_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kGroupEntries * (int)sizeof(int)));
+    CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPlaneBytes));
+    CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<2, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPlaneBytes));
     configured = true;
   }
-  dim3 grid(grid_x, a.ngroups);
-  hist_build_kernel<<<grid, kHistThreads, 2 * kGroupEntries * sizeof(int), stream>>>(a); ++g_kernel_launches;
+  if (a.ngroups == 1) {
+    hist_build_kernel<1, 256><<<dim3(grid_x, 1), 256, 2 * kPlaneBytes, stream>>>(a);
+  } else {
+    hist_build_kernel<2, 768><<<dim3(grid_x, (a.ngroups + 1) / 2), 768, 4 * kPlaneBytes, stream>>>(a);
+  }
+  ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
 }
 

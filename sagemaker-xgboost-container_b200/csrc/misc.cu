@@ -27,9 +27,8 @@ __device__ __forceinline__ float rng_uniform_dev(unsigned seed, unsigned long lo
 // gradient pairs: one thread per row, all K classes; also the running max|g|, max h of the round
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gradient_kernel(GradArgs a) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float mg = 0.f, mh = 0.f;
-  if (r < a.n) {
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (int64_t)gridDim.x * blockDim.x) {
     const float y = a.label[r];
     float w = a.weight ? a.weight[r] : 1.0f;
     bool dropped = false;
@@ -62,7 +61,7 @@ __global__ void __launch_bounds__(256) gradient_kernel(GradArgs a) {
       g *= w; h *= w;
       if (dropped) { g = 0.f; h = 0.f; }
       a.gpair[r] = make_float2(g, h);
-      mg = fabsf(g); mh = h;
+      mg = fmaxf(mg, fabsf(g)); mh = fmaxf(mh, h);
     }
   }
 #pragma unroll
@@ -94,8 +93,8 @@ __global__ void __launch_bounds__(256) bin_kernel(const float* X, int64_t n_chun
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int s = (int)(idx % kSlots);
     const int64_t t = idx / kSlots;
-    const int64_t r = t % n_chunk;
-    const int g = (int)(t / n_chunk);
+    const int g = (int)(t % ngroups);
+    const int64_t r = t / ngroups;
     const int f = g * fpg + s;
     uint8_t b = 0;
     if (s < fpg && f < F) {
@@ -110,8 +109,24 @@ __global__ void __launch_bounds__(256) bin_kernel(const float* X, int64_t n_chun
         b = (uint8_t)lo;
       }
     }
-    bins[((int64_t)g * n_total + row0 + r) * kSlots + s] = b;
+    bins[((row0 + r) * ngroups + g) * kSlots + s] = b;      // row-major [n][ngroups*32]: idx order == address order
   }
+  (void)n_total;
+}
+
+// column-major copy [F][n] of the binned matrix (used by the 1-byte-per-row consumers: partition, cache update)
+__global__ void __launch_bounds__(256) transpose_bins_kernel(const uint8_t* bins, int64_t n, int F, int fpg, int ngroups, uint8_t* bins_col) {
+  __shared__ uint8_t tile[256][kSlots + 1];
+  const int g = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * 256;
+  for (int i = threadIdx.x; i < 256 * kSlots; i += 256) {
+    int rr = i / kSlots, s = i % kSlots;
+    int64_t r = r0 + rr;
+    tile[rr][s] = r < n ? bins[(r * ngroups + g) * kSlots + s] : 0;
+  }
+  __syncthreads();
+  const int64_t r = r0 + threadIdx.x;
+  if (r < n) for (int s = 0; s < fpg; ++s) { int f = g * fpg + s; if (f < F) bins_col[(int64_t)f * n + r] = tile[threadIdx.x][s]; }
 }
 
 __global__ void __launch_bounds__(256) count_nan_kernel(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out) {
@@ -231,7 +246,7 @@ static inline int grid_for(int64_t n, int block = 256, int cap = 148 * 16) {
 }
 void launch_gradient(const GradArgs& a, cudaStream_t s) {
   if (a.n == 0) return;
-  gradient_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+  gradient_kernel<<<grid_for(a.n, 256, 148 * 8), 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s) {
   sum_gpair_kernel<<<grid_for(n), 256, 0, s>>>(gp, n, out); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
@@ -241,6 +256,11 @@ void launch_bin(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, 
   if (n_chunk == 0) return;
   bin_kernel<<<grid_for(n_chunk * ngroups * kSlots, 256, 148 * 32), 256, 0, s>>>(X, n_chunk, row0, n_total, F, fpg, ngroups, cut_ptrs, cut_vals, bins); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
+}
+void launch_transpose_bins(const uint8_t* bins, int64_t n, int F, int fpg, int ngroups, uint8_t* bins_col, cudaStream_t s) {
+  if (n == 0) return;
+  dim3 grid((unsigned)((n + 255) / 256), ngroups);
+  transpose_bins_kernel<<<grid, 256, 0, s>>>(bins, n, F, fpg, ngroups, bins_col); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_count_nan(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out, cudaStream_t s) {
   if (count == 0) return;

@@ -38,6 +38,7 @@ void launch_gradient(const GradArgs& a, cudaStream_t s);
 void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s);
 void launch_bin(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups, const int* cut_ptrs,
                 const float* cut_vals, uint8_t* bins, cudaStream_t s);
+void launch_transpose_bins(const uint8_t* bins, int64_t n, int F, int fpg, int ngroups, uint8_t* bins_col, cudaStream_t s);
 void launch_count_nan(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out, cudaStream_t s);
 void launch_replace_missing(float* X, int64_t count, float missing, cudaStream_t s);
 void launch_predict(const PredictArgs& a, cudaStream_t s);

@@ -281,24 +281,14 @@ __global__ void __launch_bounds__(256) part_count_kernel(PartArgs a) {
   const unsigned tile = blockIdx.x;
   if (tile >= gs.tile_prefix[cnt]) return;
   const int i = find_node_of_tile(gs.tile_prefix, cnt, tile);
+  if (!gs.part_action[i]) return;           // node stays a leaf: its rows simply drop out of the row-id buffer
   const int nid = gs.level_nodes[(size_t)a.level * a.max_level_nodes + i];
   const unsigned lt = tile - gs.tile_prefix[i];
   const unsigned b = gs.seg_begin[nid], c = gs.seg_count[nid];
   const unsigned p0 = b + lt * kPartTile, p1 = (b + c < p0 + kPartTile) ? b + c : p0 + kPartTile;
-  float* margin = a.margin;
-  if (!gs.part_action[i]) {                 // node stays a leaf: apply its value to the prediction cache
-    const float v = a.tree.split_cond[nid];
-    for (unsigned p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-      unsigned r = a.ridx_cur ? a.ridx_cur[p] : p;
-      margin[(size_t)r * a.K + a.k] += v;
-    }
-    return;
-  }
   const int f = a.tree.split_index[nid];
-  const int g = f / a.fpg, s = f % a.fpg;
   const int sb = a.tree.split_bin[nid], dl = a.tree.default_left[nid];
-  const uint8_t* col = a.bins + (int64_t)g * a.n * kSlots + s;
-  const float lv = a.tree.split_cond[a.tree.left[nid]], rv = a.tree.split_cond[a.tree.right[nid]];
+  const uint8_t* col = a.bins_col + (int64_t)f * a.n;        // column-major copy: one byte per row, rows ascending
   unsigned nleft = 0;
   const unsigned pt = p0 + threadIdx.x * 8;
 #pragma unroll
@@ -306,19 +296,46 @@ __global__ void __launch_bounds__(256) part_count_kernel(PartArgs a) {
     unsigned p = pt + j;
     if (p < p1) {
       unsigned r = a.ridx_cur ? a.ridx_cur[p] : p;
-      int byte = col[(int64_t)r * kSlots];
+      int byte = col[r];
       bool left = (a.has_missing && byte == kMissingBin) ? (dl != 0) : (byte <= sb);
-      if (a.final_level) margin[(size_t)r * a.K + a.k] += left ? lv : rv;
-      else { gs.flags[p] = left ? 1 : 0; nleft += left ? 1u : 0u; }
+      gs.flags[p] = left ? 1 : 0; nleft += left ? 1u : 0u;
     }
   }
-  if (a.final_level) return;
   __shared__ unsigned s_cnt[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nleft += __shfl_xor_sync(0xffffffffu, nleft, o);
   if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = nleft;
   __syncthreads();
   if (threadIdx.x == 0) { unsigned tsum = 0; for (int w = 0; w < 8; ++w) tsum += s_cnt[w]; gs.tile_left[tile] = tsum; }
+}
+
+// Prediction-cache update of a finished tree: one streaming pass in ROW order over the column-major bins
+// (coalesced, no scattered read-modify-write of the cache).
+__global__ void __launch_bounds__(256) update_margin_kernel(TreeArrays t, const uint8_t* bins_col, int64_t n, int has_missing,
+                                                            float* margin, int K, int k) {
+  // four independent traversals per thread (rows r, r+256, r+512, r+768 of the block's 1024-row tile): 4 loads in flight
+  const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  int nid[4]; bool done[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { nid[j] = 0; done[j] = (base + j * 256 >= n) || t.left[0] == -1; }
+  bool any = !(done[0] && done[1] && done[2] && done[3]);
+  while (any) {
+    int byte[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) byte[j] = done[j] ? 0 : bins_col[(int64_t)t.split_index[nid[j]] * n + base + j * 256];
+    any = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (done[j]) continue;
+      const int nd = nid[j];
+      const bool left = (has_missing && byte[j] == kMissingBin) ? (t.default_left[nd] != 0) : (byte[j] <= t.split_bin[nd]);
+      nid[j] = left ? t.left[nd] : t.right[nd];
+      done[j] = t.left[nid[j]] == -1;
+      any |= !done[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const int64_t r = base + j * 256; if (r < n) margin[r * K + k] += t.split_cond[nid[j]]; }
 }
 
 __global__ void __launch_bounds__(256) part_scan_kernel(PartArgs a) {
@@ -352,11 +369,11 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(PartArgs a) {
   const unsigned nl = gs.seg_count[a.tree.left[nid]];
   const unsigned toff = gs.tile_off[tile];
   const unsigned pt = p0 + threadIdx.x * 8;
-  unsigned rows[8]; unsigned char fl[8]; unsigned mine = 0;
+  unsigned rows[8]; float2 gp[8]; unsigned char fl[8]; unsigned mine = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     unsigned p = pt + j;
-    if (p < p1) { rows[j] = a.ridx_cur ? a.ridx_cur[p] : p; fl[j] = gs.flags[p]; mine += fl[j]; } else { rows[j] = 0; fl[j] = 2; }
+    if (p < p1) { rows[j] = a.ridx_cur ? a.ridx_cur[p] : p; gp[j] = a.gp_cur[p]; fl[j] = gs.flags[p]; mine += fl[j]; } else { rows[j] = 0; gp[j] = make_float2(0.f, 0.f); fl[j] = 2; }
   }
   __shared__ unsigned s_w[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -376,6 +393,7 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(PartArgs a) {
     if (fl[j]) { dest = b + toff + lbefore; ++lbefore; }
     else dest = b + nl + (lt * kPartTile + jj - toff - lbefore);
     a.ridx_next[dest] = rows[j];
+    a.gp_next[dest] = gp[j];
   }
 }
 
@@ -418,10 +436,13 @@ void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s) {
 void launch_apply(const ApplyArgs& a, cudaStream_t s) { apply_kernel<<<1, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s) {
   part_count_kernel<<<max_tiles, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
-  if (a.final_level) return;
   part_scan_kernel<<<max_nodes_level, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
   part_scatter_kernel<<<max_tiles, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
   build_prefix_kernel<<<1, 256, 0, s>>>(a.gs); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+}
+void launch_update_margin(const TreeArrays& t, const uint8_t* bins_col, int64_t n, int has_missing, float* margin, int K, int k, cudaStream_t s) {
+  if (n == 0) return;
+  update_margin_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(t, bins_col, n, has_missing, margin, K, k); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s) {
   dim3 grid(max_build, 8 * ngroups); subtract_kernel<<<grid, 256, 0, s>>>(gs, pool, ngroups); ++g_kernel_launches; CUDA_OK(cudaGetLastError());

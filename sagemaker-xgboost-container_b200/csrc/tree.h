@@ -22,14 +22,16 @@ struct ApplyArgs {
 };
 
 struct PartArgs {
-  GrowState gs; TreeArrays tree; const uint8_t* bins; int64_t n; const unsigned* ridx_cur; unsigned* ridx_next;
-  float* margin; int K, k, fpg, has_missing, level, max_level_nodes, final_level;
+  GrowState gs; TreeArrays tree; const uint8_t* bins_col; int64_t n; const unsigned* ridx_cur; unsigned* ridx_next;
+  const float2* gp_cur; float2* gp_next;      // (g,h) pairs travel with the row ids (position order)
+  int has_missing, level, max_level_nodes;
 };
 
 struct HistArgs {
-  const uint8_t* bins;          // [ngroups][n][32]
+  const uint8_t* bins;          // row-major [n][ngroups*32 B]
   int64_t n;
-  const float2* gpair;          // (g, h) per row of the class being grown
+  int row_stride;               // ngroups * 32
+  const float2* gpair;          // (g, h) by POSITION in the row-id buffer (== by row at the root)
   const unsigned* ridx;         // row ids by segment position; nullptr = identity (root)
   const int* build_count;       // number of nodes to build
   const int* build_nid;         // their node ids
@@ -45,11 +47,13 @@ struct HistArgs {
 };
 
 void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream);
+int hist_grid_x(int num_sms, int ngroups);
 void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s);
 void launch_scales(const GrowState& gs, cudaStream_t s);
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s);
 void launch_apply(const ApplyArgs& a, cudaStream_t s);
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s);
+void launch_update_margin(const TreeArrays& t, const uint8_t* bins_col, int64_t n, int has_missing, float* margin, int K, int k, cudaStream_t s);
 void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s);
 
 }  // namespace b200
