@@ -257,6 +257,9 @@ struct PinnedPool {
   void reset() { cur = 0; off = 0; }
 };
 
+struct TreeGraphKey { uint64_t uid; const void *margin, *mask, *packed; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds; int world; int64_t n; };
+struct TreeGraph { cudaGraphExec_t exec = nullptr; TreeGraphKey key; long long launches = 0; TreeGraph() { memset(&key, 0, sizeof key); } };
+
 struct GrowerImpl {
   int64_t n = 0; int ngroups = 0, max_depth = 0, max_nodes = 0, cap_nodes = 0, max_level_nodes = 0, region = 0;
   size_t slot_stride = 0;                  // GH64 entries per histogram slot
@@ -268,12 +271,14 @@ struct GrowerImpl {
   DevBuf<float2> gpair, gp0, gp1; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
+  DevBuf<DevNode> packed; std::vector<TreeGraph> graphs;
   int hist_grid_x = 1;
 
   void ensure(int64_t n_, int ngroups_, int max_depth_, int K) {
     if (n == n_ && ngroups == ngroups_ && max_depth == max_depth_ && gpair.n >= (size_t)n_ * K) return;
     B200_CHECK(max_depth_ >= 1 && max_depth_ <= kMaxDepth, "max_depth must be in [1, 16] for the B200 depth-wise hist builder");
     n = n_; ngroups = ngroups_; max_depth = max_depth_;
+    for (auto& tg : graphs) if (tg.exec) { cudaGraphExecDestroy(tg.exec); tg.exec = nullptr; }
     max_nodes = (1 << (max_depth + 1)) - 1;
     cap_nodes = (max_nodes + 15) & ~15;
     max_level_nodes = 1 << (max_depth - 1);
@@ -317,6 +322,7 @@ struct GrowerImpl {
     ta.split_cond = fp; ta.base_weight = fp + N; ta.loss_chg = fp + 2 * N; ta.sum_hess = fp + 3 * N;
     ta.default_left = (unsigned char*)(fp + 4 * N);
     hist_grid_x = b200::hist_grid_x(engine_num_sms(), ngroups);
+    hist_configure();
   }
 };
 
@@ -579,9 +585,8 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
 }
 
 
-// One tree of class k: the whole level loop is a fixed sequence of launches; every data-dependent decision
-// (which nodes split, which child is built, segment sizes) lives in device memory.
-void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_index) {
+// The fixed launch sequence of one tree (everything data dependent lives in device memory), capturable in a CUDA graph.
+void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned char* mask, DevNode* packed_out) {
   cudaStream_t s = engine_stream();
   GrowerImpl& g = *grower_;
   Comm& comm = Comm::get();
@@ -589,14 +594,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   const int D = param_.max_depth;
   const TrainParamDev pd = to_dev(param_);
   const BinnedMatrix bm = dtrain->binned_view();
-  const unsigned char* mask = nullptr;
-  if (param_.colsample_bytree < 1.0f) {
-    std::string m = colsample_mask(param_.seed, tree_index, dtrain->F, param_.colsample_bytree);
-    g.feat_mask.ensure(m.size());
-    CUDA_OK(cudaMemcpyAsync(g.feat_mask.p, m.data(), m.size(), cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaStreamSynchronize(s));
-    mask = g.feat_mask.p;
-  }
+  PredCache cache_view; (void)cache_view;
   const unsigned max_tiles = (unsigned)((dtrain->n + kPartTile - 1) / kPartTile) + g.max_level_nodes + 1;
 
   launch_init_tree(g.gs, g.ta, (unsigned)dtrain->n, 0, g.max_level_nodes, s);
@@ -646,7 +644,52 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   }
 
   // prediction cache += leaf values of this tree: one row-order pass over the column-major bins
-  launch_update_margin(g.ta, bm.bins_col, bm.n, bm.has_missing, cache.margin.p, K, k, s);
+  launch_update_margin(g.ta, bm.bins_col, bm.n, bm.has_missing, margin, K, k, s);
+
+  pack_tree_kernel<<<(g.cap_nodes + 255) / 256, 256, 0, s>>>(g.ta, g.gs.n_nodes, packed_out, g.cap_nodes); ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
+}
+
+// One tree of class k.  The sequence is replayed from a CUDA graph (captured once per (matrix, class, parameters)):
+// at small per-GPU shards the ~60 launches + 6 NCCL calls per tree are otherwise CPU-launch bound.
+void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_index) {
+  cudaStream_t s = engine_stream();
+  GrowerImpl& g = *grower_;
+  const unsigned char* mask = nullptr;
+  if (param_.colsample_bytree < 1.0f) {
+    std::string m = colsample_mask(param_.seed, tree_index, dtrain->F, param_.colsample_bytree);
+    g.feat_mask.ensure(m.size());
+    CUDA_OK(cudaMemcpyAsync(g.feat_mask.p, m.data(), m.size(), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    mask = g.feat_mask.p;
+  }
+  g.packed.ensure((size_t)g.cap_nodes);
+  static const bool no_graph = getenv("B200XGB_NO_GRAPH") != nullptr;
+  if (profile_ || no_graph) {
+    enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p);
+  } else {
+    if ((int)g.graphs.size() <= k) g.graphs.resize(k + 1);
+    TreeGraph& tg = g.graphs[k];
+    TreeGraphKey key; memset(&key, 0, sizeof key);
+    key.uid = dtrain->uid; key.margin = cache.margin.p; key.mask = mask; key.packed = g.packed.p; key.max_depth = param_.max_depth;
+    key.max_leaves = param_.max_leaves; key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
+    key.mcw = param_.min_child_weight; key.mds = param_.max_delta_step; key.world = Comm::get().world(); key.n = dtrain->n;
+    if (!tg.exec || memcmp(&tg.key, &key, sizeof key) != 0) {
+      if (tg.exec) { cudaGraphExecDestroy(tg.exec); tg.exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      const long long launches_before = g_kernel_launches;
+      CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try { enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p); }
+      catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+      CUDA_OK(cudaStreamEndCapture(s, &graph));
+      CUDA_OK(cudaGraphInstantiate(&tg.exec, graph, 0));
+      CUDA_OK(cudaGraphDestroy(graph));
+      tg.key = key; tg.launches = g_kernel_launches - launches_before;
+      g_kernel_launches = launches_before;               // capture enqueued nothing
+    }
+    CUDA_OK(cudaGraphLaunch(tg.exec, s));
+    g_kernel_launches += tg.launches;
+  }
 
   // ---- hand the finished tree to the model: device copy for prediction, async host copy for model IO
   const size_t need = d_nodes_used + (size_t)g.cap_nodes;
@@ -657,8 +700,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     CUDA_OK(cudaStreamSynchronize(s));
     std::swap(nb.p, d_nodes.p); std::swap(nb.n, d_nodes.n);
   }
-  pack_tree_kernel<<<(g.cap_nodes + 255) / 256, 256, 0, s>>>(g.ta, g.gs.n_nodes, d_nodes.p + d_nodes_used, g.cap_nodes); ++g_kernel_launches;
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(d_nodes.p + d_nodes_used, g.packed.p, sizeof(DevNode) * (size_t)g.cap_nodes, cudaMemcpyDeviceToDevice, s));
   if (pending_.size() - (size_t)std::count_if(pending_.begin(), pending_.end(), [](const PendingTree& p) { return p.staging == nullptr; }) >= 512) sync_model();
   PendingTree pt; pt.cap_nodes = (size_t)g.cap_nodes;
   pt.staging = g.pinned.take(g.tree_block_bytes);
@@ -669,7 +711,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   append_device_tree(k, d_nodes_used, g.cap_nodes, pt);
   d_nodes_used += (size_t)g.cap_nodes;
   d_trees_uploaded = 0;                      // offsets/info arrays need a refresh before the next predict
-  cache.trees_applied = (int)trees_.size();  // the partition passes already added this tree's leaves to the cache
+  cache.trees_applied = (int)trees_.size();  // update_margin_kernel already added this tree's leaves to the cache
 }
 
 void Booster::boost_one_iter(DMatrix*, const float*, const float*, size_t) {
@@ -789,6 +831,7 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   if (!grower_) grower_ = new GrowerImpl();
   GrowerImpl& g = *grower_;
   g.ensure(dm->n, dm->ngroups, param_.max_depth, param_.num_class);
+  hist_configure();
   CUDA_OK(cudaMemcpyAsync(g.gpair.p, gpair_host, sizeof(float2) * dm->n, cudaMemcpyHostToDevice, s));
   // scales from max|g|, max h of the supplied pairs
   float mg = 0.f, mh = 0.f;

@@ -135,6 +135,7 @@ class Booster {
   void bring_cache_up_to_date(DMatrix* dm, PredCache& c);
   void append_device_tree(int class_id, size_t device_offset, int max_nodes, PendingTree pt);
   void grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_index);
+  void enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned char* mask, DevNode* packed_out);
   void prof_begin(int level);
   void prof_end();
   JPtr model_to_json();

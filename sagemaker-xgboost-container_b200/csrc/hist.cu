@@ -218,13 +218,15 @@ int hist_grid_x(int num_sms, int ngroups) {
   return x > 0 ? x : 1;
 }
 
-void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream) {
+void hist_configure() {
   static bool configured = false;
-  if (!configured) {
-    CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPlaneBytes));
-    CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<2, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPlaneBytes));
-    configured = true;
-  }
+  if (configured) return;
+  CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPlaneBytes));
+  CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<2, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPlaneBytes));
+  configured = true;
+}
+
+void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream) {
   if (a.ngroups == 1) {
     hist_build_kernel<1, 256><<<dim3(grid_x, 1), 256, 2 * kPlaneBytes, stream>>>(a);
   } else {

@@ -48,6 +48,7 @@ struct HistArgs {
 
 void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream);
 int hist_grid_x(int num_sms, int ngroups);
+void hist_configure();     // one-time function attributes (must happen outside stream capture)
 void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s);
 void launch_scales(const GrowState& gs, cudaStream_t s);
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s);
