@@ -53,10 +53,10 @@ __device__ __forceinline__ void red_global_s64(long long* p, long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
-struct LaneConst { unsigned sel[4], offb[4], offw[4]; int q, half, qw; };
+struct LaneConst { unsigned sel[4], offb[4], offw[4]; int qw; int rowlane; int colbyte; };
 
 // 16 conflict-free (g,h) atomic pairs of one lane's 16 bin bytes into the planes at smem byte offset `plane`
-__device__ __forceinline__ void accumulate16(const LaneConst& lc, const uint4& w, int gq, unsigned hq, unsigned plane) {
+__device__ __forceinline__ void accumulate16(const LaneConst& lc, const uint4& w, int gq, unsigned hq) {
   unsigned w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
   if (lc.qw & 1) { unsigned x = w0; w0 = w1; w1 = w2; w2 = w3; w3 = x; }
   if (lc.qw & 2) { unsigned x = w0; w0 = w2; w2 = x; x = w1; w1 = w3; w3 = x; }
@@ -66,7 +66,7 @@ __device__ __forceinline__ void accumulate16(const LaneConst& lc, const uint4& w
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
       unsigned bin = __byte_perm(ww[jw], 0u, lc.sel[jb]);
-      unsigned addr = (bin << 7) + lc.offw[jw] + lc.offb[jb] + plane;
+      unsigned addr = (bin << 7) + lc.offw[jw] + lc.offb[jb];
       red_shared_s32(addr, gq);
       red_shared_u32_h(addr, hq);
     }
@@ -74,7 +74,7 @@ __device__ __forceinline__ void accumulate16(const LaneConst& lc, const uint4& w
 }
 
 struct Stage { unsigned id; float2 gh; };
-struct Rows { uint4 a0, a1, b0, b1; };                      // tile A / tile B, group 0 / group 1
+template <int NSUB> struct Rows { uint4 w[NSUB]; };         // one 16 B chunk per sub-tile of the 32-position super-tile
 
 // Spill / flush pass over the CTA's accumulators.  Between windows only accumulators that could overflow in the next
 // window leave for the global int64 histogram (sparse RED.ADD.64); `last` flushes everything that is non-zero.
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(H
   if (nb <= 0) return;
   const unsigned T = a.build_prefix[nb];
   if (T == 0) return;
-  if (a.rows_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.rows_counter, (unsigned long long)T);
+  if (a.rows_counter && blockIdx.x == 0 && a.group_base + blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.rows_counter, (unsigned long long)T);
   const unsigned C = gridDim.x;
   unsigned ceff = (T + kMinRowsPerCta - 1) / kMinRowsPerCta;
   ceff = ceff < 1 ? 1 : (ceff > C ? C : ceff);
@@ -122,20 +122,29 @@ __global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(H
   if (r0l >= T) return;
   unsigned r0 = (unsigned)r0l;
   unsigned r1 = (unsigned long long)r0 + chunk > T ? T : r0 + chunk;
-  const int g0 = blockIdx.y * NG;
-  const bool two = NG == 2 && (g0 + 1 < a.ngroups);
-  const int ng_here = two ? 2 : 1;
+  const int g0 = a.group_base + blockIdx.y * NG;
+  const int ng_here = NG;
   const uint8_t* gbins = a.bins + (int64_t)g0 * kSlots;
   const float sg = a.scales[0], sh = a.scales[1];
   const unsigned smem_g = (unsigned)__cvta_generic_to_shared(smem);
   const int64_t row_stride = (int64_t)a.row_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  // Lane roles.  NG == 1: two lanes per row (16 B halves of the 32 B slice), 16 rows per LDG.128 instruction.
+  // NG == 2: four lanes per row (16 B chunks of the row's 64 B = group A low/high, group B low/high), 8 rows per
+  // instruction, so an instruction touches each 64 B burst exactly once (half the L1 wavefronts of two 32 B loads).
+  // `rot` is the per-lane rotation of the 16-step slot schedule: the 16 lanes that share a bank range (same `half`)
+  // get 16 different rotations, so every ATOMS instruction hits 32 distinct banks.
+  constexpr int NSUB = NG == 2 ? 4 : 2;               // sub-tiles per 32-position super-tile
+  constexpr int SUBROWS = 32 / NSUB;
   LaneConst lc;
-  { lc.q = lane >> 1; lc.half = lane & 1; lc.qw = lc.q >> 2; const int qb = lc.q & 3;
+  { int rot, half; unsigned plane;
+    if (NG == 2) { const int q8 = lane >> 2, c = lane & 3; rot = 2 * q8 + (c >> 1); half = c & 1; plane = (unsigned)(c >> 1) * 2u * kPlaneBytes; lc.rowlane = q8; lc.colbyte = c * 16; }
+    else { rot = lane >> 1; half = lane & 1; plane = 0u; lc.rowlane = lane >> 1; lc.colbyte = half * 16; }
+    lc.qw = rot >> 2; const int qb = rot & 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { lc.sel[j] = 0x4440u | (unsigned)((j + qb) & 3); lc.offb[j] = 4u * (unsigned)((j + qb) & 3);
-      lc.offw[j] = smem_g + 64u * (unsigned)lc.half + 16u * (unsigned)((j + lc.qw) & 3); } }
+      lc.offw[j] = smem_g + plane + 64u * (unsigned)half + 16u * (unsigned)((j + lc.qw) & 3); } }
 
   const int entries = ng_here * 2 * kGroupEntries;
   for (int i = threadIdx.x; i < entries / 4; i += NTHREADS) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
@@ -167,30 +176,30 @@ __global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(H
       if (st < nsuper && p < pb) { s_.id = a.ridx ? __ldg(a.ridx + p) : p; s_.gh = ldg_nc_f2(a.gpair + p); }
       return s_;
     };
-    auto load_rows = [&](unsigned ids, Rows& r) {
-      unsigned rA = __shfl_sync(0xffffffffu, ids, lc.q), rB = __shfl_sync(0xffffffffu, ids, 16 + lc.q);
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      r.a0 = r.a1 = r.b0 = r.b1 = z;
-      if (rA != 0xffffffffu) { const uint8_t* p = gbins + (int64_t)rA * row_stride + lc.half * 16; r.a0 = ldg_nc_v4(p); if (NG == 2 && two) r.a1 = ldg_nc_v4(p + 32); }
-      if (rB != 0xffffffffu) { const uint8_t* p = gbins + (int64_t)rB * row_stride + lc.half * 16; r.b0 = ldg_nc_v4(p); if (NG == 2 && two) r.b1 = ldg_nc_v4(p + 32); }
+    auto load_rows = [&](unsigned ids, Rows<NSUB>& r) {
+#pragma unroll
+      for (int t = 0; t < NSUB; ++t) {
+        const unsigned rid = __shfl_sync(0xffffffffu, ids, t * SUBROWS + lc.rowlane);
+        r.w[t] = rid != 0xffffffffu ? ldg_nc_v4(gbins + (int64_t)rid * row_stride + lc.colbyte) : make_uint4(0, 0, 0, 0);
+      }
     };
     Stage cur = load_ids(warp);
     Stage nxt = load_ids(warp + NWARPS);
-    Rows rows; load_rows(cur.id, rows);
+    Rows<NSUB> rows; load_rows(cur.id, rows);
     for (unsigned it = 0; it < iters; ++it) {
       const unsigned s = warp + it * NWARPS;
       Stage nn = load_ids(s + 2 * NWARPS);
-      Rows nrows; load_rows(nxt.id, nrows);
+      Rows<NSUB> nrows; load_rows(nxt.id, nrows);
       if (s < nsuper) {
         const int gq_l = __float2int_rn(cur.gh.x * sg);
         const unsigned hq_l = (unsigned)__float2int_rn(cur.gh.y * sh);
         accG += gq_l; accH += hq_l;
-        const int gA = __shfl_sync(0xffffffffu, gq_l, lc.q), gB = __shfl_sync(0xffffffffu, gq_l, 16 + lc.q);
-        const unsigned hA = __shfl_sync(0xffffffffu, hq_l, lc.q), hB = __shfl_sync(0xffffffffu, hq_l, 16 + lc.q);
-        accumulate16(lc, rows.a0, gA, hA, 0u);
-        if (NG == 2 && two) accumulate16(lc, rows.a1, gA, hA, 2u * kPlaneBytes);
-        accumulate16(lc, rows.b0, gB, hB, 0u);
-        if (NG == 2 && two) accumulate16(lc, rows.b1, gB, hB, 2u * kPlaneBytes);
+#pragma unroll
+        for (int t = 0; t < NSUB; ++t) {
+          const int gq = __shfl_sync(0xffffffffu, gq_l, t * SUBROWS + lc.rowlane);
+          const unsigned hq = __shfl_sync(0xffffffffu, hq_l, t * SUBROWS + lc.rowlane);
+          accumulate16(lc, rows.w[t], gq, hq);
+        }
       }
       rows = nrows; cur = nxt; nxt = nn;
       if ((it + 1) % kItersPerWindow == 0 && it + 1 < iters) {       // overflow check: at most 4096 rows since the last one
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(H
     __syncthreads();
     spill_pass<NTHREADS>(smem, ng_here, out, true);
     __syncthreads();
-    if (a.accumulate_sum && blockIdx.y == 0) {
+    if (a.accumulate_sum && g0 == 0) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { accG += __shfl_xor_sync(0xffffffffu, accG, o); accH += __shfl_xor_sync(0xffffffffu, accH, o); }
       if (lane == 0 && (accG != 0 || accH != 0)) { red_global_s64(&a.node_sum[nid].g, accG); red_global_s64(&a.node_sum[nid].h, accH); }
@@ -213,8 +222,8 @@ __global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(H
 
 int hist_grid_x(int num_sms, int ngroups) {
   if (ngroups == 1) return num_sms * 3;
-  const int sets = (ngroups + 1) / 2;
-  const int x = (num_sms + sets - 1) / sets;
+  const int pairs = ngroups / 2;
+  const int x = (num_sms + pairs - 1) / pairs;
   return x > 0 ? x : 1;
 }
 
@@ -226,14 +235,19 @@ void hist_configure() {
   configured = true;
 }
 
-void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream) {
-  if (a.ngroups == 1) {
-    hist_build_kernel<1, 256><<<dim3(grid_x, 1), 256, 2 * kPlaneBytes, stream>>>(a);
-  } else {
-    hist_build_kernel<2, 768><<<dim3(grid_x, (a.ngroups + 1) / 2), 768, 4 * kPlaneBytes, stream>>>(a);
+void launch_hist_build(const HistArgs& a_in, int grid_x, cudaStream_t stream) {
+  HistArgs a = a_in;
+  const int pairs = a.ngroups / 2;
+  if (pairs > 0) {
+    a.group_base = 0;
+    hist_build_kernel<2, 768><<<dim3(grid_x, pairs), 768, 4 * kPlaneBytes, stream>>>(a); ++g_kernel_launches;
+    CUDA_OK(cudaGetLastError());
   }
-  ++g_kernel_launches;
-  CUDA_OK(cudaGetLastError());
+  if (a.ngroups & 1) {                       // single (or odd last) group: 64 KB CTAs, three per SM
+    a.group_base = a.ngroups - 1;
+    hist_build_kernel<1, 256><<<dim3(pairs > 0 ? grid_x : hist_grid_x(148, 1), 1), 256, 2 * kPlaneBytes, stream>>>(a); ++g_kernel_launches;
+    CUDA_OK(cudaGetLastError());
+  }
 }
 
 }  // namespace b200

@@ -42,6 +42,7 @@ struct HistArgs {
   GH64* hist_pool;              // slot stride = ngroups * kGroupEntries
   GH64* node_sum;               // per nid, accumulated only when accumulate_sum
   int ngroups;
+  int group_base;               // first group handled by blockIdx.y == 0 (set by the launcher)
   int accumulate_sum;
   unsigned long long* rows_counter;   // optional: += rows processed by this launch (profiling)
 };
