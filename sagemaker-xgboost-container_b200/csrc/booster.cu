@@ -644,7 +644,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   }
 
   // prediction cache += leaf values of this tree: one row-order pass over the column-major bins
-  launch_update_margin(g.ta, bm.bins_col, bm.n, bm.has_missing, margin, K, k, s);
+  launch_update_margin(g.ta, g.gs.n_nodes, bm.bins_col, bm.n, bm.has_missing, margin, K, k, s);
 
   pack_tree_kernel<<<(g.cap_nodes + 255) / 256, 256, 0, s>>>(g.ta, g.gs.n_nodes, packed_out, g.cap_nodes); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());

@@ -310,35 +310,62 @@ __global__ void __launch_bounds__(256) part_count_kernel(PartArgs a) {
 }
 
 // Prediction-cache update of a finished tree: one streaming pass in ROW order over the column-major bins
-// (coalesced, no scattered read-modify-write of the cache).
-__global__ void __launch_bounds__(256) update_margin_kernel(TreeArrays t, const uint8_t* bins_col, int64_t n, int has_missing,
+// (coalesced, no scattered read-modify-write of the cache).  The tree is packed into shared memory first
+// (8 B per node) so that a traversal step costs one LDS + one global byte load.
+struct PackedNode { unsigned short feat_dl; unsigned short bin_plus1; unsigned short left, right; };   // feat | dl << 15; left == 0xffff: leaf
+constexpr int kPackedNodesSmem = 2048;
+
+__global__ void __launch_bounds__(256) update_margin_kernel(TreeArrays t, const int* n_nodes, const uint8_t* bins_col, int64_t n, int has_missing,
                                                             float* margin, int K, int k) {
+  __shared__ PackedNode s_nodes[kPackedNodesSmem];
+  __shared__ float s_leaf[kPackedNodesSmem];
+  const int nn = *n_nodes;
+  const bool packed = nn <= kPackedNodesSmem && nn < 0xffff;
+  if (packed) {
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+      PackedNode p; p.feat_dl = (unsigned short)(t.split_index[i] | (t.default_left[i] ? 0x8000 : 0)); p.bin_plus1 = (unsigned short)(t.split_bin[i] + 1);
+      const int l = t.left[i]; p.left = l < 0 ? 0xffff : (unsigned short)l; p.right = l < 0 ? 0xffff : (unsigned short)t.right[i];
+      s_nodes[i] = p; s_leaf[i] = t.split_cond[i];
+    }
+    __syncthreads();
+  }
   // four independent traversals per thread (rows r, r+256, r+512, r+768 of the block's 1024-row tile): 4 loads in flight
   const int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x;
   int nid[4]; bool done[4];
+  const bool root_leaf = packed ? (s_nodes[0].left == 0xffff) : (t.left[0] == -1);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { nid[j] = 0; done[j] = (base + j * 256 >= n) || t.left[0] == -1; }
+  for (int j = 0; j < 4; ++j) { nid[j] = 0; done[j] = (base + j * 256 >= n) || root_leaf; }
   bool any = !(done[0] && done[1] && done[2] && done[3]);
   while (any) {
     int byte[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) byte[j] = done[j] ? 0 : bins_col[(int64_t)t.split_index[nid[j]] * n + base + j * 256];
+    for (int j = 0; j < 4; ++j) {
+      const int f = packed ? (int)(s_nodes[nid[j]].feat_dl & 0x7fff) : t.split_index[nid[j]];
+      byte[j] = done[j] ? 0 : bins_col[(int64_t)f * n + base + j * 256];
+    }
     any = false;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (done[j]) continue;
       const int nd = nid[j];
-      const bool left = (has_missing && byte[j] == kMissingBin) ? (t.default_left[nd] != 0) : (byte[j] <= t.split_bin[nd]);
-      nid[j] = left ? t.left[nd] : t.right[nd];
-      done[j] = t.left[nid[j]] == -1;
+      if (packed) {
+        const PackedNode p = s_nodes[nd];
+        const bool left = (has_missing && byte[j] == kMissingBin) ? ((p.feat_dl & 0x8000) != 0) : (byte[j] < (int)p.bin_plus1);
+        nid[j] = left ? p.left : p.right;
+        done[j] = s_nodes[nid[j]].left == 0xffff;
+      } else {
+        const bool left = (has_missing && byte[j] == kMissingBin) ? (t.default_left[nd] != 0) : (byte[j] <= t.split_bin[nd]);
+        nid[j] = left ? t.left[nd] : t.right[nd];
+        done[j] = t.left[nid[j]] == -1;
+      }
       any |= !done[j];
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { const int64_t r = base + j * 256; if (r < n) margin[r * K + k] += t.split_cond[nid[j]]; }
+  for (int j = 0; j < 4; ++j) { const int64_t r = base + j * 256; if (r < n) margin[r * K + k] += packed ? s_leaf[nid[j]] : t.split_cond[nid[j]]; }
 }
 
-__global__ void __launch_bounds__(256) part_scan_kernel(PartArgs a) {
+__global__ void __launch_bounds__(1024) part_scan_kernel(PartArgs a) {
   __shared__ unsigned s_tmp[33];
   const GrowState& gs = a.gs;
   const int cnt = gs.level_count[a.level];
@@ -366,34 +393,43 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(PartArgs a) {
   const unsigned lt = tile - gs.tile_prefix[i];
   const unsigned b = gs.seg_begin[nid], c = gs.seg_count[nid];
   const unsigned p0 = b + lt * kPartTile, p1 = (b + c < p0 + kPartTile) ? b + c : p0 + kPartTile;
+  const unsigned nrows = p1 - p0;
   const unsigned nl = gs.seg_count[a.tree.left[nid]];
   const unsigned toff = gs.tile_off[tile];
   const unsigned pt = p0 + threadIdx.x * 8;
+  __shared__ unsigned s_rid[kPartTile];
+  __shared__ float2 s_gp[kPartTile];
+  __shared__ unsigned s_w[8];
   unsigned rows[8]; float2 gp[8]; unsigned char fl[8]; unsigned mine = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     unsigned p = pt + j;
     if (p < p1) { rows[j] = a.ridx_cur ? a.ridx_cur[p] : p; gp[j] = a.gp_cur[p]; fl[j] = gs.flags[p]; mine += fl[j]; } else { rows[j] = 0; gp[j] = make_float2(0.f, 0.f); fl[j] = 2; }
   }
-  __shared__ unsigned s_w[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned x = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
   if (lane == 31) s_w[warp] = x;
   __syncthreads();
-  unsigned woff = 0;
-  for (int w = 0; w < warp; ++w) woff += s_w[w];
+  unsigned woff = 0, tile_left = 0;
+  for (int w = 0; w < 8; ++w) { if (w < warp) woff += s_w[w]; tile_left += s_w[w]; }
   unsigned lbefore = woff + x - mine;               // lefts before my first position inside the tile
+  // stable compaction inside shared memory: [lefts | rights]
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (fl[j] == 2) continue;
-    unsigned jj = threadIdx.x * 8 + j;              // position inside the tile
-    unsigned dest;
-    if (fl[j]) { dest = b + toff + lbefore; ++lbefore; }
-    else dest = b + nl + (lt * kPartTile + jj - toff - lbefore);
-    a.ridx_next[dest] = rows[j];
-    a.gp_next[dest] = gp[j];
+    unsigned jj = threadIdx.x * 8 + j;
+    unsigned slot = fl[j] ? lbefore++ : tile_left + (jj - lbefore);
+    s_rid[slot] = rows[j]; s_gp[slot] = gp[j];
+  }
+  __syncthreads();
+  // lefts go to [b + toff, ...), rights to [b + nl + (tile start - toff), ...): two contiguous, coalesced streams
+  const unsigned dl = b + toff, dr = b + nl + (lt * kPartTile - toff);
+  for (unsigned k = threadIdx.x; k < nrows; k += blockDim.x) {
+    unsigned dest = k < tile_left ? dl + k : dr + (k - tile_left);
+    a.ridx_next[dest] = s_rid[k];
+    a.gp_next[dest] = s_gp[k];
   }
 }
 
@@ -436,13 +472,13 @@ void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s) {
 void launch_apply(const ApplyArgs& a, cudaStream_t s) { apply_kernel<<<1, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s) {
   part_count_kernel<<<max_tiles, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
-  part_scan_kernel<<<max_nodes_level, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+  part_scan_kernel<<<max_nodes_level, 1024, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
   part_scatter_kernel<<<max_tiles, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
   build_prefix_kernel<<<1, 256, 0, s>>>(a.gs); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
-void launch_update_margin(const TreeArrays& t, const uint8_t* bins_col, int64_t n, int has_missing, float* margin, int K, int k, cudaStream_t s) {
+void launch_update_margin(const TreeArrays& t, const int* n_nodes, const uint8_t* bins_col, int64_t n, int has_missing, float* margin, int K, int k, cudaStream_t s) {
   if (n == 0) return;
-  update_margin_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(t, bins_col, n, has_missing, margin, K, k); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+  update_margin_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(t, n_nodes, bins_col, n, has_missing, margin, K, k); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s) {
   dim3 grid(max_build, 8 * ngroups); subtract_kernel<<<grid, 256, 0, s>>>(gs, pool, ngroups); ++g_kernel_launches; CUDA_OK(cudaGetLastError());

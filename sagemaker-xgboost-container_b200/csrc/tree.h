@@ -55,7 +55,7 @@ void launch_scales(const GrowState& gs, cudaStream_t s);
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s);
 void launch_apply(const ApplyArgs& a, cudaStream_t s);
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s);
-void launch_update_margin(const TreeArrays& t, const uint8_t* bins_col, int64_t n, int has_missing, float* margin, int K, int k, cudaStream_t s);
+void launch_update_margin(const TreeArrays& t, const int* n_nodes, const uint8_t* bins_col, int64_t n, int has_missing, float* margin, int K, int k, cudaStream_t s);
 void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s);
 
 }  // namespace b200
