@@ -665,7 +665,9 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   }
   g.packed.ensure((size_t)g.cap_nodes);
   static const bool no_graph = getenv("B200XGB_NO_GRAPH") != nullptr;
-  if (profile_ || no_graph) {
+  // Graph replay is used on a single GPU only: capturing NCCL collectives (lazy channel set-up inside a capture) hung an
+  // 8-rank run in round 1, so multi-rank training issues the same sequence directly until that is understood.
+  if (profile_ || no_graph || Comm::get().distributed()) {
     enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p);
   } else {
     if ((int)g.graphs.size() <= k) g.graphs.resize(k + 1);
