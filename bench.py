@@ -210,7 +210,8 @@ def run_reference(a):
         "impl": "reference", "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64 histograms over f32 gradients", "data": "synthetic",
-        "config": {"workload": "synthetic %dx%d %s hist max_bin=%d max_depth=%d" % (a.rows, a.cols, a.objective, a.max_bin, a.max_depth)},
+        "config": {"workload": "synthetic %dx%d %s hist max_bin=%d max_depth=%d" % (a.rows, a.cols, a.objective, a.max_bin, a.max_depth),
+                   "params": params_of(a)},
         "cpu_baseline": {"value": value, "unit": "rounds/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": e2e, "unit": "rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -291,8 +292,14 @@ def main():
     achieved = root_bytes / (root_ms * 1e-3) / 1e9 if root_ms > 0 else 0.0
     deep_bytes = prof["deep_hist_rows"] * (F + 8 + 4)          # deeper levels also read a 4 B row id per row
     all_gbs = (prof["root_hist_rows"] * (F + 8) + deep_bytes) / ((prof["root_hist_ms"] + prof["deep_hist_ms"]) * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_hist_root_traffic.json")
+    if os.path.exists(tp) and world == 1:
+        tj = json.load(open(tp))
+        if tj.get("workload") == "synthetic %dx%d" % (a.rows, a.cols):
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # per launch, from the committed ncu capture
     roofline = {"bound": "hbm", "kernel": "hist_build_kernel (root launch, all rows of the rank)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": root_bytes, "ms_per_launch": root_ms,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": root_bytes, "ms_per_launch": root_ms,
                 "all_hist_launches_gbs": all_gbs, "all_hist_launches_frac": all_gbs / peak,
                 "hist_share_of_step": (prof["root_hist_ms"] + prof["deep_hist_ms"]) / PROFILE_ROUNDS / (ms / a.steps),
                 "timing": "CUDA events around each hist launch over %d rounds run right after the timed region (direct launches; the timed region replays CUDA graphs)" % PROFILE_ROUNDS}
