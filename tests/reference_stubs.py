@@ -38,12 +38,19 @@ def install(xgb_pkg):
         class UnsupportedFormatError(Exception):
             pass
         er = _mod("sagemaker_containers._errors", UnsupportedFormatError=UnsupportedFormatError, ClientError=Exception)
-        rio = _mod("sagemaker_containers._recordio", _write_recordio=lambda *a, **k: None)
+        rio = _mod("sagemaker_containers._recordio", _write_recordio=lambda *a, **k: None, _read_recordio=lambda *a, **k: iter(()))
         pb = _mod("sagemaker_containers.record_pb2", Record=type("Record", (), {}))
         _mod("sagemaker_containers", _content_types=ct, _errors=er, _recordio=rio, record_pb2=pb)
     for name in ("dask", "dask.distributed", "dask.array", "dask.dataframe"):
         if name not in sys.modules:
-            _mod(name, Client=object)
+            _mod(name, Client=object, Array=type("Array", (), {}), DataFrame=type("DataFrame", (), {}))
+    # only needed by the reference's test helpers (test/utils/local_mode.py), never by the hot path
+    if "boto3" not in sys.modules:
+        _mod("boto3", client=lambda *a, **k: None, Session=object)
+        be = _mod("botocore.exceptions", ClientError=Exception)
+        _mod("botocore", exceptions=be)
+        sm = _mod("sagemaker", fw_utils=_mod("sagemaker.fw_utils"), utils=_mod("sagemaker.utils"))
+        del sm
     if REFERENCE_SRC not in sys.path:
         sys.path.insert(0, REFERENCE_SRC)
     # algorithm_mode/__init__.py only pre-loads the serving model (and drags in flask/gunicorn): register the package

@@ -1,0 +1,44 @@
+"""Run the REFERENCE's own unit tests (unmodified, read from /root/reference/test/unit) against this package bound as
+`xgboost` -- boundary conformance ("the reference's unit tests for loaders / checkpointing / feval are
+reusable as boundary conformance tests").  CPU only, oracle-backed engine via tests/reference_plugin.py; skipped where the
+reference tree is not mounted (e.g. on the GPU box).  recordio-protobuf cases are deselected: `sagemaker_containers.record_pb2`
+is not installed in this image and the format is out of scope."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+import reference_stubs
+
+pytestmark = pytest.mark.skipif(not reference_stubs.reference_available(), reason="/root/reference is not mounted here")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UNIT = "/root/reference/test/unit"
+
+CASES = [
+    ("test_checkpointing.py", None, 8),                       # xgb.train + checkpoint callbacks + resume (test_checkpointing.py:164-244)
+    ("test_data_utils.py", "not protobuf", 17),               # CSV / libsvm / parquet -> DMatrix shapes, pipe-mode errors
+    ("test_encoder.py", "not protobuf", 18),                  # serving payload -> DMatrix
+    ("test_distributed.py", None, 6),                         # multi-process Rabit / tracker / collective.broadcast
+    ("algorithm_mode/test_custom_metrics.py", None, 25),      # feval on raw margins with DMatrix.get_label
+    ("algorithm_mode/test_train_utils.py", None, 3),
+    ("algorithm_mode/test_serve_utils.py", "not protobuf", 50),   # get_loaded_booster, predict, selectable inference
+    ("test_prediction_utils.py", None, 9),
+]
+
+
+@pytest.mark.parametrize("path,deselect,min_passed", CASES)
+def test_reference_unit_file_passes_on_this_package(path, deselect, min_passed):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, "/root/reference", "/root/reference/src"])
+    cmd = [sys.executable, "-m", "pytest", "--noconftest", "-c", os.devnull, "-p", "reference_plugin", "-q", "--no-header", "-p", "no:cacheprovider",
+           "--rootdir", "/tmp", os.path.join(UNIT, path)]
+    if deselect:
+        cmd += ["-k", deselect]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    tail = (r.stdout + r.stderr)[-3000:]
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert r.returncode == 0, tail
+    assert " failed" not in r.stdout.splitlines()[-1], tail
+    assert m and int(m.group(1)) >= min_passed, tail
