@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predict", action="store_true")
     return ap.parse_args()
 
 
@@ -217,6 +218,38 @@ def run_reference(a):
     }))
 
 
+def predict_section(xgb, be, device, peak):
+    """BASELINE config 5 (second half of the metric: predict rows/sec): Booster.predict on a 1M x 28 batch with a
+    binary:logistic model -- device-resident DMatrix (value) and from host numpy through the public API (e2e)."""
+    import torch
+    n, F, rounds, reps = 1_000_000, 28, 50, 10
+    X, y = gen_block_torch(7, n, F, 45, "binary:logistic", 1, device)
+    bst = xgb.train({"objective": "binary:logistic", "tree_method": "hist", "max_depth": 6, "max_bin": 256, "eta": 0.3},
+                    xgb.DMatrix(X, label=y.cpu().numpy()), num_boost_round=rounds, verbose_eval=False)
+    d = xgb.DMatrix(X)
+    Xh = torch.empty(X.shape, dtype=torch.float32, pin_memory=True)
+    Xh.copy_(X)
+    Xn = Xh.numpy()
+    p0 = bst.predict(d)
+    be.synchronize()
+    be.timer_start()
+    for _ in range(reps):
+        p = bst.predict(d)                       # predict kernel + transform + D2H of the n results
+    ms = be.timer_stop() / reps
+    t0 = time.perf_counter()
+    for _ in range(3):
+        p2 = bst.predict(xgb.DMatrix(Xn))        # H2D of the batch + predict + D2H
+    e2e_s = (time.perf_counter() - t0) / 3
+    leaves = bst.predict(d, pred_leaf=True)
+    alg = n * F * 4 + n * 4
+    return {"workload": "Booster.predict, %dx%d float32 batch, binary:logistic, %d trees depth 6" % (n, F, rounds),
+            "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_call": ms,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                         "note": "call time includes the output transform and the D2H of the result; model is L2 resident"},
+            "e2e": {"value": n / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(Xn.nbytes), "d2h_bytes_per_step": int(p2.nbytes)},
+            "consistent": bool(np.array_equal(p, p0) and np.array_equal(p2, p0)), "pred_leaf_shape": list(leaves.shape)}
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
@@ -346,6 +379,10 @@ def main():
         cpu = {"value": rps * len(xs) / a.rows, "unit": "rounds/s", "cores": cores, "kind": "port",
                "sample": "first %d of %d rows, 3 timed rounds after 1 warm-up, scaled linearly in rows" % (len(xs), a.rows)}
 
+    predict = None
+    if rank == 0 and world == 1 and not a.no_predict:
+        predict = predict_section(xgb, be, device, peak)
+
     if rank == 0:
         out = {
             "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -355,7 +392,7 @@ def main():
                        "rows_per_gpu": (a.rows + world - 1) // world, "parallelism": "rows sharded x%d, per-level int64 histogram NCCL all-reduce" % world,
                        "l2": "inputs (%.1f GB of bins per GPU) exceed the 126 MB L2" % ((r1 - r0) * 32 * ((a.cols + 31) // 32) / 1e9),
                        "params": params},
-            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "predict": predict,
         }
         print(json.dumps(out))
     if dist is not None:
