@@ -271,7 +271,7 @@ struct GrowerImpl {
   DevBuf<float2> gpair, gp0, gp1; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
-  DevBuf<DevNode> packed; std::vector<TreeGraph> graphs;
+  DevBuf<DevNode> packed; std::vector<TreeGraph> graphs; std::vector<char> eager_done;
   int hist_grid_x = 1;
 
   void ensure(int64_t n_, int ngroups_, int max_depth_, int K) {
@@ -667,7 +667,14 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   static const bool no_graph = getenv("B200XGB_NO_GRAPH") != nullptr;
   // Graph replay is used on a single GPU only: capturing NCCL collectives (lazy channel set-up inside a capture) hung an
   // 8-rank run in round 1, so multi-rank training issues the same sequence directly until that is understood.
-  if (profile_ || no_graph || Comm::get().distributed()) {
+  // B200XGB_GRAPH_MULTI=1 (experiment knob): capture also with NCCL, but only after each class has run one tree eagerly
+  // so that every collective of the sequence has already set up its channels outside a capture.
+  static const bool graph_multi = getenv("B200XGB_GRAPH_MULTI") != nullptr;
+  const bool dist = Comm::get().distributed();
+  if ((int)g.eager_done.size() <= k) g.eager_done.resize(k + 1, 0);
+  const bool eager_first = dist && graph_multi && !g.eager_done[k];
+  if (profile_ || no_graph || (dist && !graph_multi) || eager_first) {
+    g.eager_done[k] = 1;
     enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p);
   } else {
     if ((int)g.graphs.size() <= k) g.graphs.resize(k + 1);

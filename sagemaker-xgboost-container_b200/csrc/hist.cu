@@ -21,6 +21,7 @@
 //    spilled to the global int64 histogram with RED.ADD.64 (sparse), and everything is flushed at the
 //    end of the CTA's node portion.  Sums are exact integers => bit-reproducible for any grid size,
 //    block schedule or GPU count, and the NCCL all-reduce of the int64 histograms is order-independent.
+#include <cstdlib>
 #include "engine.h"
 #include "tree.h"
 
@@ -232,15 +233,20 @@ void hist_configure() {
   if (configured) return;
   CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPlaneBytes));
   CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<2, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPlaneBytes));
+  CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPlaneBytes));
   configured = true;
 }
 
 void launch_hist_build(const HistArgs& a_in, int grid_x, cudaStream_t stream) {
   HistArgs a = a_in;
   const int pairs = a.ngroups / 2;
+  // experiment knob for the next round: 32 warps/SM at 64 registers (small spills) instead of 24 warps at 80
+  static const bool wide = getenv("B200XGB_HIST_THREADS") != nullptr && atoi(getenv("B200XGB_HIST_THREADS")) == 1024;
   if (pairs > 0) {
     a.group_base = 0;
-    hist_build_kernel<2, 768><<<dim3(grid_x, pairs), 768, 4 * kPlaneBytes, stream>>>(a); ++g_kernel_launches;
+    if (wide) hist_build_kernel<2, 1024><<<dim3(grid_x, pairs), 1024, 4 * kPlaneBytes, stream>>>(a);
+    else hist_build_kernel<2, 768><<<dim3(grid_x, pairs), 768, 4 * kPlaneBytes, stream>>>(a);
+    ++g_kernel_launches;
     CUDA_OK(cudaGetLastError());
   }
   if (a.ngroups & 1) {                       // single (or odd last) group: 64 KB CTAs, three per SM
