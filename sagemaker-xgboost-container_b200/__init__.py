@@ -7,10 +7,11 @@ run unchanged on top of the CUDA engine.
 """
 import sys
 
-from . import callback, collective, core, tracker, training  # noqa: F401
+from . import callback, collective, core, sklearn, tracker, training  # noqa: F401
 from .backend import XGBoostError, get_backend  # noqa: F401
 from .core import Booster, DMatrix  # noqa: F401
-from .training import train  # noqa: F401
+from .training import cv, train  # noqa: F401
+from .sklearn import XGBClassifier, XGBModel, XGBRegressor  # noqa: F401
 
 __version__ = "3.0.5"        # API level mirrored (docker/3.0-5/base/Dockerfile.cpu:33 pins xgboost==3.0.5)
 
@@ -23,6 +24,6 @@ def install_as_xgboost():
     """Alias this package as `xgboost` (+ the submodules the container imports) in sys.modules."""
     me = sys.modules[__name__]
     sys.modules["xgboost"] = me
-    for sub in ("core", "callback", "collective", "tracker", "training"):
+    for sub in ("core", "callback", "collective", "tracker", "training", "sklearn"):
         sys.modules["xgboost." + sub] = getattr(me, sub)
     return me

@@ -185,3 +185,25 @@ def test_collective_world_size_2_gloo():
         p.join(timeout=60)
     assert [(r, w) for r, w, *_ in res] == [(0, 2), (1, 2)]
     assert all(o == {"who": 1} and s == [3.0, 30.0] for *_, o, s in res)
+
+
+def test_sklearn_wrappers_and_cv(cpu_xgb, tmp_path):
+    """Script-mode surface used by the container's customer-script resource (test/resources/boston/...:54,94)."""
+    X, y = synth(400, 5, 9)
+    reg = cpu_xgb.XGBRegressor(objective="reg:squarederror", colsample_bytree=1.0, learning_rate=0.3, max_depth=3, n_estimators=8)
+    reg.fit(X, y, eval_set=[(X, y)], verbose=False)
+    p = reg.predict(X)
+    assert p.shape == (400,) and np.sqrt(np.mean((p - y) ** 2)) < np.std(y)
+    assert len(reg.evals_result()["validation_0"]["rmse"]) == 8
+    assert reg.feature_importances_.shape == (5,) and abs(reg.feature_importances_.sum() - 1) < 1e-5
+    f = str(tmp_path / "m.json")
+    reg.save_model(f)
+    reg2 = cpu_xgb.XGBRegressor()
+    reg2.load_model(f)
+    np.testing.assert_allclose(reg2.predict(X), p, atol=1e-6)
+    Xc, yc = synth(300, 4, 10, "multi", K=3)
+    clf = cpu_xgb.XGBClassifier(max_depth=2, n_estimators=4).fit(Xc, yc, verbose=False)
+    assert clf.predict_proba(Xc).shape == (300, 3) and set(np.unique(clf.predict(Xc))) <= {0, 1, 2}
+    d = cpu_xgb.DMatrix(X, label=y)
+    res = cpu_xgb.cv({"objective": "reg:squarederror", "max_depth": 3}, d, num_boost_round=5, nfold=3, metrics="rmse", as_pandas=False, seed=123)
+    assert len(res["test-rmse-mean"]) == 5 and res["train-rmse-mean"][-1] < res["train-rmse-mean"][0]
