@@ -257,7 +257,7 @@ struct PinnedPool {
   void reset() { cur = 0; off = 0; }
 };
 
-struct TreeGraphKey { uint64_t uid; const void *margin, *mask, *packed; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds; int world; int64_t n; };
+struct TreeGraphKey { uint64_t uid; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds; int world; int64_t n; };
 struct TreeGraph { cudaGraphExec_t exec = nullptr; TreeGraphKey key; long long launches = 0; TreeGraph() { memset(&key, 0, sizeof key); } };
 
 struct GrowerImpl {
@@ -681,6 +681,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     TreeGraph& tg = g.graphs[k];
     TreeGraphKey key; memset(&key, 0, sizeof key);
     key.uid = dtrain->uid; key.margin = cache.margin.p; key.mask = mask; key.packed = g.packed.p; key.max_depth = param_.max_depth;
+    key.bins = dtrain->bins.p; key.bins_col = dtrain->bins_col.p; key.cuts = dtrain->d_cut_vals.p;     // re-binning invalidates the capture
     key.max_leaves = param_.max_leaves; key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
     key.mcw = param_.min_child_weight; key.mds = param_.max_delta_step; key.world = Comm::get().world(); key.n = dtrain->n;
     if (!tg.exec || memcmp(&tg.key, &key, sizeof key) != 0) {
