@@ -101,30 +101,41 @@ int orc_make_cuts(const float* X, int64_t n, int32_t F, const float* w, int32_t 
   int nb = max_bin;
   if (nb > 256) nb = 256;
   if (has_missing && nb > 255) nb = 255;
-  VW* col = (VW*)malloc(sizeof(VW) * (size_t)(n > 0 ? n : 1));
-  float* d = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
-  double* cw = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  /* features are independent: sort / collapse them in parallel into per-feature cut lists, then concatenate */
+  float* tmp_cuts = (float*)malloc(sizeof(float) * (size_t)F * 256);
+  int* tmp_n = (int*)malloc(sizeof(int) * (size_t)(F > 0 ? F : 1));
+#pragma omp parallel
+  {
+    VW* col = (VW*)malloc(sizeof(VW) * (size_t)(n > 0 ? n : 1));
+    float* d = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+    double* cw = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+#pragma omp for schedule(dynamic, 1)
+    for (int f = 0; f < F; ++f) {
+      int64_t cnt = 0;
+      for (int64_t r = 0; r < n; ++r) {
+        float v = X[r * F + f];
+        if (!isnan(v)) { col[cnt].v = v; col[cnt].w = w ? w[r] : 1.0f; ++cnt; }
+      }
+      qsort(col, (size_t)cnt, sizeof(VW), cmp_vw);
+      int64_t m = 0;
+      for (int64_t i = 0; i < cnt; ++i) {
+        if (m > 0 && col[i].v == d[m - 1]) cw[m - 1] += col[i].w;
+        else { d[m] = col[i].v; cw[m] = col[i].w; ++m; }
+      }
+      tmp_n[f] = cuts_from_distinct(d, cw, m, nb, tmp_cuts + (size_t)f * 256);
+      float mn = m > 0 ? d[0] : 0.0f;
+      min_vals[f] = mn - (fabsf(mn) + 1e-5f);
+    }
+    free(col); free(d); free(cw);
+  }
   int total = 0;
   cut_ptrs[0] = 0;
   for (int f = 0; f < F; ++f) {
-    int64_t cnt = 0;
-    for (int64_t r = 0; r < n; ++r) {
-      float v = X[r * F + f];
-      if (!isnan(v)) { col[cnt].v = v; col[cnt].w = w ? w[r] : 1.0f; ++cnt; }
-    }
-    qsort(col, (size_t)cnt, sizeof(VW), cmp_vw);
-    int64_t m = 0;
-    for (int64_t i = 0; i < cnt; ++i) {
-      if (m > 0 && col[i].v == d[m - 1]) cw[m - 1] += col[i].w;
-      else { d[m] = col[i].v; cw[m] = col[i].w; ++m; }
-    }
-    int nc = cuts_from_distinct(d, cw, m, nb, cut_vals + total);
-    float mn = m > 0 ? d[0] : 0.0f;
-    min_vals[f] = mn - (fabsf(mn) + 1e-5f);
-    total += nc;
+    memcpy(cut_vals + total, tmp_cuts + (size_t)f * 256, sizeof(float) * (size_t)tmp_n[f]);
+    total += tmp_n[f];
     cut_ptrs[f + 1] = total;
   }
-  free(col); free(d); free(cw);
+  free(tmp_cuts); free(tmp_n);
   return total;
 }
 
@@ -332,8 +343,18 @@ void orc_build_hist(const uint8_t* bins, int32_t F, const int32_t* cut_ptrs, con
 #ifdef _OPENMP
   nt = omp_get_max_threads();
 #endif
-  if (nrows < 4096) nt = 1;
-  double* priv = nt > 1 ? (double*)calloc((size_t)nt * 2 * total_bins, sizeof(double)) : NULL;
+  /* one private histogram per thread costs a zero + reduce of 16 B x total_bins: only use as many threads as the
+   * balance row work (nrows x F / nt) against that overhead (nt x total_bins): nt ~ sqrt(nrows F / (2 total_bins)) */
+  { double want = sqrt((double)nrows * (double)F / (2.0 * (double)(total_bins > 0 ? total_bins : 1))); if (want < 1.0) want = 1.0; if (want < (double)nt) nt = (int)want; }
+  static double* g_priv = NULL; static size_t g_priv_cap = 0;
+  double* priv = NULL;
+  if (nt > 1) {
+    size_t need = (size_t)nt * 2 * total_bins;
+    if (need > g_priv_cap) { free(g_priv); g_priv = (double*)malloc(sizeof(double) * need); g_priv_cap = need; }
+    priv = g_priv;
+#pragma omp parallel for schedule(static) num_threads(nt)
+    for (int t = 0; t < nt; ++t) memset(priv + (size_t)t * 2 * total_bins, 0, sizeof(double) * 2 * (size_t)total_bins);
+  }
 #pragma omp parallel num_threads(nt)
   {
     int tid = 0;
@@ -359,7 +380,6 @@ void orc_build_hist(const uint8_t* bins, int32_t F, const int32_t* cut_ptrs, con
       double s = 0; for (int t = 0; t < nt; ++t) s += priv[(size_t)t * 2 * total_bins + i];
       hist[i] = s;
     }
-    free(priv);
   }
 }
 
