@@ -210,7 +210,7 @@ def run_reference(a):
     print(json.dumps({
         "impl": "reference", "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64 histograms over f32 gradients", "data": "synthetic",
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic %dx%d %s hist max_bin=%d max_depth=%d" % (a.rows, a.cols, a.objective, a.max_bin, a.max_depth),
                    "params": params_of(a)},
         "cpu_baseline": {"value": value, "unit": "rounds/s", "cores": cores, "kind": "port", "sample": sample},
@@ -387,10 +387,11 @@ def main():
         out = {
             "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "int64 fixed-point histograms (int32 smem partials) over f32 gradients", "data": "synthetic",
+            "dtype": "int64", "data": "synthetic",
             "config": {"workload": "synthetic %dx%d %s hist max_bin=%d max_depth=%d" % (a.rows, a.cols, a.objective, a.max_bin, a.max_depth),
                        "rows_per_gpu": (a.rows + world - 1) // world, "parallelism": "rows sharded x%d, per-level int64 histogram NCCL all-reduce" % world,
                        "l2": "inputs (%.1f GB of bins per GPU) exceed the 126 MB L2" % ((r1 - r0) * 32 * ((a.cols + 31) // 32) / 1e9),
+                       "arithmetic": "f32 gradients rounded to a 2^-k fixed-point grid, int32 shared-memory partial sums, int64 histograms (exact), f64/f32 split gains",
                        "params": params},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "predict": predict,
         }
