@@ -67,8 +67,34 @@ def _load_csv(files, q):
     return data, y, w
 
 
+def _load_libsvm_fast(files):
+    """C parser of scikit-learn when the files are plain `label idx:val ...` lines (no per-row weights / qid)."""
+    try:
+        from sklearn.datasets import load_svmlight_files
+    except ImportError:
+        return None
+    for f in files:
+        with open(f, "rb") as fh:
+            head = fh.readline().split(b"#", 1)[0].split()
+        if not head or b":" in head[0] or any(t.startswith(b"qid:") for t in head[1:2]):
+            return None
+    try:
+        out = load_svmlight_files(files, dtype=np.float32, zero_based=True)
+    except Exception:
+        return None
+    import scipy.sparse as sp
+    Xs, ys = out[0::2], out[1::2]
+    ncol = max(x.shape[1] for x in Xs)
+    Xs = [sp.csr_matrix((x.data, x.indices, x.indptr), shape=(x.shape[0], ncol)) for x in Xs]
+    X = sp.vstack(Xs, format="csr") if len(Xs) > 1 else Xs[0]
+    return X, np.concatenate(ys).astype(np.float32), None
+
+
 def _load_libsvm(files, q):
     import scipy.sparse as sp
+    fast = _load_libsvm_fast(files)
+    if fast is not None:
+        return fast
     labels, weights, rows_ptr, cols, vals = [], [], [0], [], []
     has_weight = False
     for f in files:
