@@ -29,14 +29,14 @@ CASES = [
 
 
 @pytest.mark.parametrize("path,deselect,min_passed", CASES)
-def test_reference_unit_file_passes_on_this_package(path, deselect, min_passed):
+def test_reference_unit_file_passes_on_this_package(path, deselect, min_passed, tmp_path):
     env = dict(os.environ)
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests"), ROOT, "/root/reference", "/root/reference/src"])
     cmd = [sys.executable, "-m", "pytest", "--noconftest", "-c", os.devnull, "-p", "reference_plugin", "-q", "--no-header", "-p", "no:cacheprovider",
            "--rootdir", "/tmp", os.path.join(UNIT, path)]
     if deselect:
         cmd += ["-k", deselect]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=str(tmp_path))      # some reference tests write scratch files into the cwd
     tail = (r.stdout + r.stderr)[-3000:]
     m = re.search(r"(\d+) passed", r.stdout)
     assert r.returncode == 0, tail
