@@ -112,3 +112,26 @@ def test_cuts_definition_small_cardinality():
     np.testing.assert_allclose(vals, [2.0, 4.0, 4.0 + 4.0 + 1e-5, 7.0, 7.0 + 7.0 + 1e-5])
     bins = O.bin_matrix(X, ptrs, vals)
     np.testing.assert_array_equal(bins, [[0, 0], [1, 0], [1, 1], [2, 255]])
+
+
+@pytest.mark.parametrize("objective,kind", [("reg:squarederror", "reg"), ("binary:logistic", "bin")])
+def test_fixed_point_gradient_grid_stays_inside_the_leaf_tolerance(objective, kind):
+    """The product rounds gradients to a power-of-two grid (|g_q| <= 2^18, engine.h kGradBits) before the exact integer
+    histogram.  The oracle can emulate that rounding (`set_quant_bits`): same trees, leaves within the 1e-5 bar."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from util import synth
+    X, y = synth(60000, 20, 5, kind)
+    params = dict(objective=objective, max_depth=6, eta=0.3)
+    cuts = O.make_cuts(X, 256)
+    bins = O.bin_matrix(X, cuts[0], cuts[1])
+    ref = O.Trainer(params, bins=bins, cuts=cuts, y=y)
+    fx = O.Trainer(params, bins=bins, cuts=cuts, y=y)
+    fx.set_quant_bits(19)               # 18 magnitude bits + sign, like the kernel
+    for _ in range(10):
+        ref.update(); fx.update()
+    a, b = ref.model(), fx.model()
+    np.testing.assert_array_equal(a["left"], b["left"])
+    np.testing.assert_array_equal(a["split_index"], b["split_index"])
+    leaf = a["left"] == -1
+    assert np.abs(a["split_cond"][leaf] - b["split_cond"][leaf]).max() < 1e-5
