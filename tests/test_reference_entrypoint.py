@@ -95,3 +95,24 @@ def test_bad_labels_become_user_error(container, tmp_path):
     with pytest.raises(exc.UserError, match="label must be in"):
         ref_train.sagemaker_train(train_config=hp, data_config=dc, train_path=str(tr), val_path=None, model_dir=str(tmp_path / "m"),
                                   sm_hosts=["algo-1"], sm_current_host="algo-1", checkpoint_config={})
+
+
+def test_sagemaker_train_kfold_branch(container, tmp_path, monkeypatch):
+    """train.py:378-459: RepeatedKFold -> DMatrix.slice(idx) -> xgb.train per fold -> booster.predict(fold) -> N model files
+    (what test/integration/local/test_kfold.py asserts), plus predictions.csv from the ValidationPredictionRecorder."""
+    xgb, ref_train = container
+    import shutil
+    tr, va, model_dir, out = tmp_path / "train", tmp_path / "validation", tmp_path / "model", tmp_path / "output"
+    tr.mkdir(); va.mkdir(); out.mkdir()
+    shutil.copy(os.path.join(G, "abalone.train_0"), tr / "abalone.train_0")
+    shutil.copy(os.path.join(G, "abalone.validation"), va / "abalone.validation")
+    monkeypatch.setenv("SM_OUTPUT_DATA_DIR", str(out))
+    hp = {"objective": "reg:squarederror", "num_round": "5", "max_depth": "3", "_kfold": "3", "eval_metric": "rmse"}
+    dc = {"train": {"ContentType": "libsvm", "TrainingInputMode": "File", "S3DistributionType": "FullyReplicated"},
+          "validation": {"ContentType": "libsvm", "TrainingInputMode": "File", "S3DistributionType": "FullyReplicated"}}
+    ref_train.sagemaker_train(train_config=hp, data_config=dc, train_path=str(tr), val_path=str(va), model_dir=str(model_dir),
+                              sm_hosts=["algo-1"], sm_current_host="algo-1", checkpoint_config={})
+    assert sorted(os.listdir(model_dir)) == ["xgboost-model-0", "xgboost-model-1", "xgboost-model-2"]
+    assert (out / "predictions.csv").exists()
+    rows = open(out / "predictions.csv").read().strip().splitlines()
+    assert len(rows) == 1461 + 626          # one out-of-fold prediction per row of train + validation
