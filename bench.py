@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
+    ap.add_argument("--watchdog-seconds", type=int, default=1500, help="hard exit if the whole run takes longer (a hung collective must not eat the box)")
     return ap.parse_args()
 
 
@@ -252,6 +253,14 @@ def predict_section(xgb, be, device, peak):
 
 def main():
     a = parse_args()
+    if a.watchdog_seconds > 0:
+        def _bail():
+            sys.stderr.write("bench.py: watchdog fired after %d s, exiting\n" % a.watchdog_seconds)
+            sys.stderr.flush()
+            os._exit(3)
+        wd = threading.Timer(a.watchdog_seconds, _bail)
+        wd.daemon = True
+        wd.start()
     if a.impl == "reference":
         run_reference(a)
         return
