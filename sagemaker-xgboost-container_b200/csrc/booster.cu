@@ -756,6 +756,27 @@ std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, c
       ma.is_logistic = (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic) ? 1 : 0;
       std::string base = mname;
       if (mname.rfind("error@", 0) == 0) { base = "error"; ma.threshold = std::stof(mname.substr(6)); }
+      if (base == "auc") {
+        // experimental until validated on hardware (written after the round-1 GPU budget was spent)
+        B200_CHECK(getenv("B200XGB_EXPERIMENTAL") != nullptr, "Unknown metric function auc (implemented in auc.cu but not yet validated on hardware; set B200XGB_EXPERIMENTAL=1 to use it)");
+        B200_CHECK(param_.num_class <= 1, "auc is implemented for binary / regression-style predictions only");
+        const int logistic = (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic) ? 1 : 0;
+        compute_auc_device(c.margin.p, dm->d_labels.p, dm->weights.empty() ? nullptr : dm->d_weights.p, dm->n, logistic, grower_->dsum.p, s);
+        double h3[3];
+        CUDA_OK(cudaMemcpyAsync(h3, grower_->dsum.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        double pair[2] = {h3[0], h3[1] * h3[2]};
+        if (Comm::get().distributed()) {
+          CUDA_OK(cudaMemcpyAsync(grower_->dsum.p, pair, 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+          Comm::get().allreduce_sum_f64(grower_->dsum.p, 2, s);
+          CUDA_OK(cudaMemcpyAsync(pair, grower_->dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+          CUDA_OK(cudaStreamSynchronize(s));
+        }
+        B200_CHECK(pair[1] > 0.0, "Check failed: !auc_error AUC: the dataset only contains pos or neg samples");
+        char buf[64]; snprintf(buf, sizeof buf, "%.17g", pair[0] / pair[1]);
+        out += "\t" + names[i] + "-" + mname + ":" + buf;
+        continue;
+      }
       if (base == "rmse") ma.metric = kMetricRmse; else if (base == "mse") ma.metric = kMetricRmse; else if (base == "mae") ma.metric = kMetricMae;
       else if (base == "logloss") ma.metric = kMetricLogloss; else if (base == "error") ma.metric = kMetricError;
       else if (base == "merror") ma.metric = kMetricMerror; else if (base == "mlogloss") ma.metric = kMetricMlogloss;

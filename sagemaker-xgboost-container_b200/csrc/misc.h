@@ -45,6 +45,8 @@ void launch_predict(const PredictArgs& a, cudaStream_t s);
 void launch_transform(float* m, int64_t n, int K, int objective, float* out_class, cudaStream_t s);
 void launch_fill(float* p, int64_t n, float v, cudaStream_t s);
 void launch_metric(const MetricArgs& a, cudaStream_t s);
+// auc.cu (experimental): out[0] += unnormalised ROC area, out[1] = positive weight, out[2] = negative weight
+void compute_auc_device(const float* margin, const float* label, const float* weight, int64_t n, int is_logistic, double* out, cudaStream_t s);
 
 // quantile.cu: exact weighted-quantile cuts per feature (same definition as oracle/gbt_oracle.c cuts_from_distinct).
 // X: device, row-major n x F. Returns host vectors.
