@@ -39,10 +39,7 @@ class CudaBackend:
                 "libb200xgb.so not found at %s -- build it with `python sagemaker-xgboost-container_b200/build.py` "
                 "(nvcc, sm_100a). This package has no CPU fallback." % path)
         self.lib = C.CDLL(path)
-        L = self.lib
-        L.XGBGetLastError.restype = C.c_char_p
-        for name in dir(self):
-            pass
+        self.lib.XGBGetLastError.restype = C.c_char_p
         self.path = path
 
     # ------------------------------------------------------------------ helpers

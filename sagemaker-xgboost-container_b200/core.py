@@ -11,7 +11,6 @@ import warnings
 
 import numpy as np
 
-from . import backend as _be
 from .backend import XGBoostError, get_backend  # noqa: F401  (re-exported like xgboost.core)
 from .data import load_uri
 
@@ -67,7 +66,7 @@ class DMatrix:
             if arr.dtype == object:
                 arr = arr.astype(np.float32)
             if arr.ndim == 1:
-                arr = arr.reshape(1, -1) if arr.size and False else arr.reshape(-1, 1)
+                arr = arr.reshape(-1, 1)
             if arr.ndim != 2:
                 raise ValueError("Expecting 2 dimensional numpy.ndarray, got: %s" % (arr.shape,))
             self.handle = be.dmatrix_from_dense(arr, miss)
@@ -288,6 +287,8 @@ class Booster:
             params = [(params, value)]
         for k, v in _param_items(params):
             if k in _IGNORED_PARAMS:
+                if k in ("monotone_constraints", "interaction_constraints") and str(v).strip("()[] ,0") != "":
+                    warnings.warn("%s is accepted for hyperparameter compatibility but NOT applied by the B200 hist builder yet" % k)
                 continue
             get_backend().booster_set_param(self.handle, k, v)
 
