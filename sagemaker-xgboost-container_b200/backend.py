@@ -309,6 +309,23 @@ class CudaBackend:
                                                       C.byref(ms)))
         return hist, scales, float(ms.value)
 
+    def build_histogram_ex(self, bh, dh, gpair, mode=0, row_ids=None, repeats=1):
+        """Kernel-level entry point: (hist [F][256][2] int64, scales, ms, kernel name); see include/b200xgb.h."""
+        gpair = np.ascontiguousarray(gpair, np.float32)
+        F = self.dmatrix_num_col(dh)
+        hist = np.zeros((F, 256, 2), np.int64)
+        scales = np.zeros(4, np.float32)
+        ms = C.c_float()
+        name = C.c_char_p()
+        ids, n_ids = None, 0
+        if row_ids is not None:
+            row_ids = np.ascontiguousarray(row_ids, np.uint32)
+            ids, n_ids = row_ids.ctypes.data_as(C.POINTER(C.c_uint)), len(row_ids)
+        self._check(self.lib.XGB200BuildHistogramEx(bh, dh, gpair.ctypes.data_as(C.POINTER(C.c_float)), C.c_int(repeats), C.c_int(mode), ids,
+                                                    C.c_ulong(n_ids), hist.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    scales.ctypes.data_as(C.POINTER(C.c_float)), C.byref(ms), C.byref(name)))
+        return hist, scales, float(ms.value), (name.value or b"").decode()
+
     def booster_cached_margin(self, bh, dh, K):
         n = self.dmatrix_num_row(dh)
         out = np.zeros((n, K), np.float32)

@@ -152,16 +152,20 @@ const std::vector<float>& DMatrix::get_float_info(const std::string& field) cons
 
 void DMatrix::bin_with_cuts() {
   cudaStream_t s = engine_stream();
-  ngroups = std::max(1, (F + kSlots - 1) / kSlots);
-  fpg = F > 0 ? (F + ngroups - 1) / ngroups : 1;
+  feature_layout(F, &ngroups, &tw, &ntail);
+  ++binned_version;
   d_cut_ptrs.alloc(cuts.ptrs.size()); d_cut_vals.alloc(cuts.vals.size()); d_min_vals.alloc(cuts.mins.size());
   CUDA_OK(cudaMemcpyAsync(d_cut_ptrs.p, cuts.ptrs.data(), sizeof(int) * cuts.ptrs.size(), cudaMemcpyHostToDevice, s));
   if (!cuts.vals.empty()) CUDA_OK(cudaMemcpyAsync(d_cut_vals.p, cuts.vals.data(), sizeof(float) * cuts.vals.size(), cudaMemcpyHostToDevice, s));
   if (!cuts.mins.empty()) CUDA_OK(cudaMemcpyAsync(d_min_vals.p, cuts.mins.data(), sizeof(float) * cuts.mins.size(), cudaMemcpyHostToDevice, s));
-  bins.alloc((size_t)ngroups * n * kSlots);
-  launch_bin(X.p, n, 0, n, F, fpg, ngroups, d_cut_ptrs.p, d_cut_vals.p, bins.p, s);
+  // 512 pad rows: the root kernel's bulk copies always move whole tiles (rows past n are masked in the kernel)
+  const size_t n_alloc = (size_t)n + 512;
+  bins.alloc(n_alloc * ngroups * kSlots); bins_tail.alloc(tw ? n_alloc * tw : 0);
+  CUDA_OK(cudaMemsetAsync(bins.p + (size_t)n * ngroups * kSlots, 0, (size_t)512 * ngroups * kSlots, s));
+  if (tw) CUDA_OK(cudaMemsetAsync(bins_tail.p + (size_t)n * tw, 0, (size_t)512 * tw, s));
+  launch_bin(X.p, n, F, ngroups, tw, d_cut_ptrs.p, d_cut_vals.p, bins.p, bins_tail.p, s);
   bins_col.alloc((size_t)std::max(F, 1) * n);
-  launch_transpose_bins(bins.p, n, F, fpg, ngroups, bins_col.p, s);
+  launch_transpose_bins(bins.p, bins_tail.p, n, F, ngroups, tw, bins_col.p, s);
   CUDA_OK(cudaStreamSynchronize(s));
   binned = true;
 }
@@ -245,6 +249,15 @@ __global__ void pack_tree_kernel(TreeArrays t, const int* n_nodes, DevNode* out,
   }
 }
 
+// Constant-hessian root pass (reg:squarederror without weights / subsampling): the H plane of the root histogram is the
+// same every round, so it is snapshotted once and later rounds start the root slot from it and accumulate G only.
+__global__ void snapshot_h_kernel(const GH64* slot, long long* cache, size_t entries) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < entries; e += (size_t)gridDim.x * blockDim.x) cache[e] = slot[e].h;
+}
+__global__ void slot_from_cache_kernel(GH64* slot, const long long* cache, size_t entries) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < entries; e += (size_t)gridDim.x * blockDim.x) { GH64 v; v.g = 0; v.h = cache[e]; slot[e] = v; }
+}
+
 struct PinnedPool {
   std::vector<std::pair<char*, size_t>> chunks; size_t cur = 0, off = 0;
   ~PinnedPool() { for (auto& c : chunks) cudaFreeHost(c.first); }
@@ -257,12 +270,14 @@ struct PinnedPool {
   void reset() { cur = 0; off = 0; }
 };
 
-struct TreeGraphKey { uint64_t uid; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds; int world; int64_t n; };
+struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds; int world, root_mode; int64_t n; };
 struct TreeGraph { cudaGraphExec_t exec = nullptr; TreeGraphKey key; long long launches = 0; TreeGraph() { memset(&key, 0, sizeof key); } };
 
 struct GrowerImpl {
-  int64_t n = 0; int ngroups = 0, max_depth = 0, max_nodes = 0, cap_nodes = 0, max_level_nodes = 0, region = 0;
+  int64_t n = 0; int ngroups = 0, tw = 0, max_depth = 0, max_nodes = 0, cap_nodes = 0, max_level_nodes = 0, region = 0;
   size_t slot_stride = 0;                  // GH64 entries per histogram slot
+  int64_t gp_stride = 0;                   // rows reserved per class in gpair
+  DevBuf<long long> root_h_cache; uint64_t root_h_uid = 0, root_h_version = 0; bool root_h_valid = false;
   GrowState gs{}; TreeArrays ta{};
   DevBuf<unsigned char> state_block;       // all GrowState arrays
   DevBuf<unsigned char> tree_block;        // header + TreeArrays, copied to the host in one piece
@@ -272,31 +287,32 @@ struct GrowerImpl {
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
   DevBuf<DevNode> packed; std::vector<TreeGraph> graphs; std::vector<char> eager_done;
-  int hist_grid_x = 1;
 
-  void ensure(int64_t n_, int ngroups_, int max_depth_, int K) {
-    if (n == n_ && ngroups == ngroups_ && max_depth == max_depth_ && gpair.n >= (size_t)n_ * K) return;
+  void ensure(int64_t n_, int ngroups_, int tw_, int max_depth_, int K) {
+    const int64_t stride_ = (n_ + 63) & ~(int64_t)63;
+    if (n == n_ && ngroups == ngroups_ && tw == tw_ && max_depth == max_depth_ && gpair.n >= (size_t)stride_ * K + 512) return;
     B200_CHECK(max_depth_ >= 1 && max_depth_ <= kMaxDepth, "max_depth must be in [1, 16] for the B200 depth-wise hist builder");
-    n = n_; ngroups = ngroups_; max_depth = max_depth_;
+    n = n_; ngroups = ngroups_; tw = tw_; max_depth = max_depth_; gp_stride = stride_; root_h_valid = false;
     for (auto& tg : graphs) if (tg.exec) { cudaGraphExecDestroy(tg.exec); tg.exec = nullptr; }
     max_nodes = (1 << (max_depth + 1)) - 1;
     cap_nodes = (max_nodes + 15) & ~15;
     max_level_nodes = 1 << (max_depth - 1);
     region = max_level_nodes;
-    slot_stride = (size_t)ngroups * kGroupEntries;
+    slot_stride = hist_slot_entries(ngroups, tw);
     const size_t pool_bytes = 2 * (size_t)region * slot_stride * sizeof(GH64);
     size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
     B200_CHECK(pool_bytes < free_b / 2 + hist_pool.n * sizeof(GH64), "histogram pool for this max_depth / feature count does not fit in device memory");
     hist_pool.alloc(2 * (size_t)region * slot_stride);
     ridx0.alloc(n); ridx1.alloc(n);
-    gpair.alloc((size_t)n * K); gp0.alloc(n); gp1.alloc(n); err.alloc(1); dsum.alloc(4);
+    gpair.alloc((size_t)gp_stride * K + 512); gpair.zero(engine_stream()); gp0.alloc(n); gp1.alloc(n); err.alloc(1); dsum.alloc(4);
+    root_h_cache.alloc(slot_stride);
     const unsigned max_tiles = (unsigned)((n + kPartTile - 1) / kPartTile) + max_level_nodes + 1;
     scratch.alloc(3 * (size_t)max_level_nodes + 8);
     // ---- GrowState block
     size_t off = 0; auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t N = cap_nodes, L = max_level_nodes;
     size_t o_seg_begin = take(4 * N), o_seg_count = take(4 * N), o_slot = take(4 * N), o_sum = take(16 * N), o_rg = take(4 * N), o_w = take(4 * N);
-    size_t o_best = take(sizeof(SplitCand) * N), o_bestg = take(sizeof(SplitCand) * N * ngroups);
+    size_t o_best = take(sizeof(SplitCand) * N), o_bestg = take(sizeof(SplitCand) * N * (ngroups + (tw > 0 ? 1 : 0)));
     size_t o_lnodes = take(4 * (size_t)(kMaxDepth + 1) * L), o_lcount = take(4 * (kMaxDepth + 2));
     size_t o_bnid = take(4 * L), o_bsub = take(4 * L), o_bps = take(4 * L), o_bcount = take(4), o_bprefix = take(4 * (L + 1));
     size_t o_action = take(4 * L), o_tprefix = take(4 * (L + 1)), o_tleft = take(4 * (size_t)max_tiles), o_toff = take(4 * (size_t)max_tiles);
@@ -321,7 +337,6 @@ struct GrowerImpl {
     float* fp = (float*)(ip + 5 * N);
     ta.split_cond = fp; ta.base_weight = fp + N; ta.loss_chg = fp + 2 * N; ta.sum_hess = fp + 3 * N;
     ta.default_left = (unsigned char*)(fp + 4 * N);
-    hist_grid_x = b200::hist_grid_x(engine_num_sms(), ngroups);
     hist_configure();
   }
 };
@@ -430,7 +445,7 @@ void Booster::estimate_base_score(DMatrix* dtrain) {
   cudaStream_t s = engine_stream();
   GrowerImpl& g = *grower_;
   GradArgs ga{}; ga.margin = nullptr; ga.label = dtrain->d_labels.p; ga.weight = dtrain->weights.empty() ? nullptr : dtrain->d_weights.p;
-  ga.gpair = g.gpair.p; ga.absmax = nullptr; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = 1; ga.objective = param_.objective;
+  ga.gpair = g.gpair.p; ga.gp_stride = g.gp_stride; ga.absmax = nullptr; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = 1; ga.objective = param_.objective;
   ga.scale_pos_weight = param_.scale_pos_weight; ga.subsample = 1.0f; ga.seed = 0; ga.iter = 0;
   CUDA_OK(cudaMemsetAsync(g.dsum.p, 0, 4 * sizeof(double), s));
   launch_gradient(ga, s);
@@ -556,7 +571,7 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
   const int K = param_.num_class;
   if (!grower_) grower_ = new GrowerImpl();
   GrowerImpl& g = *grower_;
-  g.ensure(dtrain->n, dtrain->ngroups, param_.max_depth, K);
+  g.ensure(dtrain->n, dtrain->ngroups, dtrain->tw, param_.max_depth, K);
   if (!labels_checked_) {
     // label-range errors must surface from update() (the container maps them to UserError, train.py:461-467)
     const std::vector<float>& y = dtrain->labels;
@@ -574,7 +589,7 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
   // ---- gradients + fixed-point scales
   CUDA_OK(cudaMemsetAsync(g.gs.absmax, 0, 8, s));
   GradArgs ga{}; ga.margin = cache.margin.p; ga.label = dtrain->d_labels.p; ga.weight = dtrain->weights.empty() ? nullptr : dtrain->d_weights.p;
-  ga.gpair = g.gpair.p; ga.absmax = g.gs.absmax; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = K; ga.objective = param_.objective;
+  ga.gpair = g.gpair.p; ga.gp_stride = g.gp_stride; ga.absmax = g.gs.absmax; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = K; ga.objective = param_.objective;
   ga.scale_pos_weight = param_.scale_pos_weight; ga.subsample = param_.subsample; ga.seed = param_.seed; ga.iter = (unsigned long long)round;
   ga.row_offset = (int64_t)Comm::get().rank() << 40;
   launch_gradient(ga, s);
@@ -586,7 +601,7 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
 
 
 // The fixed launch sequence of one tree (everything data dependent lives in device memory), capturable in a CUDA graph.
-void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned char* mask, DevNode* packed_out) {
+void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned char* mask, DevNode* packed_out, int root_mode) {
   cudaStream_t s = engine_stream();
   GrowerImpl& g = *grower_;
   Comm& comm = Comm::get();
@@ -594,39 +609,43 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   const int D = param_.max_depth;
   const TrainParamDev pd = to_dev(param_);
   const BinnedMatrix bm = dtrain->binned_view();
-  PredCache cache_view; (void)cache_view;
+  const int num_sms = engine_num_sms();
   const unsigned max_tiles = (unsigned)((dtrain->n + kPartTile - 1) / kPartTile) + g.max_level_nodes + 1;
 
   launch_init_tree(g.gs, g.ta, (unsigned)dtrain->n, 0, g.max_level_nodes, s);
-  CUDA_OK(cudaMemsetAsync(g.hist_pool.p, 0, g.slot_stride * sizeof(GH64), s));
+  if (root_mode == 2) { slot_from_cache_kernel<<<148, 256, 0, s>>>(g.hist_pool.p, g.root_h_cache.p, g.slot_stride); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
+  else CUDA_OK(cudaMemsetAsync(g.hist_pool.p, 0, g.slot_stride * sizeof(GH64), s));
 
-  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.gpair = g.gpair.p + (size_t)k * dtrain->n; ha.ridx = nullptr;
+  HistArgs ha{}; ha.bins = bm.bins; ha.bins_tail = bm.bins_tail; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.tw = bm.tw;
+  ha.gpair = g.gpair.p + (size_t)k * g.gp_stride; ha.ridx = nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups;
-  ha.accumulate_sum = 1;
+  ha.accumulate_sum = 1; ha.g_only = root_mode == 2 ? 1 : 0;
   ha.rows_counter = profile_ ? prof_rows_.p : nullptr;
   prof_begin(0);
-  launch_hist_build(ha, g.hist_grid_x, s);
+  launch_hist_build(ha, num_sms, s);
   prof_end();
+  if (root_mode == 1) { snapshot_h_kernel<<<148, 256, 0, s>>>(g.hist_pool.p, g.root_h_cache.p, g.slot_stride); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
+  ha.g_only = 0;
   if (comm.distributed()) {
     comm.allreduce_sum_i64(g.hist_pool.p, g.slot_stride * 2, s);
     comm.allreduce_sum_i64(g.gs.node_sum, 2, s);
   }
   EvalArgs ea{}; ea.hist_pool = g.hist_pool.p; ea.gs = g.gs; ea.cut_ptrs = dtrain->d_cut_ptrs.p; ea.feat_mask = mask; ea.p = pd; ea.F = bm.F;
-  ea.ngroups = bm.ngroups; ea.fpg = bm.fpg; ea.has_missing = bm.has_missing; ea.level = 0; ea.max_level_nodes = g.max_level_nodes;
+  ea.ngroups = bm.ngroups; ea.tw = bm.tw; ea.ntail = bm.ntail; ea.has_missing = bm.has_missing; ea.level = 0; ea.max_level_nodes = g.max_level_nodes;
   launch_eval(ea, 1, s);
 
   for (int L = 0; L < D; ++L) {
     const bool final_level = (L == D - 1);
     const int next_base = ((L + 1) & 1) * g.region, next_half = 1 << L;
     ApplyArgs aa{}; aa.gs = g.gs; aa.tree = g.ta; aa.cut_ptrs = dtrain->d_cut_ptrs.p; aa.cut_vals = dtrain->d_cut_vals.p; aa.min_vals = dtrain->d_min_vals.p;
-    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups; aa.level = L; aa.max_level_nodes = g.max_level_nodes; aa.next_base = next_base; aa.next_half = next_half;
+    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups + (bm.tw > 0 ? 1 : 0); aa.level = L; aa.max_level_nodes = g.max_level_nodes; aa.next_base = next_base; aa.next_half = next_half;
     launch_apply(aa, s);
     if (final_level) break;                  // children of the last level are leaves: no partition, no histograms
     PartArgs pa{}; pa.gs = g.gs; pa.tree = g.ta; pa.bins_col = bm.bins_col; pa.n = bm.n;
     pa.ridx_cur = L == 0 ? nullptr : ((L & 1) ? g.ridx0.p : g.ridx1.p);
     pa.ridx_next = (L & 1) ? g.ridx1.p : g.ridx0.p;
-    pa.gp_cur = L == 0 ? g.gpair.p + (size_t)k * dtrain->n : ((L & 1) ? g.gp0.p : g.gp1.p);
+    pa.gp_cur = L == 0 ? g.gpair.p + (size_t)k * g.gp_stride : ((L & 1) ? g.gp0.p : g.gp1.p);
     pa.gp_next = (L & 1) ? g.gp1.p : g.gp0.p;
     pa.has_missing = bm.has_missing; pa.level = L; pa.max_level_nodes = g.max_level_nodes;
     launch_partition(pa, max_tiles, 1 << L, s);
@@ -635,10 +654,10 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
     ha.ridx = pa.ridx_next; ha.gpair = pa.gp_next; ha.accumulate_sum = 0;
     ha.rows_counter = profile_ ? prof_rows_.p + 1 : nullptr;
     prof_begin(L + 1);
-    launch_hist_build(ha, g.hist_grid_x, s);
+    launch_hist_build(ha, num_sms, s);
     prof_end();
     if (comm.distributed()) comm.allreduce_sum_i64(g.hist_pool.p + (size_t)next_base * g.slot_stride, (size_t)next_half * g.slot_stride * 2, s);
-    launch_subtract(g.gs, g.hist_pool.p, bm.ngroups, next_half, s);
+    launch_subtract(g.gs, g.hist_pool.p, g.slot_stride, next_half, s);
     ea.level = L + 1;
     launch_eval(ea, 1 << (L + 1), s);
   }
@@ -673,14 +692,25 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   const bool dist = Comm::get().distributed();
   if ((int)g.eager_done.size() <= k) g.eager_done.resize(k + 1, 0);
   const bool eager_first = dist && graph_multi && !g.eager_done[k];
-  if (profile_ || no_graph || (dist && !graph_multi) || eager_first) {
+  // constant-hessian root pass: eligible when every row has h == 1 in every round
+  static const bool no_consth = getenv("B200XGB_NO_CONSTH") != nullptr;
+  const bool consth = !no_consth && param_.objective == kSquaredError && param_.num_class == 1 && dtrain->weights.empty() &&
+                      param_.subsample >= 1.0f && param_.scale_pos_weight == 1.0f;
+  int root_mode = 0;
+  if (consth) {
+    if (g.root_h_valid && g.root_h_uid == dtrain->uid && g.root_h_version == dtrain->binned_version) root_mode = 2;
+    else root_mode = 1;
+  }
+  if (profile_ || no_graph || (dist && !graph_multi) || eager_first || root_mode == 1) {
     g.eager_done[k] = 1;
-    enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p);
+    enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p, root_mode);
+    if (root_mode == 1) { g.root_h_valid = true; g.root_h_uid = dtrain->uid; g.root_h_version = dtrain->binned_version; }
   } else {
     if ((int)g.graphs.size() <= k) g.graphs.resize(k + 1);
     TreeGraph& tg = g.graphs[k];
     TreeGraphKey key; memset(&key, 0, sizeof key);
-    key.uid = dtrain->uid; key.margin = cache.margin.p; key.mask = mask; key.packed = g.packed.p; key.max_depth = param_.max_depth;
+    key.uid = dtrain->uid; key.binned_version = dtrain->binned_version; key.root_mode = root_mode;
+    key.margin = cache.margin.p; key.mask = mask; key.packed = g.packed.p; key.max_depth = param_.max_depth;
     key.bins = dtrain->bins.p; key.bins_col = dtrain->bins_col.p; key.cuts = dtrain->d_cut_vals.p;     // re-binning invalidates the capture
     key.max_leaves = param_.max_leaves; key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
     key.mcw = param_.min_child_weight; key.mds = param_.max_delta_step; key.world = Comm::get().world(); key.n = dtrain->n;
@@ -689,7 +719,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
       cudaGraph_t graph = nullptr;
       const long long launches_before = g_kernel_launches;
       CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      try { enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p); }
+      try { enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p, root_mode); }
       catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
       CUDA_OK(cudaStreamEndCapture(s, &graph));
       CUDA_OK(cudaGraphInstantiate(&tg.exec, graph, 0));
@@ -852,35 +882,42 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
   else shape->assign({(uint64_t)n, (uint64_t)out_cols});
 }
 
-// Kernel-level entry point for parity tests and the roofline bench: build the root histogram of `dm` from host
-// gradient pairs `repeats` times; returns the int64 histogram [ngroups][256][32][2] and the fixed-point scales.
+// Kernel-level entry point for parity tests and the roofline bench: build the histogram of all rows (or of the row
+// subset `row_ids`, gradient pairs by position) from host gradient pairs `repeats` times; returns the int64 histogram in
+// pool layout ([ngroups][256][32]{g,h} then the tail [256][tw]{g,h}) and the fixed-point scales.
 void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::vector<long long>* hist_out, float* scales_out,
-                                    int repeats, float* ms_out) {
+                                    int repeats, float* ms_out, int mode, const unsigned* row_ids, int64_t n_ids) {
   configure();
   cudaStream_t s = engine_stream();
   dm->ensure_binned(param_.max_bin);
   if (!grower_) grower_ = new GrowerImpl();
   GrowerImpl& g = *grower_;
-  g.ensure(dm->n, dm->ngroups, param_.max_depth, param_.num_class);
+  g.ensure(dm->n, dm->ngroups, dm->tw, param_.max_depth, param_.num_class);
   hist_configure();
-  CUDA_OK(cudaMemcpyAsync(g.gpair.p, gpair_host, sizeof(float2) * dm->n, cudaMemcpyHostToDevice, s));
+  const int64_t rows = row_ids ? n_ids : dm->n;
+  B200_CHECK(rows <= dm->n, "debug_build_root_hist: more row ids than rows");
+  CUDA_OK(cudaMemcpyAsync(g.gpair.p, gpair_host, sizeof(float2) * rows, cudaMemcpyHostToDevice, s));
+  if (row_ids) CUDA_OK(cudaMemcpyAsync(g.ridx0.p, row_ids, sizeof(unsigned) * rows, cudaMemcpyHostToDevice, s));
   // scales from max|g|, max h of the supplied pairs
   float mg = 0.f, mh = 0.f;
-  for (int64_t i = 0; i < dm->n; ++i) { mg = std::max(mg, std::fabs(gpair_host[2 * i])); mh = std::max(mh, gpair_host[2 * i + 1]); }
+  for (int64_t i = 0; i < rows; ++i) { mg = std::max(mg, std::fabs(gpair_host[2 * i])); mh = std::max(mh, gpair_host[2 * i + 1]); }
   unsigned am[2]; memcpy(&am[0], &mg, 4); memcpy(&am[1], &mh, 4);
   CUDA_OK(cudaMemcpyAsync(g.gs.absmax, am, 8, cudaMemcpyHostToDevice, s));
   launch_scales(g.gs, s);
   const BinnedMatrix bm = dm->binned_view();
-  HistArgs ha{}; ha.bins = bm.bins; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.gpair = g.gpair.p; ha.ridx = nullptr;
+  HistArgs ha{}; ha.bins = bm.bins; ha.bins_tail = bm.bins_tail; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.tw = bm.tw; ha.gpair = g.gpair.p;
+  ha.ridx = row_ids ? g.ridx0.p : nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups; ha.accumulate_sum = 1;
+  ha.force_gather = mode == 1 ? 1 : 0; ha.g_only = mode == 2 ? 1 : 0;
+  g.root_h_valid = false;                       // the debug entry point overwrites gpair and the root slot
   cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
   float total = 0.f;
   for (int r = 0; r < std::max(1, repeats); ++r) {
-    launch_init_tree(g.gs, g.ta, (unsigned)dm->n, 0, g.max_level_nodes, s);
+    launch_init_tree(g.gs, g.ta, (unsigned)rows, 0, g.max_level_nodes, s);
     CUDA_OK(cudaMemsetAsync(g.hist_pool.p, 0, g.slot_stride * sizeof(GH64), s));
     CUDA_OK(cudaEventRecord(e0, s));
-    launch_hist_build(ha, g.hist_grid_x, s);
+    launch_hist_build(ha, engine_num_sms(), s);
     CUDA_OK(cudaEventRecord(e1, s));
     CUDA_OK(cudaEventSynchronize(e1));
     float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, e0, e1)); total += ms;

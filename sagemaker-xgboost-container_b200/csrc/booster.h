@@ -28,7 +28,8 @@ class DMatrix {
   // binned representation (built on first use as a training matrix)
   bool binned = false; int binned_max_bin = 0;
   HostCuts cuts; DevBuf<int> d_cut_ptrs; DevBuf<float> d_cut_vals, d_min_vals;
-  DevBuf<uint8_t> bins, bins_col; int ngroups = 0, fpg = 0;
+  DevBuf<uint8_t> bins, bins_tail, bins_col; int ngroups = 0, tw = 0, ntail = 0;   // engine.h BinnedMatrix layout
+  uint64_t binned_version = 0;                        // bumped by every (re)binning: invalidates captured graphs / cached planes
   uint64_t uid;                                       // identity for prediction caches
 
   DMatrix();
@@ -40,7 +41,8 @@ class DMatrix {
   const std::vector<float>& get_float_info(const std::string& field) const;
   void ensure_binned(int max_bin);
   void set_cuts(const HostCuts& c);                   // external cuts (shared with the oracle in tests)
-  BinnedMatrix binned_view() const { BinnedMatrix b; b.bins = bins.p; b.bins_col = bins_col.p; b.n = n; b.F = F; b.ngroups = ngroups; b.fpg = fpg; b.has_missing = has_missing; return b; }
+  BinnedMatrix binned_view() const { BinnedMatrix b; b.bins = bins.p; b.bins_tail = tw ? bins_tail.p : nullptr; b.bins_col = bins_col.p; b.n = n; b.F = F;
+    b.ngroups = ngroups; b.tw = tw; b.ntail = ntail; b.has_missing = has_missing; return b; }
  private:
   void finish_upload(float missing);
   void bin_with_cuts();
@@ -99,8 +101,10 @@ class Booster {
   void set_profile(bool on);
   std::string get_profile();                      // JSON, see include/b200xgb.h
   // histogram of one node for kernel-level parity tests / the roofline bench
+  // mode: 0 = production choice (TMA root kernel), 1 = gather kernel, 2 = G-only TMA root kernel (H plane stays zero).
+  // row_ids (optional, n_ids entries): histogram of that row subset, gpair given by POSITION -> exercises the gathered path.
   void debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::vector<long long>* hist_out, float* scales_out,
-                             int repeats, float* ms_out);
+                             int repeats, float* ms_out, int mode = 0, const unsigned* row_ids = nullptr, int64_t n_ids = 0);
 
  private:
   friend struct GrowerImpl;
@@ -135,7 +139,8 @@ class Booster {
   void bring_cache_up_to_date(DMatrix* dm, PredCache& c);
   void append_device_tree(int class_id, size_t device_offset, int max_nodes, PendingTree pt);
   void grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_index);
-  void enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned char* mask, DevNode* packed_out);
+  // root_mode: 0 = accumulate G and H, 1 = G and H + snapshot of the root H plane, 2 = G only on top of the cached H plane
+  void enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned char* mask, DevNode* packed_out, int root_mode);
   void prof_begin(int level);
   void prof_end();
   JPtr model_to_json();

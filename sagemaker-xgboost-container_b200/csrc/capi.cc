@@ -266,12 +266,12 @@ int XGB200DMatrixSetCuts(DMatrixHandle handle, const int* ptrs, bst_ulong n_ptrs
 int XGB200DMatrixGetBins(DMatrixHandle handle, int max_bin, uint8_t* out_row_major) {
   API_BEGIN();
   DMatrix* dm = DM(handle); dm->ensure_binned(max_bin);
-  std::vector<uint8_t> h((size_t)dm->ngroups * dm->n * kSlots);
+  const size_t W = (size_t)dm->ngroups * kSlots;
+  std::vector<uint8_t> h((size_t)dm->n * W), t((size_t)dm->n * dm->tw);
   if (!h.empty()) { CUDA_OK(cudaMemcpy(h.data(), dm->bins.p, h.size(), cudaMemcpyDeviceToHost)); }
-  for (int64_t r = 0; r < dm->n; ++r) for (int f = 0; f < dm->F; ++f) {
-    int g = f / dm->fpg, s = f % dm->fpg;
-    out_row_major[r * dm->F + f] = h[((size_t)r * dm->ngroups + g) * kSlots + s];
-  }
+  if (!t.empty()) { CUDA_OK(cudaMemcpy(t.data(), dm->bins_tail.p, t.size(), cudaMemcpyDeviceToHost)); }
+  for (int64_t r = 0; r < dm->n; ++r) for (int f = 0; f < dm->F; ++f)
+    out_row_major[r * dm->F + f] = (size_t)f < W ? h[(size_t)r * W + f] : t[(size_t)r * dm->tw + (f - W)];
   API_END();
 }
 int XGB200BoosterModelShape(BoosterHandle handle, bst_ulong* num_trees, bst_ulong* num_nodes, float* base_score, int* num_class) {
@@ -301,20 +301,35 @@ int XGB200BoosterExportModel(BoosterHandle handle, int64_t* tree_offset, int32_t
   if (tree_offset) tree_offset[trees.size()] = (int64_t)off;
   API_END();
 }
+static void hist_to_feature_major(const DMatrix* dm, const std::vector<long long>& h, int64_t* out_hist) {
+  // pool layout [group][bin][slot]{g,h} + tail [bin][tw]{g,h} -> [F][256]{g,h}
+  const size_t W = (size_t)dm->ngroups * kSlots, tail0 = (size_t)dm->ngroups * kGroupEntries;
+  for (int f = 0; f < dm->F; ++f) {
+    for (int b = 0; b < kBins; ++b) {
+      const size_t e = (size_t)f < W ? ((size_t)(f / kSlots) * kBins + b) * kSlots + f % kSlots : tail0 + (size_t)b * dm->tw + (f - W);
+      const size_t dst = ((size_t)f * kBins + b) * 2;
+      out_hist[dst] = h[e * 2]; out_hist[dst + 1] = h[e * 2 + 1];
+    }
+  }
+}
 int XGB200BuildRootHistogram(BoosterHandle handle, DMatrixHandle dmat, const float* gpair, int repeats, int64_t* out_hist, float* scales, float* out_ms) {
   API_BEGIN();
   DMatrix* dm = DM(dmat);
   std::vector<long long> h; float sc[4];
   BST(handle)->debug_build_root_hist(dm, gpair, &h, sc, repeats, out_ms);
-  // device layout [group][bin][slot]{g,h} -> [F][256]{g,h}
-  for (int f = 0; f < dm->F; ++f) {
-    int g = f / dm->fpg, s = f % dm->fpg;
-    for (int b = 0; b < kBins; ++b) {
-      size_t src = (((size_t)g * kBins + b) * kSlots + s) * 2, dst = ((size_t)f * kBins + b) * 2;
-      out_hist[dst] = h[src]; out_hist[dst + 1] = h[src + 1];
-    }
-  }
+  hist_to_feature_major(dm, h, out_hist);
   if (scales) memcpy(scales, sc, sizeof sc);
+  API_END();
+}
+int XGB200BuildHistogramEx(BoosterHandle handle, DMatrixHandle dmat, const float* gpair, int repeats, int mode, const unsigned* row_ids, bst_ulong n_ids,
+                           int64_t* out_hist, float* scales, float* out_ms, const char** out_kernel) {
+  API_BEGIN();
+  DMatrix* dm = DM(dmat);
+  std::vector<long long> h; float sc[4];
+  BST(handle)->debug_build_root_hist(dm, gpair, &h, sc, repeats, out_ms, mode, row_ids, (int64_t)n_ids);
+  hist_to_feature_major(dm, h, out_hist);
+  if (scales) memcpy(scales, sc, sizeof sc);
+  if (out_kernel) *out_kernel = hist_last_kernel();
   API_END();
 }
 int XGB200BoosterGetCachedMargin(BoosterHandle handle, DMatrixHandle dmat, float* out) {

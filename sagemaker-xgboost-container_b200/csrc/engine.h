@@ -46,14 +46,28 @@ constexpr int kMaxDepth = 16;
 
 struct GH64 { long long g, h; };      // exact fixed-point gradient/hessian sums
 
-// Binned matrix: each row is ngroups feature blocks of 32 B (one sector each); plus a column-major copy.
+// Binned matrix (DESIGN.md "data layout in HBM"): features are laid out in full 32-wide groups plus an optional narrow
+// tail so that neither HBM traffic nor shared-memory atomics are spent on pad slots (F = 100 -> 3 groups + a 4-wide tail):
+//   main  row-major [n][ngroups*32 B]   feature f < ngroups*32 -> group f >> 5, slot f & 31
+//   tail  row-major [n][tw B]           feature f >= ngroups*32 -> tail slot f - ngroups*32   (tw in {0, 4, 8})
+// plus a column-major copy [F][n] for the one-byte-per-row consumers (partition, prediction-cache update).
 struct BinnedMatrix {
-  const uint8_t* bins = nullptr;      // row-major [n][ngroups*32 B]: group g of row r at (r*ngroups+g)*32
-  const uint8_t* bins_col = nullptr;  // column-major [F][n]
+  const uint8_t* bins = nullptr;
+  const uint8_t* bins_tail = nullptr;
+  const uint8_t* bins_col = nullptr;
   int64_t n = 0;
-  int F = 0, ngroups = 0, fpg = 0;    // feature f -> group f / fpg, slot f % fpg
+  int F = 0, ngroups = 0, tw = 0, ntail = 0;
   int has_missing = 0;
 };
+
+// F = 32 a + L: a tail exists when there is at least one full group and 1 <= L <= 8; otherwise L features get a padded group.
+inline void feature_layout(int F, int* ngroups, int* tw, int* ntail) {
+  const int a = F / 32, L = F % 32;
+  if (a >= 1 && L >= 1 && L <= 8) { *ngroups = a; *ntail = L; *tw = L <= 4 ? 4 : 8; }
+  else { *ngroups = a + (L > 0 ? 1 : 0); if (*ngroups == 0) *ngroups = 1; *ntail = 0; *tw = 0; }
+}
+// (g,h) accumulators of one histogram-pool slot: [ngroups][256][32] then the tail [256][tw]
+inline size_t hist_slot_entries(int ngroups, int tw) { return (size_t)ngroups * 256 * 32 + (size_t)256 * tw; }
 
 // ---------------------------------------------------------------------------------------------
 // training parameters (names follow the container's hyperparameter schema,
@@ -92,7 +106,7 @@ struct GrowState {
   GH64* node_sum;                               // exact node totals
   float* root_gain; float* weight;
   SplitCand* best;                              // reduced over groups
-  SplitCand* best_group;                        // [nid][ngroups]
+  SplitCand* best_group;                        // [nid][ngroups + (tail ? 1 : 0)]
   // per level
   int* level_nodes;                             // [kMaxDepth+1][max_level_nodes] nids alive at each depth
   int* level_count;                             // [kMaxDepth+2]

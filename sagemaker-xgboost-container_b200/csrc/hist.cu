@@ -2,46 +2,82 @@
 // Replaces upstream xgboost's BuildHist (src/common/hist_util.cc / src/tree/gpu_hist/histogram.cu),
 // reached from the container at algorithm_mode/train.py:367-376 (xgb.train -> Booster.update).
 //
-// Design (DESIGN.md "histogram kernel"; measurements in profiles/):
-//  * sm_100a has exactly one fast shared-memory atomic: 32-bit integer ATOMS.ADD (float and 64-bit
-//    adds compile to ATOMS.CAST.SPIN CAS loops), and it runs 2x faster when the 32 lanes of the
-//    instruction hit 32 distinct banks.  So the histogram of one 32-feature group is two int32 planes
-//    [256 bins][32 slots]: bank == slot, and every instruction below has lanes on 32 distinct slots.
-//  * The binned matrix is row-major, each row = feature groups of 32 B.  A CTA owns a PAIR of adjacent
-//    groups (64 B of every row = one full DRAM burst, so gathered rows of deep levels waste nothing)
-//    or a single group when the matrix has only one.
-//  * A warp takes a tile of 16 rows; two lanes share a row, each holding 16 of a group's 32 bin bytes
-//    (one LDG.128 per lane and group).  Step j of 16 makes lane (row q, half h) update slot
-//    16h + rot_q(j): the per-row rotation makes the 16 rows of an instruction touch 16 different slots
-//    of each half -> conflict-free by construction.
-//  * (g,h) pairs are read by POSITION (they travel with the row ids through the partition), so the
-//    only gathered loads are the bin slices; row ids and pairs are prefetched two stages ahead.
-//  * Gradients are rounded to a power-of-two fixed-point grid (|g_q| <= 2^18, h_q <= 2^19) so a
-//    window of 4096 rows per CTA cannot overflow int32; between windows, accumulators above 2^24 are
-//    spilled to the global int64 histogram with RED.ADD.64 (sparse), and everything is flushed at the
-//    end of the CTA's node portion.  Sums are exact integers => bit-reproducible for any grid size,
-//    block schedule or GPU count, and the NCCL all-reduce of the int64 histograms is order-independent.
+// Design (DESIGN.md "histogram kernels"; measurements in profiles/):
+//  * sm_100a has exactly one fast shared-memory atomic: 32-bit integer ATOMS.ADD (float and 64-bit adds compile to
+//    ATOMS.CAST.SPIN CAS loops), and it runs at full rate only when the 32 lanes of the instruction hit 32 distinct
+//    banks.  So the histogram of one 32-feature group is int32 planes [256 bins][32 slots]: bank == slot, and every
+//    instruction below has its lanes on 32 distinct slots (per-row slot rotation, see LaneConst).
+//  * Layout without pad work: features live in FULL 32-wide groups plus a narrow tail (F = 100 -> 3 groups + 4-wide
+//    tail), so no atomic and no HBM byte is spent on pad slots (round 1: 4 groups x 25 of 32 slots = 22 % waste).
+//  * Two kernels share the accumulate / spill code:
+//      hist_root_kernel    the contiguous root pass.  A producer thread streams row tiles with TMA (2-D tensor map for
+//                          the main block: cp.async.bulk.tensor -> UTMALDG, 1-D bulk copies for (g,h) and the tail:
+//                          UBLKCP) into an mbarrier ring; consumer warps read bins with conflict-free LDS.128 and issue
+//                          the atomics.  GONLY variant for constant-hessian objectives: the H plane of the root never
+//                          changes between rounds, so the slot is pre-loaded with the cached H plane and only G is
+//                          accumulated (1 atomic per update instead of 2).
+//      hist_gather_kernel  the deeper levels: rows gathered by row id (LDG.128 per 16 B chunk straight to registers, a
+//                          rolling one-super-tile-ahead prefetch), (g,h) read by POSITION (they travel with the row
+//                          ids through the partition).
+//  * Gradients are rounded to a power-of-two fixed-point grid (|g_q| <= 2^18, h_q <= 2^19) so a window of 8064 rows per
+//    CTA cannot overflow int32; between windows, accumulators above 2^24 are spilled to the global int64 histogram with
+//    RED.ADD.64 (sparse), and everything is flushed at the end of the CTA's portion.  Sums are exact integers =>
+//    bit-reproducible for any grid size, block schedule or GPU count; the NCCL all-reduce is order-independent.
+#include <cuda.h>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "engine.h"
 #include "tree.h"
 
 namespace b200 {
 
-constexpr int kTileRows = 16;
-constexpr int kSuperRows = 2 * kTileRows;
-constexpr int kWindowRows = 4096;                 // rows per CTA between overflow checks
+constexpr int kSuperRows = 32;
+constexpr int kWindowRows = 8064;                 // rows per CTA between overflow checks: 8064 * 2^18 + 2^24 < 2^31
 constexpr int kMinRowsPerCta = 4096;              // do not pay a flush for fewer rows than this
 constexpr int kSpillThreshold = 1 << 24;
 constexpr int kPlaneBytes = kGroupEntries * 4;    // 32 KB
+constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
+constexpr int kRootConsumerWarps = 31;            // + 1 producer warp = 1024 threads
 
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned ldg_nc_u32(const void* p) {
+  unsigned r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ float2 ldg_nc_f2(const void* p) {
   float2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_v4(unsigned addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint2 lds_v2(unsigned addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+  unsigned r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
   return r;
 }
 __device__ __forceinline__ void red_shared_s32(unsigned addr, int v) {
@@ -50,52 +86,129 @@ __device__ __forceinline__ void red_shared_s32(unsigned addr, int v) {
 __device__ __forceinline__ void red_shared_u32_h(unsigned addr, unsigned v) {      // hessian plane = gradient plane + 32 KB
   asm volatile("red.shared.add.u32 [%0+32768], %1;" :: "r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_shared_u32(unsigned addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void red_global_s64(long long* p, long long v) {
   asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+// mbarrier / TMA (Hopper+ async-copy machinery; SASS: SYNCS.*, UTMALDG, UBLKCP)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* tm, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
 
-struct LaneConst { unsigned sel[4], offb[4], offw[4]; int qw; int rowlane; int colbyte; };
+// ---------------------------------------------------------------------------------------------
+// lane -> slot schedule of a (16 rows x one 32-feature group) unit.
+// Two lanes share a row: lane = 2*row + half, each holds 16 of the group's 32 bin bytes.  Step j of 16 makes the lane
+// update slot 16*half + rot(j): the per-row rotation (rot = row) makes the 16 rows of an instruction touch 16 different
+// slots of each half -> every ATOMS instruction hits 32 distinct banks (enumerated in tests/test_hist_lane_mapping.py).
+// ---------------------------------------------------------------------------------------------
+struct LaneConst { unsigned sel[4], offb[4], offw[4]; int qw; };
 
-// 16 conflict-free (g,h) atomic pairs of one lane's 16 bin bytes into the planes at smem byte offset `plane`
-__device__ __forceinline__ void accumulate16(const LaneConst& lc, const uint4& w, int gq, unsigned hq) {
+__device__ __forceinline__ LaneConst make_lane_const(int lane) {
+  LaneConst lc;
+  const int rot = lane >> 1, half = lane & 1;
+  lc.qw = rot >> 2;
+  const int qb = rot & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lc.sel[j] = 0x4440u | (unsigned)((j + qb) & 3);
+    lc.offb[j] = 4u * (unsigned)((j + qb) & 3);
+    lc.offw[j] = 64u * (unsigned)half + 16u * (unsigned)((j + lc.qw) & 3);
+  }
+  return lc;
+}
+
+// 16 conflict-free atomic (pairs) of one lane's 16 bin bytes into the planes of the group whose G plane starts at `base`
+template <bool GONLY>
+__device__ __forceinline__ void accumulate16(const LaneConst& lc, unsigned base, const uint4& w, int gq, unsigned hq) {
   unsigned w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
   if (lc.qw & 1) { unsigned x = w0; w0 = w1; w1 = w2; w2 = w3; w3 = x; }
   if (lc.qw & 2) { unsigned x = w0; w0 = w2; w2 = x; x = w1; w1 = w3; w3 = x; }
   const unsigned ww[4] = {w0, w1, w2, w3};
 #pragma unroll
   for (int jw = 0; jw < 4; ++jw) {
+    const unsigned ow = base + lc.offw[jw];
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
-      unsigned bin = __byte_perm(ww[jw], 0u, lc.sel[jb]);
-      unsigned addr = (bin << 7) + lc.offw[jw] + lc.offb[jb];
+      const unsigned bin = __byte_perm(ww[jw], 0u, lc.sel[jb]);
+      const unsigned addr = (bin << 7) + ow + lc.offb[jb];
       red_shared_s32(addr, gq);
-      red_shared_u32_h(addr, hq);
+      if (!GONLY) red_shared_u32_h(addr, hq);
     }
   }
 }
 
-struct Stage { unsigned id; float2 gh; };
-template <int NSUB> struct Rows { uint4 w[NSUB]; };         // one 16 B chunk per sub-tile of the 32-position super-tile
+// Tail features (tw = 4 or 8 bytes per row, one row per lane).  Plane layout [bin][trep][tw]: with trep * tw == 32 the
+// replica index (from the lane) makes bank == (replica, slot) -> conflict-free; with trep == 1 (no room for replicas
+// next to 200 KB of main planes) bank conflicts are data dependent but the tail is only tw of F features.
+struct TailConst { unsigned base_g, hplane_bytes, bin_stride, rep_off; int tw; };
+
+template <bool GONLY>
+__device__ __forceinline__ void tail_accumulate(const TailConst& tc, int lane, unsigned w0, unsigned w1, int gq, unsigned hq) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < tc.tw) {
+      const unsigned slot = (unsigned)(j + lane) & (unsigned)(tc.tw - 1);
+      const unsigned bin = __byte_perm(w0, w1, slot);
+      const unsigned addr = tc.base_g + bin * tc.bin_stride + tc.rep_off + slot * 4u;
+      red_shared_s32(addr, gq);
+      if (!GONLY) red_shared_u32(addr + tc.hplane_bytes, hq);
+    }
+  }
+}
 
 // Spill / flush pass over the CTA's accumulators.  Between windows only accumulators that could overflow in the next
 // window leave for the global int64 histogram (sparse RED.ADD.64); `last` flushes everything that is non-zero.
-template <int NTHREADS>
-__device__ __forceinline__ void spill_pass(int* smem, int ng_here, GH64* out, bool last) {
-  const int vecs = ng_here * 2 * kGroupEntries / 4;
-  for (int v = threadIdx.x; v < vecs; v += NTHREADS) {
+template <int PL>      // planes per group in shared memory: 1 = G only, 2 = G then H
+__device__ __forceinline__ void spill_main(int* smem, int ng_here, GH64* out, bool last, int tid, int nthr) {
+  const int vecs = ng_here * PL * (kGroupEntries / 4);
+  for (int v = tid; v < vecs; v += nthr) {
     int4 x = reinterpret_cast<int4*>(smem)[v];
-    const int plane = (v * 4) / kGroupEntries;              // 0: G of group 0, 1: H of group 0, 2: G of group 1, 3: H of group 1
-    const int e0 = v * 4 - plane * kGroupEntries;
-    const bool is_h = plane & 1;
+    if ((x.x | x.y | x.z | x.w) == 0) continue;
+    const int plane = v >> 11;                                // 2048 int4 per plane
+    const int e0 = (v & 2047) << 2;
+    const bool is_h = PL == 2 && (plane & 1);
+    GH64* o = out + (size_t)(plane / PL) * kGroupEntries + e0;
     int vals[4] = {x.x, x.y, x.z, x.w};
     bool any = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int val = vals[k];
-      bool sp = last ? (val != 0) : (is_h ? ((unsigned)val >= (unsigned)kSpillThreshold) : (val >= kSpillThreshold || val <= -kSpillThreshold));
+      const bool sp = last ? (val != 0) : (is_h ? ((unsigned)val >= (unsigned)kSpillThreshold) : (val >= kSpillThreshold || val <= -kSpillThreshold));
       if (sp) {
-        GH64* o = out + (size_t)(plane >> 1) * kGroupEntries + e0 + k;
-        red_global_s64(is_h ? &o->h : &o->g, is_h ? (long long)(unsigned)val : (long long)val);
+        red_global_s64(is_h ? &o[k].h : &o[k].g, is_h ? (long long)(unsigned)val : (long long)val);
         vals[k] = 0; any = true;
       }
     }
@@ -103,17 +216,181 @@ __device__ __forceinline__ void spill_pass(int* smem, int ng_here, GH64* out, bo
   }
 }
 
-template <int NG, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(HistArgs a) {
-  constexpr int NWARPS = NTHREADS / 32;
-  constexpr int kItersPerWindow = kWindowRows / (kSuperRows * NWARPS);     // super-tiles per warp between overflow checks
-  static_assert(kItersPerWindow >= 1, "window too small");
-  extern __shared__ __align__(16) int smem[];         // per group: LG[8192] then LH[8192]
+template <int PL>
+__device__ __forceinline__ void spill_tail(int* tsm, int tw, int trep, GH64* out_tail, bool last, int tid, int nthr) {
+  const int per_plane = 256 * tw * trep;
+  const int per_bin = tw * trep;
+  for (int idx = tid; idx < PL * per_plane; idx += nthr) {
+    const int val = tsm[idx];
+    if (val == 0) continue;
+    const bool is_h = idx >= per_plane;
+    const int e = is_h ? idx - per_plane : idx;
+    const int bin = e / per_bin, slot = e & (tw - 1);
+    const bool sp = last ? true : (is_h ? ((unsigned)val >= (unsigned)kSpillThreshold) : (val >= kSpillThreshold || val <= -kSpillThreshold));
+    if (sp) {
+      GH64* o = out_tail + bin * tw + slot;
+      red_global_s64(is_h ? &o->h : &o->g, is_h ? (long long)(unsigned)val : (long long)val);
+      tsm[idx] = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Root pass: contiguous rows, TMA-staged.  One CTA per SM; warp kRootConsumerWarps is the producer.
+// ---------------------------------------------------------------------------------------------
+struct RootCfg {
+  int R;                   // rows per ring stage (TMA box height)
+  int S;                   // ring stages
+  int trep;                // tail replicas in shared memory
+  int box_groups;          // TMA box width / 32
+  unsigned tail_off;       // byte offsets inside dynamic shared memory
+  unsigned ring_off;       // (128 B aligned at run time, slack reserved)
+  unsigned stage_bytes;
+  unsigned total;
+};
+
+template <bool GONLY>
+__global__ void __launch_bounds__((kRootConsumerWarps + 1) * 32, 1)
+hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) {
+  constexpr int PL = GONLY ? 1 : 2;
+  constexpr int NCW = kRootConsumerWarps;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nb = *a.build_count;
   if (nb <= 0) return;
   const unsigned T = a.build_prefix[nb];
   if (T == 0) return;
-  if (a.rows_counter && blockIdx.x == 0 && a.group_base + blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.rows_counter, (unsigned long long)T);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g0 = blockIdx.y * a.ng_chunk;
+  const int ng_here = min(a.ng_chunk, a.ngroups - g0);
+  const bool has_tail = a.tw > 0 && blockIdx.y == gridDim.y - 1;
+  if (a.rows_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.rows_counter, (unsigned long long)T);
+
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const unsigned ring = (smem_base + c.ring_off + 127u) & ~127u;
+  const unsigned bars = ring + (unsigned)c.S * c.stage_bytes;                 // full[S] then empty[S]
+  const unsigned main_tile_bytes = (unsigned)c.R * 32u * (unsigned)c.box_groups;
+  const unsigned gp_off = main_tile_bytes, tail_tile_off = main_tile_bytes + (unsigned)c.R * 8u;
+  const unsigned ntiles = (T + c.R - 1) / c.R;
+
+  // zero the planes, init the barriers
+  {
+    const int words4 = (ng_here * PL * kPlaneBytes + (has_tail ? PL * 256 * a.tw * c.trep * 4 : 0)) / 16;
+    int4* z = reinterpret_cast<int4*>(smem_raw);
+    const int main4 = ng_here * PL * kPlaneBytes / 16;
+    for (int i = threadIdx.x; i < main4; i += blockDim.x) z[i] = make_int4(0, 0, 0, 0);
+    if (has_tail) { int4* zt = reinterpret_cast<int4*>(smem_raw + c.tail_off); for (int i = threadIdx.x; i < words4 - main4; i += blockDim.x) zt[i] = make_int4(0, 0, 0, 0); }
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < c.S; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (c.S + s), NCW); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncthreads();
+
+  const int nid = a.build_nid[0];
+  const size_t slot_entries = (size_t)a.ngroups * kGroupEntries + (size_t)256 * a.tw;
+  GH64* out_slot = a.hist_pool + (size_t)a.hist_slot[nid] * slot_entries;
+  GH64* out_main = out_slot + (size_t)g0 * kGroupEntries;
+  GH64* out_tail = out_slot + (size_t)a.ngroups * kGroupEntries;
+
+  if (warp == NCW) {                                    // ---------------- producer
+    if (lane == 0) {
+      const unsigned tx = main_tile_bytes + (unsigned)c.R * 8u + (has_tail ? (unsigned)c.R * (unsigned)a.tw : 0u);
+      unsigned k = 0;
+      for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+        const unsigned s = k % (unsigned)c.S;
+        if (k >= (unsigned)c.S) mbar_wait(bars + 8u * (c.S + s), ((k / (unsigned)c.S) - 1u) & 1u);
+        const unsigned full = bars + 8u * s, dst = ring + s * c.stage_bytes;
+        const unsigned row0 = t * (unsigned)c.R;
+        mbar_expect_tx(full, tx);
+        tma_load_2d(dst, &tm, g0 * 32, (int)row0, full);
+        bulk_load_1d(dst + gp_off, a.gpair + row0, (unsigned)c.R * 8u, full);
+        if (has_tail) bulk_load_1d(dst + tail_tile_off, a.bins_tail + (size_t)row0 * a.tw, (unsigned)c.R * (unsigned)a.tw, full);
+        const unsigned tp = t + 4u * gridDim.x;        // warm L2 four tiles ahead of this CTA
+        if (tp < ntiles) tma_prefetch_2d(&tm, g0 * 32, (int)(tp * (unsigned)c.R));
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  const float sg = a.scales[0], sh = a.scales[1];
+  const LaneConst lc = make_lane_const(lane);
+  TailConst tc;
+  tc.tw = a.tw; tc.base_g = smem_base + c.tail_off; tc.hplane_bytes = 256u * (unsigned)a.tw * (unsigned)c.trep * 4u;
+  tc.bin_stride = (unsigned)a.tw * (unsigned)c.trep * 4u;
+  tc.rep_off = has_tail ? (unsigned)((lane / a.tw) % c.trep) * (unsigned)a.tw * 4u : 0u;
+  const int units_main = (c.R >> 4) * ng_here;
+  const int upt = units_main + (has_tail ? (c.R >> 5) : 0);
+  const unsigned row_bytes = 32u * (unsigned)c.box_groups;
+  const int tiles_per_window = kWindowRows / c.R;
+  long long accG = 0, accH = 0;
+  int base = 0;                                          // (tile counter * upt) mod NCW: rotates the unit -> warp assignment
+  unsigned k = 0;
+  for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+    const unsigned s = k % (unsigned)c.S;
+    mbar_wait(bars + 8u * s, (k / (unsigned)c.S) & 1u);
+    const unsigned tile = ring + s * c.stage_bytes;
+    const unsigned row0 = t * (unsigned)c.R;
+    int u = warp - base; if (u < 0) u += NCW;
+    for (; u < upt; u += NCW) {
+      if (u < units_main) {
+        const int rb = u / ng_here, g = u - rb * ng_here;
+        const unsigned rowl = (unsigned)(rb << 4) + (unsigned)(lane >> 1);
+        const uint4 w = lds_v4(tile + rowl * row_bytes + (unsigned)g * 32u + (unsigned)(lane & 1) * 16u);
+        const uint2 ghb = lds_v2(tile + gp_off + rowl * 8u);
+        int gq = 0; unsigned hq = 0;
+        if (row0 + rowl < T) { gq = __float2int_rn(__uint_as_float(ghb.x) * sg); hq = (unsigned)__float2int_rn(__uint_as_float(ghb.y) * sh); }
+        if (g == 0 && (lane & 1) == 0) { accG += gq; accH += hq; }
+        accumulate16<GONLY>(lc, smem_base + (unsigned)g * (unsigned)(PL * kPlaneBytes), w, gq, hq);
+      } else {
+        const unsigned rowl = (unsigned)((u - units_main) << 5) + (unsigned)lane;
+        unsigned w0, w1 = 0;
+        if (a.tw == 4) w0 = lds_u32(tile + tail_tile_off + rowl * 4u);
+        else { const uint2 ww = lds_v2(tile + tail_tile_off + rowl * 8u); w0 = ww.x; w1 = ww.y; }
+        const uint2 ghb = lds_v2(tile + gp_off + rowl * 8u);
+        int gq = 0; unsigned hq = 0;
+        if (row0 + rowl < T) { gq = __float2int_rn(__uint_as_float(ghb.x) * sg); hq = (unsigned)__float2int_rn(__uint_as_float(ghb.y) * sh); }
+        else { w0 = 0; w1 = 0; }
+        tail_accumulate<GONLY>(tc, lane, w0, w1, gq, hq);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8u * (c.S + s));
+    base += upt % NCW; if (base >= NCW) base -= NCW;
+    if ((k + 1) % (unsigned)tiles_per_window == 0 && t + gridDim.x < ntiles) {       // overflow check
+      named_bar_sync(1, NCW * 32);
+      spill_main<PL>(reinterpret_cast<int*>(smem_raw), ng_here, out_main, false, threadIdx.x, NCW * 32);
+      if (has_tail) spill_tail<PL>(reinterpret_cast<int*>(smem_raw + c.tail_off), a.tw, c.trep, out_tail, false, threadIdx.x, NCW * 32);
+      named_bar_sync(1, NCW * 32);
+    }
+  }
+  named_bar_sync(1, NCW * 32);
+  spill_main<PL>(reinterpret_cast<int*>(smem_raw), ng_here, out_main, true, threadIdx.x, NCW * 32);
+  if (has_tail) spill_tail<PL>(reinterpret_cast<int*>(smem_raw + c.tail_off), a.tw, c.trep, out_tail, true, threadIdx.x, NCW * 32);
+  if (a.accumulate_sum && blockIdx.y == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { accG += __shfl_xor_sync(0xffffffffu, accG, o); accH += __shfl_xor_sync(0xffffffffu, accH, o); }
+    if (lane == 0 && (accG != 0 || accH != 0)) { red_global_s64(&a.node_sum[nid].g, accG); red_global_s64(&a.node_sum[nid].h, accH); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deeper levels (and the fallback for the root): rows gathered by row id, register-staged.
+// ---------------------------------------------------------------------------------------------
+struct Stage { unsigned id; float2 gh; };
+
+template <int NG, bool TAIL, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_gather_kernel(HistArgs a) {
+  constexpr int NWARPS = NTHREADS / 32;
+  constexpr int kItersPerWindow = kWindowRows / (kSuperRows * NWARPS);     // super-tiles per warp between overflow checks
+  constexpr int U = 2 * NG;                                                // (16-row sub-tile, group) units per super-tile
+  static_assert(kItersPerWindow >= 1, "window too small");
+  extern __shared__ __align__(16) int smem[];                              // per group: G[8192] then H[8192]; then the tail planes
+  const int nb = *a.build_count;
+  if (nb <= 0) return;
+  const unsigned T = a.build_prefix[nb];
+  if (T == 0) return;
+  if (a.rows_counter && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd(a.rows_counter, (unsigned long long)T);
   const unsigned C = gridDim.x;
   unsigned ceff = (T + kMinRowsPerCta - 1) / kMinRowsPerCta;
   ceff = ceff < 1 ? 1 : (ceff > C ? C : ceff);
@@ -123,96 +400,107 @@ __global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(H
   if (r0l >= T) return;
   unsigned r0 = (unsigned)r0l;
   unsigned r1 = (unsigned long long)r0 + chunk > T ? T : r0 + chunk;
-  const int g0 = a.group_base + blockIdx.y * NG;
-  const int ng_here = NG;
+  const int g0 = blockIdx.y * a.ng_chunk;
+  const int ng_here = min(min(a.ng_chunk, NG), a.ngroups - g0);
+  const bool has_tail = TAIL && a.tw > 0 && blockIdx.y == gridDim.y - 1;
   const uint8_t* gbins = a.bins + (int64_t)g0 * kSlots;
   const float sg = a.scales[0], sh = a.scales[1];
   const unsigned smem_g = (unsigned)__cvta_generic_to_shared(smem);
   const int64_t row_stride = (int64_t)a.row_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const LaneConst lc = make_lane_const(lane);
+  const int colbyte = (lane & 1) * 16, rowlane = lane >> 1;
+  TailConst tc;
+  tc.tw = TAIL ? a.tw : 4; tc.base_g = smem_g + (unsigned)(NG * 2 * kPlaneBytes); tc.hplane_bytes = 256u * (unsigned)tc.tw * 4u;
+  tc.bin_stride = (unsigned)tc.tw * 4u; tc.rep_off = 0u;
 
-  // Lane roles.  NG == 1: two lanes per row (16 B halves of the 32 B slice), 16 rows per LDG.128 instruction.
-  // NG == 2: four lanes per row (16 B chunks of the row's 64 B = group A low/high, group B low/high), 8 rows per
-  // instruction, so an instruction touches each 64 B burst exactly once (half the L1 wavefronts of two 32 B loads).
-  // `rot` is the per-lane rotation of the 16-step slot schedule: the 16 lanes that share a bank range (same `half`)
-  // get 16 different rotations, so every ATOMS instruction hits 32 distinct banks.
-  constexpr int NSUB = NG == 2 ? 4 : 2;               // sub-tiles per 32-position super-tile
-  constexpr int SUBROWS = 32 / NSUB;
-  LaneConst lc;
-  { int rot, half; unsigned plane;
-    if (NG == 2) { const int q8 = lane >> 2, c = lane & 3; rot = 2 * q8 + (c >> 1); half = c & 1; plane = (unsigned)(c >> 1) * 2u * kPlaneBytes; lc.rowlane = q8; lc.colbyte = c * 16; }
-    else { rot = lane >> 1; half = lane & 1; plane = 0u; lc.rowlane = lane >> 1; lc.colbyte = half * 16; }
-    lc.qw = rot >> 2; const int qb = rot & 3;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { lc.sel[j] = 0x4440u | (unsigned)((j + qb) & 3); lc.offb[j] = 4u * (unsigned)((j + qb) & 3);
-      lc.offw[j] = smem_g + plane + 64u * (unsigned)half + 16u * (unsigned)((j + lc.qw) & 3); } }
-
-  const int entries = ng_here * 2 * kGroupEntries;
-  for (int i = threadIdx.x; i < entries / 4; i += NTHREADS) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
+  {
+    const int words4 = (NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * tc.tw * 4 : 0)) / 16;
+    for (int i = threadIdx.x; i < words4; i += NTHREADS) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
+  }
   __syncthreads();
 
   int b = 0;   // first build node whose range contains r0
   { int lo = 0, hi = nb; while (lo < hi) { int mid = (lo + hi) >> 1; if (a.build_prefix[mid + 1] > r0) hi = mid; else lo = mid + 1; } b = lo; }
 
+  const size_t slot_entries = (size_t)a.ngroups * kGroupEntries + (size_t)256 * a.tw;
   const Stage none{0xffffffffu, make_float2(0.f, 0.f)};
   while (r0 < r1) {
     const unsigned nbeg = a.build_prefix[b], nend_node = a.build_prefix[b + 1];
     const unsigned nend = nend_node < r1 ? nend_node : r1;
     const int nid = a.build_nid[b];
     const unsigned seg = a.seg_begin[nid];
-    GH64* out = a.hist_pool + ((int64_t)a.hist_slot[nid] * a.ngroups + g0) * kGroupEntries;
+    GH64* out_slot = a.hist_pool + (size_t)a.hist_slot[nid] * slot_entries;
+    GH64* out_main = out_slot + (size_t)g0 * kGroupEntries;
+    GH64* out_tail = out_slot + (size_t)a.ngroups * kGroupEntries;
     long long accG = 0, accH = 0;
     const unsigned pa = seg + (r0 - nbeg), pb = seg + (nend - nbeg);
     const unsigned nsuper = (pb - pa + kSuperRows - 1) / kSuperRows;
     const unsigned iters = (nsuper + NWARPS - 1) / NWARPS;          // same for every warp: barriers stay aligned
 
-    // Three-stage software pipeline per warp over super-tiles of 32 positions; it runs THROUGH the overflow-check
-    // barriers (the loads of the next super-tiles stay in flight while the CTA spills), so no window restarts cold:
-    //   stage A: row ids + (g,h) of super-tile s+2 (coalesced, one position per lane)
-    //   stage B: bin slices of super-tile s+1 (LDG.128 per lane and group, addresses from stage A via SHFL)
-    //   stage C: conflict-free ATOMS pairs of super-tile s
+    // Software pipeline per warp over super-tiles of 32 positions; it runs THROUGH the overflow-check barriers:
+    //   row ids + (g,h) two super-tiles ahead (coalesced, one position per lane);
+    //   bin chunks (LDG.128 per lane and unit) one super-tile ahead, ROLLING: the register of unit k is refilled with
+    //   unit k of the next super-tile right after it has been consumed (U + 1 loads in flight per lane at all times);
+    //   conflict-free ATOMS pairs now.
     auto load_ids = [&](unsigned st) -> Stage {
       Stage s_ = none;
       unsigned p = pa + st * kSuperRows + lane;
       if (st < nsuper && p < pb) { s_.id = a.ridx ? __ldg(a.ridx + p) : p; s_.gh = ldg_nc_f2(a.gpair + p); }
       return s_;
     };
-    auto load_rows = [&](unsigned ids, Rows<NSUB>& r) {
-#pragma unroll
-      for (int t = 0; t < NSUB; ++t) {
-        const unsigned rid = __shfl_sync(0xffffffffu, ids, t * SUBROWS + lc.rowlane);
-        r.w[t] = rid != 0xffffffffu ? ldg_nc_v4(gbins + (int64_t)rid * row_stride + lc.colbyte) : make_uint4(0, 0, 0, 0);
+    auto load_unit = [&](unsigned ids, int k) -> uint4 {
+      const int sub = k / NG, g = k - sub * NG;
+      const unsigned rid = __shfl_sync(0xffffffffu, ids, sub * 16 + rowlane);
+      return (rid != 0xffffffffu && g < ng_here) ? ldg_nc_v4(gbins + (int64_t)rid * row_stride + g * 32 + colbyte) : make_uint4(0, 0, 0, 0);
+    };
+    auto load_tail = [&](unsigned id, unsigned& t0, unsigned& t1) {
+      t0 = 0; t1 = 0;
+      if (has_tail && id != 0xffffffffu) {
+        if (tc.tw == 4) t0 = ldg_nc_u32(a.bins_tail + (int64_t)id * 4);
+        else { const uint2 v = ldg_nc_v2(a.bins_tail + (int64_t)id * 8); t0 = v.x; t1 = v.y; }
       }
     };
     Stage cur = load_ids(warp);
     Stage nxt = load_ids(warp + NWARPS);
-    Rows<NSUB> rows; load_rows(cur.id, rows);
+    uint4 w[U]; unsigned t0 = 0, t1 = 0;
+#pragma unroll
+    for (int k = 0; k < U; ++k) w[k] = load_unit(cur.id, k);
+    if (TAIL) load_tail(cur.id, t0, t1);
     for (unsigned it = 0; it < iters; ++it) {
       const unsigned s = warp + it * NWARPS;
       Stage nn = load_ids(s + 2 * NWARPS);
-      Rows<NSUB> nrows; load_rows(nxt.id, nrows);
-      if (s < nsuper) {
-        const int gq_l = __float2int_rn(cur.gh.x * sg);
-        const unsigned hq_l = (unsigned)__float2int_rn(cur.gh.y * sh);
-        accG += gq_l; accH += hq_l;
+      const bool active = s < nsuper;
+      const int gq_l = __float2int_rn(cur.gh.x * sg);
+      const unsigned hq_l = (unsigned)__float2int_rn(cur.gh.y * sh);
+      accG += gq_l; accH += hq_l;
 #pragma unroll
-        for (int t = 0; t < NSUB; ++t) {
-          const int gq = __shfl_sync(0xffffffffu, gq_l, t * SUBROWS + lc.rowlane);
-          const unsigned hq = __shfl_sync(0xffffffffu, hq_l, t * SUBROWS + lc.rowlane);
-          accumulate16(lc, rows.w[t], gq, hq);
+      for (int k = 0; k < U; ++k) {
+        const int sub = k / NG, g = k - sub * NG;
+        if (active && g < ng_here) {
+          const int gq = __shfl_sync(0xffffffffu, gq_l, sub * 16 + rowlane);
+          const unsigned hq = __shfl_sync(0xffffffffu, hq_l, sub * 16 + rowlane);
+          accumulate16<false>(lc, smem_g + (unsigned)(g * 2 * kPlaneBytes), w[k], gq, hq);
         }
+        w[k] = load_unit(nxt.id, k);
       }
-      rows = nrows; cur = nxt; nxt = nn;
-      if ((it + 1) % kItersPerWindow == 0 && it + 1 < iters) {       // overflow check: at most 4096 rows since the last one
+      if (TAIL) {
+        if (active && has_tail) tail_accumulate<false>(tc, lane, t0, t1, gq_l, hq_l);
+        load_tail(nxt.id, t0, t1);
+      }
+      cur = nxt; nxt = nn;
+      if ((it + 1) % kItersPerWindow == 0 && it + 1 < iters) {       // overflow check: at most kWindowRows rows since the last one
         __syncthreads();
-        spill_pass<NTHREADS>(smem, ng_here, out, false);
+        spill_main<2>(smem, ng_here, out_main, false, threadIdx.x, NTHREADS);
+        if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, 1, out_tail, false, threadIdx.x, NTHREADS);
         __syncthreads();
       }
     }
     __syncthreads();
-    spill_pass<NTHREADS>(smem, ng_here, out, true);
+    spill_main<2>(smem, ng_here, out_main, true, threadIdx.x, NTHREADS);
+    if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, 1, out_tail, true, threadIdx.x, NTHREADS);
     __syncthreads();
-    if (a.accumulate_sum && g0 == 0) {
+    if (a.accumulate_sum && blockIdx.y == 0) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { accG += __shfl_xor_sync(0xffffffffu, accG, o); accH += __shfl_xor_sync(0xffffffffu, accH, o); }
       if (lane == 0 && (accG != 0 || accH != 0)) { red_global_s64(&a.node_sum[nid].g, accG); red_global_s64(&a.node_sum[nid].h, accH); }
@@ -221,39 +509,126 @@ __global__ void __launch_bounds__(NTHREADS, NG == 2 ? 1 : 3) hist_build_kernel(H
   }
 }
 
-int hist_grid_x(int num_sms, int ngroups) {
-  if (ngroups == 1) return num_sms * 3;
-  const int pairs = ngroups / 2;
-  const int x = (num_sms + pairs - 1) / pairs;
-  return x > 0 ? x : 1;
+// ---------------------------------------------------------------------------------------------
+// host side: kernel selection, shared-memory plan of the root kernel, tensor maps
+// ---------------------------------------------------------------------------------------------
+static thread_local const char* g_last_kernel = "none";
+const char* hist_last_kernel() { return g_last_kernel; }
+
+static int chunks_for(int ngroups) { return (ngroups + 2) / 3; }
+static int groups_per_chunk(int ngroups) { const int nc = chunks_for(ngroups); return (ngroups + nc - 1) / nc; }
+
+// Shared-memory plan of hist_root_kernel; returns false when not even a minimal ring fits next to the planes.
+static bool root_plan(int ngc, int tw, bool gonly, RootCfg* c) {
+  const int PL = gonly ? 1 : 2;
+  const unsigned main_b = (unsigned)ngc * PL * kPlaneBytes;
+  const unsigned avail = kMaxSmem - 128 /* alignment slack */ - 2 * 8 * 8 /* barriers */;
+  int trep = tw ? 32 / tw : 0;
+  unsigned tail_b = (unsigned)PL * 256u * tw * trep * 4u;
+  const unsigned min_ring = 3u * 64u * (32u * ngc + 8u + tw);
+  if (tw && main_b + tail_b + min_ring > avail) { trep = 1; tail_b = (unsigned)PL * 256u * tw * 4u; }
+  if (main_b + tail_b + min_ring > avail) return false;
+  const unsigned ring_avail = avail - main_b - tail_b;
+  int R = ngc >= 3 ? 128 : (ngc == 2 ? 192 : 256);
+  unsigned stage = (unsigned)R * (32u * ngc + 8u + tw);
+  int S = (int)(ring_avail / stage);
+  while (S < 4 && R > 64) { R = R > 128 ? 128 : 64; stage = (unsigned)R * (32u * ngc + 8u + tw); S = (int)(ring_avail / stage); }
+  if (S > 8) S = 8;
+  if (S < 2) return false;
+  c->R = R; c->S = S; c->trep = trep; c->box_groups = ngc; c->tail_off = main_b; c->ring_off = main_b + tail_b; c->stage_bytes = stage;
+  c->total = main_b + tail_b + 128 + (unsigned)S * stage + 2 * 8 * (unsigned)S;
+  return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); p = nullptr; }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// tensor map of the main block [n][row_stride] uint8 with box {32 * box_groups, R}; cached per (pointer, shape, box)
+static bool get_tensor_map(const uint8_t* bins, int64_t n, int row_stride, int box_groups, int R, CUtensorMap* out) {
+  typedef std::tuple<const void*, int64_t, int, int, int> Key;
+  static std::map<Key, CUtensorMap> cache; static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  const Key key(bins, n, row_stride, box_groups, R);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)row_stride, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)row_stride};
+  const cuuint32_t box[2] = {(cuuint32_t)(32 * box_groups), (cuuint32_t)R};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(bins), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 64) cache.clear();
+  cache[key] = tm; *out = tm;
+  return true;
+}
+
+template <int NG, bool TAIL, int NT> static void set_gather_attr() {
+  CUDA_OK(cudaFuncSetAttribute(hist_gather_kernel<NG, TAIL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * 8 * 4 : 0)));
 }
 
 void hist_configure() {
   static bool configured = false;
   if (configured) return;
-  CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kPlaneBytes));
-  CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<2, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPlaneBytes));
-  CUDA_OK(cudaFuncSetAttribute(hist_build_kernel<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kPlaneBytes));
+  set_gather_attr<1, false, 256>(); set_gather_attr<1, true, 256>();
+  set_gather_attr<2, false, 768>(); set_gather_attr<2, true, 768>();
+  set_gather_attr<3, false, 768>(); set_gather_attr<3, true, 768>();
+  CUDA_OK(cudaFuncSetAttribute(hist_root_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CUDA_OK(cudaFuncSetAttribute(hist_root_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   configured = true;
 }
 
-void launch_hist_build(const HistArgs& a_in, int grid_x, cudaStream_t stream) {
+template <int NG, bool TAIL, int NT>
+static void launch_gather(const HistArgs& a, int gx, int nchunks, cudaStream_t stream) {
+  const int smem = NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * a.tw * 4 : 0);
+  hist_gather_kernel<NG, TAIL, NT><<<dim3(gx, nchunks), NT, smem, stream>>>(a);
+}
+
+void launch_hist_build(const HistArgs& a_in, int num_sms, cudaStream_t stream) {
   HistArgs a = a_in;
-  const int pairs = a.ngroups / 2;
-  // experiment knob for the next round: 32 warps/SM at 64 registers (small spills) instead of 24 warps at 80
-  static const bool wide = getenv("B200XGB_HIST_THREADS") != nullptr && atoi(getenv("B200XGB_HIST_THREADS")) == 1024;
-  if (pairs > 0) {
-    a.group_base = 0;
-    if (wide) hist_build_kernel<2, 1024><<<dim3(grid_x, pairs), 1024, 4 * kPlaneBytes, stream>>>(a);
-    else hist_build_kernel<2, 768><<<dim3(grid_x, pairs), 768, 4 * kPlaneBytes, stream>>>(a);
-    ++g_kernel_launches;
-    CUDA_OK(cudaGetLastError());
+  const int nchunks = chunks_for(a.ngroups);
+  a.ng_chunk = groups_per_chunk(a.ngroups);
+  static const bool no_tma = getenv("B200XGB_NO_TMA") != nullptr;
+  if (a.ridx == nullptr && !no_tma && !a.force_gather) {
+    RootCfg c; CUtensorMap tm;
+    const bool gonly = a.g_only != 0;
+    if (root_plan(a.ng_chunk, a.tw, gonly, &c) && get_tensor_map(a.bins, a.n, a.row_stride, c.box_groups, c.R, &tm)) {
+      const int gx = num_sms / nchunks > 0 ? num_sms / nchunks : 1;
+      if (gonly) hist_root_kernel<true><<<dim3(gx, nchunks), (kRootConsumerWarps + 1) * 32, c.total, stream>>>(tm, a, c);
+      else hist_root_kernel<false><<<dim3(gx, nchunks), (kRootConsumerWarps + 1) * 32, c.total, stream>>>(tm, a, c);
+      g_last_kernel = gonly ? "hist_root_kernel<GONLY>" : "hist_root_kernel<GH>";
+      ++g_kernel_launches;
+      CUDA_OK(cudaGetLastError());
+      return;
+    }
   }
-  if (a.ngroups & 1) {                       // single (or odd last) group: 64 KB CTAs, three per SM
-    a.group_base = a.ngroups - 1;
-    hist_build_kernel<1, 256><<<dim3(pairs > 0 ? grid_x : hist_grid_x(148, 1), 1), 256, 2 * kPlaneBytes, stream>>>(a); ++g_kernel_launches;
-    CUDA_OK(cudaGetLastError());
+  B200_CHECK(!a.g_only || a.ridx == nullptr, "hist: G-only accumulation is a root-pass mode");
+  B200_CHECK(!a.g_only, "hist: the G-only root pass needs the TMA kernel (tensor-map creation failed or B200XGB_NO_TMA is set)");
+  const bool tail = a.tw > 0;
+  const int ng = a.ng_chunk;
+  if (ng == 1) {
+    const int per_sm = tail ? 2 : 3;
+    const int gx = (num_sms * per_sm + nchunks - 1) / nchunks;
+    if (tail) launch_gather<1, true, 256>(a, gx, nchunks, stream); else launch_gather<1, false, 256>(a, gx, nchunks, stream);
+  } else {
+    const int gx = (num_sms + nchunks - 1) / nchunks;
+    if (ng == 2) { if (tail) launch_gather<2, true, 768>(a, gx, nchunks, stream); else launch_gather<2, false, 768>(a, gx, nchunks, stream); }
+    else { if (tail) launch_gather<3, true, 768>(a, gx, nchunks, stream); else launch_gather<3, false, 768>(a, gx, nchunks, stream); }
   }
+  g_last_kernel = "hist_gather_kernel";
+  ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
 }
 
 }  // namespace b200

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) gradient_kernel(GradArgs a) {
         float h = fmaxf(2.0f * pk * (1.0f - pk) * w, 1e-16f);
         float g = (label == k ? pk - 1.0f : pk) * w;
         if (dropped) { g = 0.f; h = 0.f; }
-        a.gpair[(int64_t)k * a.n + r] = make_float2(g, h);
+        a.gpair[(int64_t)k * a.gp_stride + r] = make_float2(g, h);
         mg = fmaxf(mg, fabsf(g)); mh = fmaxf(mh, h);
       }
     } else {
@@ -85,48 +85,46 @@ __global__ void __launch_bounds__(256) sum_gpair_kernel(const float2* gp, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
-// binning: float matrix (row-major, NaN = missing) -> uint8 feature-group blocks [g][n][32]
+// binning: float matrix (row-major, NaN = missing) -> uint8 codes in the layout of engine.h BinnedMatrix:
+// main [n][ngroups*32] (byte column c == feature c) and tail [n][tw] (tail slot s == feature ngroups*32 + s)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bin_kernel(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups,
-                                                  const int* cut_ptrs, const float* cut_vals, uint8_t* bins) {
-  const int64_t total = n_chunk * ngroups * kSlots;
+__device__ __forceinline__ uint8_t bin_of(float v, const float* c, int nc) {
+  if (isnan(v)) return (uint8_t)kMissingBin;
+  int lo = 0, hi = nc;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (c[mid] > v) hi = mid; else lo = mid + 1; }
+  if (lo >= nc) lo = nc - 1;
+  return (uint8_t)lo;
+}
+
+__global__ void __launch_bounds__(256) bin_kernel(const float* X, int64_t n, int F, int ngroups, int tw, const int* cut_ptrs, const float* cut_vals,
+                                                  uint8_t* bins, uint8_t* bins_tail) {
+  const int W = ngroups * kSlots + tw;                  // byte columns per row over both blocks
+  const int64_t total = n * W;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int s = (int)(idx % kSlots);
-    const int64_t t = idx / kSlots;
-    const int g = (int)(t % ngroups);
-    const int64_t r = t / ngroups;
-    const int f = g * fpg + s;
+    const int c = (int)(idx % W);
+    const int64_t r = idx / W;
     uint8_t b = 0;
-    if (s < fpg && f < F) {
-      float v = X[r * F + f];
-      if (isnan(v)) b = kMissingBin;
-      else {
-        const float* c = cut_vals + cut_ptrs[f];
-        int nc = cut_ptrs[f + 1] - cut_ptrs[f];
-        int lo = 0, hi = nc;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (c[mid] > v) hi = mid; else lo = mid + 1; }
-        if (lo >= nc) lo = nc - 1;
-        b = (uint8_t)lo;
-      }
-    }
-    bins[((row0 + r) * ngroups + g) * kSlots + s] = b;      // row-major [n][ngroups*32]: idx order == address order
+    if (c < F) b = bin_of(X[r * F + c], cut_vals + cut_ptrs[c], cut_ptrs[c + 1] - cut_ptrs[c]);     // byte column == feature index in both blocks
+    if (c < ngroups * kSlots) bins[r * (ngroups * kSlots) + c] = b;
+    else bins_tail[r * tw + (c - ngroups * kSlots)] = b;
   }
-  (void)n_total;
 }
 
 // column-major copy [F][n] of the binned matrix (used by the 1-byte-per-row consumers: partition, cache update)
-__global__ void __launch_bounds__(256) transpose_bins_kernel(const uint8_t* bins, int64_t n, int F, int fpg, int ngroups, uint8_t* bins_col) {
+__global__ void __launch_bounds__(256) transpose_bins_kernel(const uint8_t* bins, const uint8_t* bins_tail, int64_t n, int F, int ngroups, int tw, uint8_t* bins_col) {
   __shared__ uint8_t tile[256][kSlots + 1];
-  const int g = blockIdx.y;
+  const int g = blockIdx.y;                             // ngroups == the tail block
+  const bool is_tail = g == ngroups;
+  const int width = is_tail ? tw : kSlots;
   const int64_t r0 = (int64_t)blockIdx.x * 256;
-  for (int i = threadIdx.x; i < 256 * kSlots; i += 256) {
-    int rr = i / kSlots, s = i % kSlots;
+  for (int i = threadIdx.x; i < 256 * width; i += 256) {
+    int rr = i / width, s = i % width;
     int64_t r = r0 + rr;
-    tile[rr][s] = r < n ? bins[(r * ngroups + g) * kSlots + s] : 0;
+    tile[rr][s] = r < n ? (is_tail ? bins_tail[r * tw + s] : bins[r * (ngroups * kSlots) + g * kSlots + s]) : 0;
   }
   __syncthreads();
   const int64_t r = r0 + threadIdx.x;
-  if (r < n) for (int s = 0; s < fpg; ++s) { int f = g * fpg + s; if (f < F) bins_col[(int64_t)f * n + r] = tile[threadIdx.x][s]; }
+  if (r < n) for (int s = 0; s < width; ++s) { int f = g * kSlots + s; if (f < F) bins_col[(int64_t)f * n + r] = tile[threadIdx.x][s]; }
 }
 
 __global__ void __launch_bounds__(256) count_nan_kernel(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out) {
@@ -251,16 +249,15 @@ void launch_gradient(const GradArgs& a, cudaStream_t s) {
 void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s) {
   sum_gpair_kernel<<<grid_for(n), 256, 0, s>>>(gp, n, out); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
-void launch_bin(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups, const int* cut_ptrs,
-                const float* cut_vals, uint8_t* bins, cudaStream_t s) {
-  if (n_chunk == 0) return;
-  bin_kernel<<<grid_for(n_chunk * ngroups * kSlots, 256, 148 * 32), 256, 0, s>>>(X, n_chunk, row0, n_total, F, fpg, ngroups, cut_ptrs, cut_vals, bins); ++g_kernel_launches;
+void launch_bin(const float* X, int64_t n, int F, int ngroups, int tw, const int* cut_ptrs, const float* cut_vals, uint8_t* bins, uint8_t* bins_tail, cudaStream_t s) {
+  if (n == 0) return;
+  bin_kernel<<<grid_for(n * (ngroups * kSlots + tw), 256, 148 * 32), 256, 0, s>>>(X, n, F, ngroups, tw, cut_ptrs, cut_vals, bins, bins_tail); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
 }
-void launch_transpose_bins(const uint8_t* bins, int64_t n, int F, int fpg, int ngroups, uint8_t* bins_col, cudaStream_t s) {
+void launch_transpose_bins(const uint8_t* bins, const uint8_t* bins_tail, int64_t n, int F, int ngroups, int tw, uint8_t* bins_col, cudaStream_t s) {
   if (n == 0) return;
-  dim3 grid((unsigned)((n + 255) / 256), ngroups);
-  transpose_bins_kernel<<<grid, 256, 0, s>>>(bins, n, F, fpg, ngroups, bins_col); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+  dim3 grid((unsigned)((n + 255) / 256), ngroups + (tw > 0 ? 1 : 0));
+  transpose_bins_kernel<<<grid, 256, 0, s>>>(bins, bins_tail, n, F, ngroups, tw, bins_col); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_count_nan(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out, cudaStream_t s) {
   if (count == 0) return;

@@ -7,7 +7,8 @@ namespace b200 {
 struct GradArgs {
   const float* margin;      // n x K row-major, nullptr = all zero (base-score stump)
   const float* label; const float* weight;
-  float2* gpair;            // [K][n]
+  float2* gpair;            // [K][gp_stride]
+  int64_t gp_stride;        // rows reserved per class (>= n, multiple of 64: keeps class blocks 16 B aligned for the TMA bulk copies)
   unsigned* absmax;         // max|g|, max h as float bits (atomicMax), may be nullptr
   int* err;                 // 1 = logistic label range, 2 = multiclass label range
   int64_t n, row_offset;    // row_offset: global index of local row 0 (multi-GPU subsampling stream)
@@ -36,9 +37,8 @@ struct MetricArgs {
 
 void launch_gradient(const GradArgs& a, cudaStream_t s);
 void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s);
-void launch_bin(const float* X, int64_t n_chunk, int64_t row0, int64_t n_total, int F, int fpg, int ngroups, const int* cut_ptrs,
-                const float* cut_vals, uint8_t* bins, cudaStream_t s);
-void launch_transpose_bins(const uint8_t* bins, int64_t n, int F, int fpg, int ngroups, uint8_t* bins_col, cudaStream_t s);
+void launch_bin(const float* X, int64_t n, int F, int ngroups, int tw, const int* cut_ptrs, const float* cut_vals, uint8_t* bins, uint8_t* bins_tail, cudaStream_t s);
+void launch_transpose_bins(const uint8_t* bins, const uint8_t* bins_tail, int64_t n, int F, int ngroups, int tw, uint8_t* bins_col, cudaStream_t s);
 void launch_count_nan(const float* X, int64_t count, float missing, int use_missing, unsigned long long* out, cudaStream_t s);
 void launch_replace_missing(float* X, int64_t count, float missing, cudaStream_t s);
 void launch_predict(const PredictArgs& a, cudaStream_t s);

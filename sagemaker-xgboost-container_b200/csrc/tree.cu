@@ -77,11 +77,15 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalArgs a) {
   const int li = blockIdx.x;
   if (li >= a.gs.level_count[a.level]) return;
   const int nid = a.gs.level_nodes[(size_t)a.level * a.max_level_nodes + li];
-  const int group = blockIdx.y;
-  const GH64* hist = a.hist_pool + ((int64_t)a.gs.hist_slot[nid] * a.ngroups + group) * kGroupEntries;
+  const int group = blockIdx.y;                    // 0 .. ngroups-1: full groups; ngroups: the narrow tail block
+  const bool is_tail = group == a.ngroups;
+  const int nblocks = a.ngroups + (a.tw > 0 ? 1 : 0);
+  const int64_t slot_entries = (int64_t)a.ngroups * kGroupEntries + 256 * a.tw;
+  const GH64* hist = a.hist_pool + (int64_t)a.gs.hist_slot[nid] * slot_entries + (int64_t)group * kGroupEntries;
+  const int stride = is_tail ? a.tw : kSlots;      // accumulators per bin row
   const int slot = threadIdx.x & 31, seg = threadIdx.x >> 5;
-  const int f = group * a.fpg + slot;
-  const bool active = slot < a.fpg && f < a.F && (a.feat_mask == nullptr || a.feat_mask[f] != 0);
+  const int f = group * kSlots + slot;
+  const bool active = slot < stride && f < a.F && (a.feat_mask == nullptr || a.feat_mask[f] != 0);
   const int nbf = active ? a.cut_ptrs[f + 1] - a.cut_ptrs[f] : 0;
   const double isg = (double)a.gs.scales[2], ish = (double)a.gs.scales[3];
   const GH64 tot = a.gs.node_sum[nid];
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalArgs a) {
   __shared__ unsigned long long wkey[8];
   const int b0 = seg * 32;
   long long sG = 0, sH = 0;
-  for (int i = 0; i < 32; ++i) { int b = b0 + i; if (b < nbf) { GH64 v = hist[b * kSlots + slot]; sG += v.g; sH += v.h; } }
+  for (int i = 0; i < 32; ++i) { int b = b0 + i; if (b < nbf) { GH64 v = hist[b * stride + slot]; sG += v.g; sH += v.h; } }
   segG[seg][slot] = sG; segH[seg][slot] = sH;
   __syncthreads();
   long long pG = 0, pH = 0, tG = 0, tH = 0;
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalArgs a) {
   for (int i = 0; i < 32; ++i) {          // forward scan: missing goes right, threshold = cut[b]
     int b = b0 + i;
     if (b < nbf) {
-      GH64 v = hist[b * kSlots + slot]; cG += v.g; cH += v.h;
+      GH64 v = hist[b * stride + slot]; cG += v.g; cH += v.h;
       double GL = (double)cG * isg, HL = (double)cH * ish;
       double GR = (double)(tot.g - cG) * isg, HR = (double)(tot.h - cH) * ish;
       if (HL >= mcw && HR >= mcw) {
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalArgs a) {
           unsigned long long k = cand_key(lc, f, ord);
           if (k > bkey) { bkey = k; best.loss_chg = lc; best.feature = f; best.bin = b - 1; best.dleft = 1; best.ord = ord; best.GL = lG; best.HL = lH; }
         }
-        GH64 v = hist[b * kSlots + slot]; rG -= v.g; rH -= v.h;
+        GH64 v = hist[b * stride + slot]; rG -= v.g; rH -= v.h;
       }
     }
   }
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalArgs a) {
   unsigned long long m = 0ull;
 #pragma unroll
   for (int s = 0; s < 8; ++s) m = wkey[s] > m ? wkey[s] : m;
-  SplitCand* out = a.gs.best_group + (size_t)nid * a.ngroups + group;
+  SplitCand* out = a.gs.best_group + (size_t)nid * nblocks + group;
   if (m == 0ull) { if (threadIdx.x == 0) { SplitCand z; z.loss_chg = 0.f; z.feature = 0; z.bin = -1; z.dleft = 0; z.ord = 0; z.GL = 0; z.HL = 0; *out = z; } }
   else if (bkey == m) *out = best;        // keys are unique per (feature, ord)
 }
@@ -446,11 +450,10 @@ __global__ void __launch_bounds__(256) build_prefix_kernel(GrowState gs) {
 }
 
 // sibling = parent - built child (exact int64)
-__global__ void __launch_bounds__(256) subtract_kernel(GrowState gs, GH64* pool, int ngroups) {
+__global__ void __launch_bounds__(256) subtract_kernel(GrowState gs, GH64* pool, size_t stride) {
   const int r = blockIdx.x;
   if (r >= *gs.build_count) return;
   const int bld = gs.build_nid[r], sub = gs.build_sub_nid[r];
-  const size_t stride = (size_t)ngroups * kGroupEntries;
   const GH64* hb = pool + (size_t)gs.hist_slot[bld] * stride;
   const GH64* hp = pool + (size_t)gs.build_parent_slot[r] * stride;
   GH64* hs = pool + (size_t)gs.hist_slot[sub] * stride;
@@ -467,7 +470,7 @@ void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int 
 }
 void launch_scales(const GrowState& gs, cudaStream_t s) { scales_kernel<<<1, 32, 0, s>>>(gs); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s) {
-  dim3 grid(max_nodes_level, a.ngroups); eval_kernel<<<grid, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+  dim3 grid(max_nodes_level, a.ngroups + (a.tw > 0 ? 1 : 0)); eval_kernel<<<grid, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_apply(const ApplyArgs& a, cudaStream_t s) { apply_kernel<<<1, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s) {
@@ -480,8 +483,8 @@ void launch_update_margin(const TreeArrays& t, const int* n_nodes, const uint8_t
   if (n == 0) return;
   update_margin_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, s>>>(t, n_nodes, bins_col, n, has_missing, margin, K, k); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
-void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s) {
-  dim3 grid(max_build, 8 * ngroups); subtract_kernel<<<grid, 256, 0, s>>>(gs, pool, ngroups); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+void launch_subtract(const GrowState& gs, GH64* pool, size_t slot_entries, int max_build, cudaStream_t s) {
+  dim3 grid(max_build, (unsigned)((slot_entries + 1023) / 1024)); subtract_kernel<<<grid, 256, 0, s>>>(gs, pool, slot_entries); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 
 }  // namespace b200

@@ -13,12 +13,12 @@ struct TrainParamDev {
 
 struct EvalArgs {
   const GH64* hist_pool; GrowState gs; const int* cut_ptrs; const unsigned char* feat_mask;
-  TrainParamDev p; int F, ngroups, fpg, has_missing, level, max_level_nodes;
+  TrainParamDev p; int F, ngroups, tw, ntail, has_missing, level, max_level_nodes;
 };
 
 struct ApplyArgs {
   GrowState gs; TreeArrays tree; const int* cut_ptrs; const float* cut_vals; const float* min_vals;
-  TrainParamDev p; unsigned* scratch; int ngroups, level, max_level_nodes, next_base, next_half;
+  TrainParamDev p; unsigned* scratch; int ngroups /* candidate blocks per node: groups + tail */, level, max_level_nodes, next_base, next_half;
 };
 
 struct PartArgs {
@@ -28,9 +28,11 @@ struct PartArgs {
 };
 
 struct HistArgs {
-  const uint8_t* bins;          // row-major [n][ngroups*32 B]
+  const uint8_t* bins;          // main: row-major [n][ngroups*32 B]
+  const uint8_t* bins_tail;     // tail: row-major [n][tw B], nullptr when tw == 0
   int64_t n;
   int row_stride;               // ngroups * 32
+  int tw;                       // tail width in bytes (0, 4, 8)
   const float2* gpair;          // (g, h) by POSITION in the row-id buffer (== by row at the root)
   const unsigned* ridx;         // row ids by segment position; nullptr = identity (root)
   const int* build_count;       // number of nodes to build
@@ -39,23 +41,25 @@ struct HistArgs {
   const unsigned* seg_begin;    // per nid
   const int* hist_slot;         // per nid
   const float* scales;          // sg, sh
-  GH64* hist_pool;              // slot stride = ngroups * kGroupEntries
+  GH64* hist_pool;              // slot stride = hist_slot_entries(ngroups, tw)
   GH64* node_sum;               // per nid, accumulated only when accumulate_sum
   int ngroups;
-  int group_base;               // first group handled by blockIdx.y == 0 (set by the launcher)
+  int ng_chunk;                 // groups per blockIdx.y chunk (set by the launcher)
   int accumulate_sum;
+  int g_only;                   // constant-hessian root pass: accumulate G only (the slot already holds the cached H plane)
+  int force_gather;             // tests / profiling: use hist_gather_kernel even for the contiguous root pass
   unsigned long long* rows_counter;   // optional: += rows processed by this launch (profiling)
 };
 
-void launch_hist_build(const HistArgs& a, int grid_x, cudaStream_t stream);
-int hist_grid_x(int num_sms, int ngroups);
+void launch_hist_build(const HistArgs& a, int num_sms, cudaStream_t stream);
 void hist_configure();     // one-time function attributes (must happen outside stream capture)
+const char* hist_last_kernel();   // name of the kernel variant the last launch used (profiling / tests)
 void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s);
 void launch_scales(const GrowState& gs, cudaStream_t s);
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s);
 void launch_apply(const ApplyArgs& a, cudaStream_t s);
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s);
 void launch_update_margin(const TreeArrays& t, const int* n_nodes, const uint8_t* bins_col, int64_t n, int has_missing, float* margin, int K, int k, cudaStream_t s);
-void launch_subtract(const GrowState& gs, GH64* pool, int ngroups, int max_build, cudaStream_t s);
+void launch_subtract(const GrowState& gs, GH64* pool, size_t slot_entries, int max_build, cudaStream_t s);
 
 }  // namespace b200

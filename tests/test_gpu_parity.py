@@ -44,19 +44,36 @@ def test_bins_with_missing_values(xgb, oracle):
     np.testing.assert_array_equal(_be().dmatrix_get_bins(d.handle, 256), oracle.bin_matrix(X, optrs, ovals))
 
 
-@pytest.mark.parametrize("n,F", [(1, 3), (17, 5), (4096, 28), (4097, 33), (100003, 50), (300000, 100)])
-def test_root_histogram_bit_exact(xgb, oracle, n, F):
-    """Histogram kernel vs the fixed-point mirror in the oracle: exact int64 equality for ragged sizes."""
-    X, y = synth(n, F, 21, "reg")
+HIST_SHAPES = [(1, 3), (17, 5), (4096, 28), (4097, 33), (100003, 50), (300000, 100), (70001, 36), (50000, 104), (20000, 130)]
+MODE_KERNEL = {0: "hist_root_kernel<GH>", 1: "hist_gather_kernel", 2: "hist_root_kernel<GONLY>"}
+
+
+def _hist_inputs(xgb, n, F, seed=21):
+    X, y = synth(n, F, seed, "reg")
     rng = np.random.default_rng(5)
     gpair = np.stack([rng.standard_normal(n).astype(np.float32) * 3, rng.random(n).astype(np.float32) + 0.01], axis=1)
     d = xgb.DMatrix(X, label=y)
     b = xgb.Booster({"max_bin": 256}, [d])
-    hist, scales, ms = _be().build_root_histogram(b.handle, d.handle, gpair, repeats=1)
+    return X, gpair, d, b
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n,F", HIST_SHAPES)
+def test_root_histogram_bit_exact(xgb, oracle, n, F, mode):
+    """Both histogram kernels (TMA-staged root kernel incl. its G-only variant, gather kernel) vs the fixed-point mirror
+    in the oracle: exact int64 equality for ragged sizes and every feature layout (padded group, 4- and 8-wide tails,
+    two group chunks)."""
+    X, gpair, d, b = _hist_inputs(xgb, n, F)
+    hist, scales, ms, kernel = _be().build_histogram_ex(b.handle, d.handle, gpair, mode=mode)
+    assert kernel == MODE_KERNEL[mode]
     gq = np.rint(gpair[:, 0] * scales[0]).astype(np.int32)
     hq = np.rint(gpair[:, 1] * scales[1]).astype(np.int32)
     bins = _be().dmatrix_get_bins(d.handle, 256)
     ref = oracle.build_hist_fixed(bins, gq, hq)
+    if mode == 2:                      # constant-hessian fast path: only G is accumulated, the H plane is pre-loaded by the caller
+        np.testing.assert_array_equal(hist[:, :, 0], ref[:, :, 0])
+        assert not hist[:, :, 1].any()
+        return
     np.testing.assert_array_equal(hist, ref)
     # and close to the reference-faithful double histogram (same bins, float gradients)
     optrs, ovals, _, _ = oracle.make_cuts(X, 256)
@@ -65,6 +82,51 @@ def test_root_histogram_bit_exact(xgb, oracle, n, F):
         nb = optrs[f + 1] - optrs[f]
         got = hist[f, :nb, 0] / scales[0]
         np.testing.assert_allclose(got, dref[optrs[f]:optrs[f + 1], 0], rtol=0, atol=2e-5 * max(1.0, np.abs(gpair[:, 0]).max()) * np.sqrt(n))
+
+
+@pytest.mark.parametrize("n,F,frac,ordered", [(50000, 28, 0.3, True), (120000, 100, 0.25, True), (30000, 50, 0.5, False), (40000, 130, 0.1, True), (9000, 40, 1.0, False)])
+def test_gathered_histogram_bit_exact(xgb, oracle, n, F, frac, ordered):
+    """The deeper levels' access pattern: a row subset by row id (ascending like a partitioned node, or shuffled), gradient
+    pairs by position."""
+    X, gpair, d, b = _hist_inputs(xgb, n, F, seed=23)
+    rng = np.random.default_rng(9)
+    m = max(1, int(n * frac))
+    rows = rng.choice(n, size=m, replace=False).astype(np.uint32)
+    if ordered:
+        rows.sort()
+    gp_pos = gpair[:m]
+    hist, scales, ms, kernel = _be().build_histogram_ex(b.handle, d.handle, gp_pos, mode=0, row_ids=rows)
+    assert kernel == "hist_gather_kernel"
+    gq = np.zeros(n, np.int32); hq = np.zeros(n, np.int32)
+    gq[rows] = np.rint(gp_pos[:, 0] * scales[0]).astype(np.int32)
+    hq[rows] = np.rint(gp_pos[:, 1] * scales[1]).astype(np.int32)
+    bins = _be().dmatrix_get_bins(d.handle, 256)
+    np.testing.assert_array_equal(hist, oracle.build_hist_fixed(bins, gq, hq, rows=rows))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_histogram_int32_overflow_spill_path(xgb, oracle, mode):
+    """2.4 M rows x 100 features with a constant column, a 95 %-skewed column and same-sign gradients near the top of the
+    fixed-point grid: every CTA crosses several 8064-row windows and its hot accumulators pass 2^24 in each of them, so the
+    sparse RED.ADD.64 spill between windows carries most of the mass.  Bit-exact against the oracle's int64 mirror."""
+    n, F = 2_400_000, 100
+    rng = np.random.default_rng(77)
+    X = rng.integers(0, 200, size=(n, F)).astype(np.float32)
+    X[:, 0] = 3.0                                              # constant column: one bin takes every row
+    X[:, 1] = np.where(rng.random(n) < 0.95, 7.0, X[:, 1])     # heavily skewed column
+    X[:, 97] = 1.0                                             # constant column in the narrow tail block
+    gpair = np.stack([(0.6 + 0.4 * rng.random(n)).astype(np.float32) * 5, (0.5 + 0.5 * rng.random(n)).astype(np.float32)], axis=1)
+    d = xgb.DMatrix(X, label=np.zeros(n, np.float32))
+    b = xgb.Booster({"max_bin": 256}, [d])
+    hist, scales, ms, kernel = _be().build_histogram_ex(b.handle, d.handle, gpair, mode=mode)
+    gq = np.rint(gpair[:, 0] * scales[0]).astype(np.int32)
+    hq = np.rint(gpair[:, 1] * scales[1]).astype(np.int32)
+    assert gq.min() > (1 << 16) and int(gq.astype(np.int64).sum()) > (1 << 38)       # the window sums really exceed int32 many times over
+    bins = _be().dmatrix_get_bins(d.handle, 256)
+    ref = oracle.build_hist_fixed(bins, gq, hq)
+    np.testing.assert_array_equal(hist[:, :, 0], ref[:, :, 0])
+    if mode != 2:
+        np.testing.assert_array_equal(hist[:, :, 1], ref[:, :, 1])
 
 
 CASES = [
