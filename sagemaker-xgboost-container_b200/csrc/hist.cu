@@ -29,6 +29,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 #include "engine.h"
 #include "tree.h"
 
@@ -40,7 +41,15 @@ constexpr int kMinRowsPerCta = 4096;              // do not pay a flush for fewe
 constexpr int kSpillThreshold = 1 << 24;
 constexpr int kPlaneBytes = kGroupEntries * 4;    // 32 KB
 constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
-constexpr int kRootConsumerWarps = 31;            // + 1 producer warp = 1024 threads
+// root kernel: consumer warps work in teams; a ring stage (tile of kRootRows rows) is consumed by ONE team, warp w of the team
+// taking row block w (16 rows) across all groups, so per-tile synchronisation is amortised over ng units per warp
+constexpr int kTeamWarps = 4, kTeams = 6, kRootRows = 16 * kTeamWarps;
+constexpr int kRootConsumerWarps = kTeamWarps * kTeams;     // + 1 producer warp = 800 threads, <= 80 registers
+
+// compile-time loop: the body receives std::integral_constant<int, K> (template arguments depend on the index)
+template <int K, int N, typename F> __device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (K < N) { f(std::integral_constant<int, K>{}); static_for<K + 1, N>(f); }
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX helpers
@@ -83,8 +92,11 @@ __device__ __forceinline__ unsigned lds_u32(unsigned addr) {
 __device__ __forceinline__ void red_shared_s32(unsigned addr, int v) {
   asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void red_shared_u32_h(unsigned addr, unsigned v) {      // hessian plane = gradient plane + 32 KB
-  asm volatile("red.shared.add.u32 [%0+32768], %1;" :: "r"(addr), "r"(v) : "memory");
+template <int OFF> __device__ __forceinline__ void red_shared_s32_off(unsigned addr, int v) {       // plane offsets ride in the immediate field
+  asm volatile("red.shared.add.s32 [%0+%2], %1;" :: "r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void red_shared_u32_off(unsigned addr, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0+%2], %1;" :: "r"(addr), "r"(v), "n"(OFF) : "memory");
 }
 __device__ __forceinline__ void red_shared_u32(unsigned addr, unsigned v) {
   asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
@@ -134,38 +146,50 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // update slot 16*half + rot(j): the per-row rotation (rot = row) makes the 16 rows of an instruction touch 16 different
 // slots of each half -> every ATOMS instruction hits 32 distinct banks (enumerated in tests/test_hist_lane_mapping.py).
 // ---------------------------------------------------------------------------------------------
-struct LaneConst { unsigned sel[4], offb[4], offw[4]; int qw; };
+// The inner loop is issue-bound, so everything lane-constant is precomputed: A[4*jw+jb] is the complete shared-memory
+// address of the slot that step (jw, jb) updates (bin 0, group 0, G plane) and S[jb] the PRMT selector of its bin byte;
+// a step is PRMT + LEA + one RED per plane, with the group / plane offset in the RED's immediate field.
+struct LaneConst { unsigned A[16]; unsigned S[4]; int qw; };
 
-__device__ __forceinline__ LaneConst make_lane_const(int lane) {
+__device__ __forceinline__ LaneConst make_lane_const(int lane, unsigned smem_base) {
   LaneConst lc;
   const int rot = lane >> 1, half = lane & 1;
   lc.qw = rot >> 2;
   const int qb = rot & 3;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    lc.sel[j] = 0x4440u | (unsigned)((j + qb) & 3);
-    lc.offb[j] = 4u * (unsigned)((j + qb) & 3);
-    lc.offw[j] = 64u * (unsigned)half + 16u * (unsigned)((j + lc.qw) & 3);
-  }
+  for (int jb = 0; jb < 4; ++jb) lc.S[jb] = 0x4440u | (unsigned)((jb + qb) & 3);
+#pragma unroll
+  for (int jw = 0; jw < 4; ++jw)
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb)
+      lc.A[4 * jw + jb] = smem_base + 64u * (unsigned)half + 16u * (unsigned)((jw + lc.qw) & 3) + 4u * (unsigned)((jb + qb) & 3);
+  // opaque to the optimiser: otherwise it rematerialises these 20 values from their formulas inside the issue-bound loop
+#pragma unroll
+  for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(lc.A[i]));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) asm volatile("" : "+r"(lc.S[i]));
   return lc;
 }
 
-// 16 conflict-free atomic (pairs) of one lane's 16 bin bytes into the planes of the group whose G plane starts at `base`
-template <bool GONLY>
-__device__ __forceinline__ void accumulate16(const LaneConst& lc, unsigned base, const uint4& w, int gq, unsigned hq) {
+// word rotation of a 16 B chunk held in registers: ww[jw] = w[(jw + qw) & 3]
+__device__ __forceinline__ void rotate_words(const LaneConst& lc, const uint4& w, unsigned (&ww)[4]) {
   unsigned w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
   if (lc.qw & 1) { unsigned x = w0; w0 = w1; w1 = w2; w2 = w3; w3 = x; }
   if (lc.qw & 2) { unsigned x = w0; w0 = w2; w2 = x; x = w1; w1 = w3; w3 = x; }
-  const unsigned ww[4] = {w0, w1, w2, w3};
+  ww[0] = w0; ww[1] = w1; ww[2] = w2; ww[3] = w3;
+}
+
+// 16 conflict-free atomic (pairs) of one lane's 16 bin bytes (already word-rotated) into the planes at byte offset GOFF
+template <bool GONLY, int GOFF>
+__device__ __forceinline__ void accumulate16(const LaneConst& lc, const unsigned (&ww)[4], int gq, unsigned hq) {
 #pragma unroll
   for (int jw = 0; jw < 4; ++jw) {
-    const unsigned ow = base + lc.offw[jw];
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
-      const unsigned bin = __byte_perm(ww[jw], 0u, lc.sel[jb]);
-      const unsigned addr = (bin << 7) + ow + lc.offb[jb];
-      red_shared_s32(addr, gq);
-      if (!GONLY) red_shared_u32_h(addr, hq);
+      const unsigned bin = __byte_perm(ww[jw], 0u, lc.S[jb]);
+      const unsigned addr = (bin << 7) + lc.A[4 * jw + jb];
+      red_shared_s32_off<GOFF>(addr, gq);
+      if (!GONLY) red_shared_u32_off<GOFF + 32768>(addr, hq);
     }
   }
 }
@@ -181,7 +205,7 @@ __device__ __forceinline__ void tail_accumulate(const TailConst& tc, int lane, u
   for (int j = 0; j < 8; ++j) {
     if (j < tc.tw) {
       const unsigned slot = (unsigned)(j + lane) & (unsigned)(tc.tw - 1);
-      const unsigned bin = __byte_perm(w0, w1, slot);
+      const unsigned bin = __byte_perm(w0, w1, slot) & 0xffu;       // selector nibbles 1..3 are 0 -> mask the replicated byte 0
       const unsigned addr = tc.base_g + bin * tc.bin_stride + tc.rep_off + slot * 4u;
       red_shared_s32(addr, gq);
       if (!GONLY) red_shared_u32(addr + tc.hplane_bytes, hq);
@@ -236,24 +260,36 @@ __device__ __forceinline__ void spill_tail(int* tsm, int tw, int trep, GH64* out
 }
 
 // ---------------------------------------------------------------------------------------------
-// Root pass: contiguous rows, TMA-staged.  One CTA per SM; warp kRootConsumerWarps is the producer.
+// Root pass: contiguous rows, TMA-staged.  One CTA per SM; the last warp is the producer.
 // ---------------------------------------------------------------------------------------------
 struct RootCfg {
-  int R;                   // rows per ring stage (TMA box height)
-  int S;                   // ring stages
+  int S;                   // ring stages (tiles of kRootRows rows)
   int trep;                // tail replicas in shared memory
   int box_groups;          // TMA box width / 32
   unsigned tail_off;       // byte offsets inside dynamic shared memory
   unsigned ring_off;       // (128 B aligned at run time, slack reserved)
   unsigned stage_bytes;
   unsigned total;
+  int flags;               // experiment knobs (B200XGB_ROOT_FLAGS): 1 = main block by 1-D bulk copy when the tile is contiguous,
+                           // 2 = consumers skip the atomics (pure streaming rate of the ring), 4 = no L2 prefetch
 };
+
+// one (16 rows x group G) unit of the tile at shared address `rowaddr` (this lane's row, group 0): four LDS.32 at word
+// offsets rotated per lane (the word rotation of the slot schedule is free in the address), then the 16 steps
+template <bool GONLY, int G>
+__device__ __forceinline__ void root_unit(const LaneConst& lc, const unsigned (&ldsoff)[4], unsigned rowaddr, int gq, unsigned hq) {
+  constexpr int PL = GONLY ? 1 : 2;
+  unsigned ww[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ww[j] = lds_u32(rowaddr + (unsigned)(G * 32) + ldsoff[j]);
+  accumulate16<GONLY, G * PL * kPlaneBytes>(lc, ww, gq, hq);
+}
 
 template <bool GONLY>
 __global__ void __launch_bounds__((kRootConsumerWarps + 1) * 32, 1)
 hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) {
   constexpr int PL = GONLY ? 1 : 2;
-  constexpr int NCW = kRootConsumerWarps;
+  constexpr int NCW = kRootConsumerWarps, R = kRootRows;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nb = *a.build_count;
   if (nb <= 0) return;
@@ -268,19 +304,24 @@ hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) 
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
   const unsigned ring = (smem_base + c.ring_off + 127u) & ~127u;
   const unsigned bars = ring + (unsigned)c.S * c.stage_bytes;                 // full[S] then empty[S]
-  const unsigned main_tile_bytes = (unsigned)c.R * 32u * (unsigned)c.box_groups;
-  const unsigned gp_off = main_tile_bytes, tail_tile_off = main_tile_bytes + (unsigned)c.R * 8u;
-  const unsigned ntiles = (T + c.R - 1) / c.R;
+  const unsigned row_bytes = 32u * (unsigned)c.box_groups;
+  const unsigned main_tile_bytes = (unsigned)R * row_bytes;
+  const unsigned gp_off = main_tile_bytes, tail_tile_off = main_tile_bytes + (unsigned)R * 8u;
+  const unsigned ntiles = (T + R - 1) / R;
+  const unsigned my_ntiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;   // tiles blockIdx.x + i * gridDim.x
 
   // zero the planes, init the barriers
   {
-    const int words4 = (ng_here * PL * kPlaneBytes + (has_tail ? PL * 256 * a.tw * c.trep * 4 : 0)) / 16;
-    int4* z = reinterpret_cast<int4*>(smem_raw);
     const int main4 = ng_here * PL * kPlaneBytes / 16;
+    int4* z = reinterpret_cast<int4*>(smem_raw);
     for (int i = threadIdx.x; i < main4; i += blockDim.x) z[i] = make_int4(0, 0, 0, 0);
-    if (has_tail) { int4* zt = reinterpret_cast<int4*>(smem_raw + c.tail_off); for (int i = threadIdx.x; i < words4 - main4; i += blockDim.x) zt[i] = make_int4(0, 0, 0, 0); }
+    if (has_tail) {
+      const int tail4 = PL * 256 * a.tw * c.trep * 4 / 16;
+      int4* zt = reinterpret_cast<int4*>(smem_raw + c.tail_off);
+      for (int i = threadIdx.x; i < tail4; i += blockDim.x) zt[i] = make_int4(0, 0, 0, 0);
+    }
     if (threadIdx.x == 0) {
-      for (int s = 0; s < c.S; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (c.S + s), NCW); }
+      for (int s = 0; s < c.S; ++s) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (c.S + s), kTeamWarps); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -294,75 +335,81 @@ hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) 
 
   if (warp == NCW) {                                    // ---------------- producer
     if (lane == 0) {
-      const unsigned tx = main_tile_bytes + (unsigned)c.R * 8u + (has_tail ? (unsigned)c.R * (unsigned)a.tw : 0u);
-      unsigned k = 0;
-      for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
-        const unsigned s = k % (unsigned)c.S;
-        if (k >= (unsigned)c.S) mbar_wait(bars + 8u * (c.S + s), ((k / (unsigned)c.S) - 1u) & 1u);
+      const unsigned tx = main_tile_bytes + (unsigned)R * 8u + (has_tail ? (unsigned)R * (unsigned)a.tw : 0u);
+      unsigned s = 0, round = 0;
+      for (unsigned i = 0; i < my_ntiles; ++i) {
+        if (round > 0) mbar_wait(bars + 8u * (c.S + s), (round - 1u) & 1u);
         const unsigned full = bars + 8u * s, dst = ring + s * c.stage_bytes;
-        const unsigned row0 = t * (unsigned)c.R;
+        const unsigned t = blockIdx.x + i * gridDim.x;
+        const unsigned row0 = t * (unsigned)R;
         mbar_expect_tx(full, tx);
-        tma_load_2d(dst, &tm, g0 * 32, (int)row0, full);
-        bulk_load_1d(dst + gp_off, a.gpair + row0, (unsigned)c.R * 8u, full);
-        if (has_tail) bulk_load_1d(dst + tail_tile_off, a.bins_tail + (size_t)row0 * a.tw, (unsigned)c.R * (unsigned)a.tw, full);
-        const unsigned tp = t + 4u * gridDim.x;        // warm L2 four tiles ahead of this CTA
-        if (tp < ntiles) tma_prefetch_2d(&tm, g0 * 32, (int)(tp * (unsigned)c.R));
+        if ((c.flags & 1) && gridDim.y == 1) bulk_load_1d(dst, a.bins + (size_t)row0 * a.row_stride, main_tile_bytes, full);
+        else tma_load_2d(dst, &tm, g0 * 32, (int)row0, full);
+        bulk_load_1d(dst + gp_off, a.gpair + row0, (unsigned)R * 8u, full);
+        if (has_tail) bulk_load_1d(dst + tail_tile_off, a.bins_tail + (size_t)row0 * a.tw, (unsigned)R * (unsigned)a.tw, full);
+        const unsigned tp = t + 8u * gridDim.x;        // warm L2 eight tiles ahead of this CTA
+        if (tp < ntiles && !(c.flags & 4)) tma_prefetch_2d(&tm, g0 * 32, (int)(tp * (unsigned)R));
+        if (++s == (unsigned)c.S) { s = 0; ++round; }
       }
     }
     return;
   }
 
   // ---------------- consumers
+  const int team = warp / kTeamWarps, wit = warp % kTeamWarps;
   const float sg = a.scales[0], sh = a.scales[1];
-  const LaneConst lc = make_lane_const(lane);
+  const LaneConst lc = make_lane_const(lane, smem_base);
+  unsigned ldsoff[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { ldsoff[j] = 16u * (unsigned)(lane & 1) + 4u * (unsigned)((j + lc.qw) & 3); asm volatile("" : "+r"(ldsoff[j])); }
   TailConst tc;
   tc.tw = a.tw; tc.base_g = smem_base + c.tail_off; tc.hplane_bytes = 256u * (unsigned)a.tw * (unsigned)c.trep * 4u;
   tc.bin_stride = (unsigned)a.tw * (unsigned)c.trep * 4u;
   tc.rep_off = has_tail ? (unsigned)((lane / a.tw) % c.trep) * (unsigned)a.tw * 4u : 0u;
-  const int units_main = (c.R >> 4) * ng_here;
-  const int upt = units_main + (has_tail ? (c.R >> 5) : 0);
-  const unsigned row_bytes = 32u * (unsigned)c.box_groups;
-  const int tiles_per_window = kWindowRows / c.R;
+  const unsigned rowl = (unsigned)(wit << 4) + (unsigned)(lane >> 1);          // this lane's row inside a tile
+  const unsigned tiles_per_window = kWindowRows / R;
   long long accG = 0, accH = 0;
-  int base = 0;                                          // (tile counter * upt) mod NCW: rotates the unit -> warp assignment
-  unsigned k = 0;
-  for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
-    const unsigned s = k % (unsigned)c.S;
-    mbar_wait(bars + 8u * s, (k / (unsigned)c.S) & 1u);
-    const unsigned tile = ring + s * c.stage_bytes;
-    const unsigned row0 = t * (unsigned)c.R;
-    int u = warp - base; if (u < 0) u += NCW;
-    for (; u < upt; u += NCW) {
-      if (u < units_main) {
-        const int rb = u / ng_here, g = u - rb * ng_here;
-        const unsigned rowl = (unsigned)(rb << 4) + (unsigned)(lane >> 1);
-        const uint4 w = lds_v4(tile + rowl * row_bytes + (unsigned)g * 32u + (unsigned)(lane & 1) * 16u);
+  unsigned i = (unsigned)team, s = (unsigned)team, ph = 0;                      // c.S >= kTeams (root_plan)
+  for (unsigned wstart = 0;; wstart += tiles_per_window) {
+    const unsigned wend = wstart + tiles_per_window < my_ntiles ? wstart + tiles_per_window : my_ntiles;
+    while (i < wend) {
+      mbar_wait(bars + 8u * s, ph);
+      const unsigned tile = ring + s * c.stage_bytes;
+      const unsigned row0 = (blockIdx.x + i * gridDim.x) * (unsigned)R;
+      if (!(c.flags & 2)) {
         const uint2 ghb = lds_v2(tile + gp_off + rowl * 8u);
         int gq = 0; unsigned hq = 0;
         if (row0 + rowl < T) { gq = __float2int_rn(__uint_as_float(ghb.x) * sg); hq = (unsigned)__float2int_rn(__uint_as_float(ghb.y) * sh); }
-        if (g == 0 && (lane & 1) == 0) { accG += gq; accH += hq; }
-        accumulate16<GONLY>(lc, smem_base + (unsigned)g * (unsigned)(PL * kPlaneBytes), w, gq, hq);
-      } else {
-        const unsigned rowl = (unsigned)((u - units_main) << 5) + (unsigned)lane;
-        unsigned w0, w1 = 0;
-        if (a.tw == 4) w0 = lds_u32(tile + tail_tile_off + rowl * 4u);
-        else { const uint2 ww = lds_v2(tile + tail_tile_off + rowl * 8u); w0 = ww.x; w1 = ww.y; }
-        const uint2 ghb = lds_v2(tile + gp_off + rowl * 8u);
-        int gq = 0; unsigned hq = 0;
-        if (row0 + rowl < T) { gq = __float2int_rn(__uint_as_float(ghb.x) * sg); hq = (unsigned)__float2int_rn(__uint_as_float(ghb.y) * sh); }
-        else { w0 = 0; w1 = 0; }
-        tail_accumulate<GONLY>(tc, lane, w0, w1, gq, hq);
+        if ((lane & 1) == 0) { accG += gq; accH += hq; }
+        const unsigned rowaddr = tile + rowl * row_bytes;
+        root_unit<GONLY, 0>(lc, ldsoff, rowaddr, gq, hq);
+        if (ng_here > 1) root_unit<GONLY, 1>(lc, ldsoff, rowaddr, gq, hq);
+        if (ng_here > 2) root_unit<GONLY, 2>(lc, ldsoff, rowaddr, gq, hq);
+        if (has_tail) {
+          const unsigned tu = ((unsigned)wit + i) & (unsigned)(kTeamWarps - 1);       // rotate the two 32-row tail units over the team
+          if (tu < (unsigned)(R >> 5)) {
+            const unsigned trow = (tu << 5) + (unsigned)lane;
+            unsigned w0, w1 = 0;
+            if (a.tw == 4) w0 = lds_u32(tile + tail_tile_off + trow * 4u);
+            else { const uint2 ww = lds_v2(tile + tail_tile_off + trow * 8u); w0 = ww.x; w1 = ww.y; }
+            const uint2 gt = lds_v2(tile + gp_off + trow * 8u);
+            int gqt = 0; unsigned hqt = 0;
+            if (row0 + trow < T) { gqt = __float2int_rn(__uint_as_float(gt.x) * sg); hqt = (unsigned)__float2int_rn(__uint_as_float(gt.y) * sh); }
+            else { w0 = 0; w1 = 0; }
+            tail_accumulate<GONLY>(tc, lane, w0, w1, gqt, hqt);
+          }
+        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 8u * (c.S + s));
+      i += kTeams; s += kTeams;
+      if (s >= (unsigned)c.S) { s -= (unsigned)c.S; ph ^= 1u; }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bars + 8u * (c.S + s));
-    base += upt % NCW; if (base >= NCW) base -= NCW;
-    if ((k + 1) % (unsigned)tiles_per_window == 0 && t + gridDim.x < ntiles) {       // overflow check
-      named_bar_sync(1, NCW * 32);
-      spill_main<PL>(reinterpret_cast<int*>(smem_raw), ng_here, out_main, false, threadIdx.x, NCW * 32);
-      if (has_tail) spill_tail<PL>(reinterpret_cast<int*>(smem_raw + c.tail_off), a.tw, c.trep, out_tail, false, threadIdx.x, NCW * 32);
-      named_bar_sync(1, NCW * 32);
-    }
+    if (wend == my_ntiles) break;
+    named_bar_sync(1, NCW * 32);                          // overflow check: at most kWindowRows rows since the last one
+    spill_main<PL>(reinterpret_cast<int*>(smem_raw), ng_here, out_main, false, threadIdx.x, NCW * 32);
+    if (has_tail) spill_tail<PL>(reinterpret_cast<int*>(smem_raw + c.tail_off), a.tw, c.trep, out_tail, false, threadIdx.x, NCW * 32);
+    named_bar_sync(1, NCW * 32);
   }
   named_bar_sync(1, NCW * 32);
   spill_main<PL>(reinterpret_cast<int*>(smem_raw), ng_here, out_main, true, threadIdx.x, NCW * 32);
@@ -408,7 +455,7 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_g
   const unsigned smem_g = (unsigned)__cvta_generic_to_shared(smem);
   const int64_t row_stride = (int64_t)a.row_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const LaneConst lc = make_lane_const(lane);
+  const LaneConst lc = make_lane_const(lane, smem_g);
   const int colbyte = (lane & 1) * 16, rowlane = lane >> 1;
   TailConst tc;
   tc.tw = TAIL ? a.tw : 4; tc.base_g = smem_g + (unsigned)(NG * 2 * kPlaneBytes); tc.hplane_bytes = 256u * (unsigned)tc.tw * 4u;
@@ -474,16 +521,17 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_g
       const int gq_l = __float2int_rn(cur.gh.x * sg);
       const unsigned hq_l = (unsigned)__float2int_rn(cur.gh.y * sh);
       accG += gq_l; accH += hq_l;
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int sub = k / NG, g = k - sub * NG;
+      static_for<0, U>([&](auto kc) {
+        constexpr int k = decltype(kc)::value, sub = k / NG, g = k - sub * NG;
         if (active && g < ng_here) {
           const int gq = __shfl_sync(0xffffffffu, gq_l, sub * 16 + rowlane);
           const unsigned hq = __shfl_sync(0xffffffffu, hq_l, sub * 16 + rowlane);
-          accumulate16<false>(lc, smem_g + (unsigned)(g * 2 * kPlaneBytes), w[k], gq, hq);
+          unsigned ww[4];
+          rotate_words(lc, w[k], ww);
+          accumulate16<false, g * 2 * kPlaneBytes>(lc, ww, gq, hq);
         }
         w[k] = load_unit(nxt.id, k);
-      }
+      });
       if (TAIL) {
         if (active && has_tail) tail_accumulate<false>(tc, lane, t0, t1, gq_l, hq_l);
         load_tail(nxt.id, t0, t1);
@@ -518,25 +566,26 @@ const char* hist_last_kernel() { return g_last_kernel; }
 static int chunks_for(int ngroups) { return (ngroups + 2) / 3; }
 static int groups_per_chunk(int ngroups) { const int nc = chunks_for(ngroups); return (ngroups + nc - 1) / nc; }
 
-// Shared-memory plan of hist_root_kernel; returns false when not even a minimal ring fits next to the planes.
+// Shared-memory plan of hist_root_kernel; returns false when the ring next to the planes would be too shallow to keep
+// every team busy (3 groups of G+H planes = 192 KB: that shape uses the gather kernel for its root pass).
 static bool root_plan(int ngc, int tw, bool gonly, RootCfg* c) {
   const int PL = gonly ? 1 : 2;
   const unsigned main_b = (unsigned)ngc * PL * kPlaneBytes;
-  const unsigned avail = kMaxSmem - 128 /* alignment slack */ - 2 * 8 * 8 /* barriers */;
+  const unsigned avail = kMaxSmem - 128 /* alignment slack */ - 2 * 8 * 16 /* barriers */;
+  const unsigned stage = (unsigned)kRootRows * (32u * ngc + 8u + tw);
   int trep = tw ? 32 / tw : 0;
   unsigned tail_b = (unsigned)PL * 256u * tw * trep * 4u;
-  const unsigned min_ring = 3u * 64u * (32u * ngc + 8u + tw);
-  if (tw && main_b + tail_b + min_ring > avail) { trep = 1; tail_b = (unsigned)PL * 256u * tw * 4u; }
-  if (main_b + tail_b + min_ring > avail) return false;
-  const unsigned ring_avail = avail - main_b - tail_b;
-  int R = ngc >= 3 ? 128 : (ngc == 2 ? 192 : 256);
-  unsigned stage = (unsigned)R * (32u * ngc + 8u + tw);
-  int S = (int)(ring_avail / stage);
-  while (S < 4 && R > 64) { R = R > 128 ? 128 : 64; stage = (unsigned)R * (32u * ngc + 8u + tw); S = (int)(ring_avail / stage); }
-  if (S > 8) S = 8;
-  if (S < 2) return false;
-  c->R = R; c->S = S; c->trep = trep; c->box_groups = ngc; c->tail_off = main_b; c->ring_off = main_b + tail_b; c->stage_bytes = stage;
+  if (tw && main_b + tail_b + kTeams * stage > avail) { trep = 1; tail_b = (unsigned)PL * 256u * tw * 4u; }
+  if (main_b + tail_b + kTeams * stage > avail) return false;
+  int S = (int)((avail - main_b - tail_b) / stage);
+  int smax = 16;
+  if (const char* e = getenv("B200XGB_ROOT_S")) smax = atoi(e);
+  if (S > smax) S = smax;
+  if (S < kTeams) return false;
+  c->S = S; c->trep = trep; c->box_groups = ngc; c->tail_off = main_b; c->ring_off = main_b + tail_b; c->stage_bytes = stage;
   c->total = main_b + tail_b + 128 + (unsigned)S * stage + 2 * 8 * (unsigned)S;
+  c->flags = 0;
+  if (const char* f = getenv("B200XGB_ROOT_FLAGS")) c->flags = atoi(f);
   return true;
 }
 
@@ -603,7 +652,7 @@ void launch_hist_build(const HistArgs& a_in, int num_sms, cudaStream_t stream) {
   if (a.ridx == nullptr && !no_tma && !a.force_gather) {
     RootCfg c; CUtensorMap tm;
     const bool gonly = a.g_only != 0;
-    if (root_plan(a.ng_chunk, a.tw, gonly, &c) && get_tensor_map(a.bins, a.n, a.row_stride, c.box_groups, c.R, &tm)) {
+    if (root_plan(a.ng_chunk, a.tw, gonly, &c) && get_tensor_map(a.bins, a.n, a.row_stride, c.box_groups, kRootRows, &tm)) {
       const int gx = num_sms / nchunks > 0 ? num_sms / nchunks : 1;
       if (gonly) hist_root_kernel<true><<<dim3(gx, nchunks), (kRootConsumerWarps + 1) * 32, c.total, stream>>>(tm, a, c);
       else hist_root_kernel<false><<<dim3(gx, nchunks), (kRootConsumerWarps + 1) * 32, c.total, stream>>>(tm, a, c);

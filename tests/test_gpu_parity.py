@@ -65,7 +65,8 @@ def test_root_histogram_bit_exact(xgb, oracle, n, F, mode):
     two group chunks)."""
     X, gpair, d, b = _hist_inputs(xgb, n, F)
     hist, scales, ms, kernel = _be().build_histogram_ex(b.handle, d.handle, gpair, mode=mode)
-    assert kernel == MODE_KERNEL[mode]
+    # 3 groups of G+H planes (192 KB) leave no room for a useful TMA ring: those shapes use the gather kernel for their root pass too
+    assert kernel == MODE_KERNEL[mode] or (mode == 0 and F in (100, 104) and kernel == "hist_gather_kernel")
     gq = np.rint(gpair[:, 0] * scales[0]).astype(np.int32)
     hq = np.rint(gpair[:, 1] * scales[1]).astype(np.int32)
     bins = _be().dmatrix_get_bins(d.handle, 256)
