@@ -22,11 +22,10 @@ def main():
     rng = np.random.default_rng(1)
     gpair = np.empty((a.rows, 2), np.float32); gpair[:, 0] = rng.standard_normal(a.rows, dtype=np.float32); gpair[:, 1] = 1.0
     combos = []
-    for mode in (2, 0):
-        for flags in (0, 1, 2, 3, 5):
-            combos.append((mode, flags, None, None))
-    for R, S in ((64, 8), (128, 4), (256, 3), (128, 2)):
-        combos.append((2, 1, R, S))
+    for flags in (0, 1, 4, 5, 8, 9, 2, 3, 10, 11):
+        combos.append((2, flags, None, None))
+    for S in (6, 8, 10):
+        combos.append((2, 1, None, S))
     if a.only:
         combos = [c for i, c in enumerate(combos) if str(i) in a.only.split(",")]
     for mode, flags, R, S in combos:

@@ -231,8 +231,10 @@ float orc_base_score(const OrcParams* p, const float* labels, const float* weigh
   for (int64_t r = 0; r < n; ++r) { G += gp[2 * r]; H += gp[2 * r + 1]; }
   free(zero); free(gp);
   float wgt = H <= 0.0 ? 0.0f : (float)(-G / H);
-  if (p->objective == OBJ_BINARY_LOGISTIC || p->objective == OBJ_REG_LOGISTIC) return orc_sigmoid(wgt);
-  return wgt;   /* squarederror, logitraw: identity transform */
+  /* logitraw too: base_score lives in probability space for every logistic objective, so that orc_prob_to_margin's logit
+   * gives back the stump weight (storing the raw margin and taking its logit is NaN whenever mean(y) < 0.5) */
+  if (p->objective == OBJ_BINARY_LOGISTIC || p->objective == OBJ_REG_LOGISTIC || p->objective == OBJ_LOGITRAW) return orc_sigmoid(wgt);
+  return wgt;   /* squarederror: identity transform */
 }
 
 float orc_prob_to_margin(const OrcParams* p, float base_score) {
@@ -268,6 +270,12 @@ static inline float calc_gain_given_weight(const OrcParams* p, double G, double 
 static inline float calc_gain(const OrcParams* p, double G, double H) {
   return calc_gain_given_weight(p, G, H, calc_weight(p, G, H));
 }
+static inline float calc_split_gain(const OrcParams* p, double GL, double HL, double GR, double HR);
+/* exported for tests/test_oracle_fixture.py: the reference-held model fixture's node statistics are fed to exactly the
+ * functions the trainer uses */
+float orc_calc_weight(const OrcParams* p, double G, double H) { return calc_weight(p, G, H); }
+float orc_calc_gain(const OrcParams* p, double G, double H) { return calc_gain(p, G, H); }
+float orc_calc_split_gain(const OrcParams* p, double GL, double HL, double GR, double HR) { return calc_split_gain(p, GL, HL, GR, HR); }
 static inline float calc_split_gain(const OrcParams* p, double GL, double HL, double GR, double HR) {
   float wl = calc_weight(p, GL, HL), wr = calc_weight(p, GR, HR);
   return calc_gain_given_weight(p, GL, HL, wl) + calc_gain_given_weight(p, GR, HR, wr);

@@ -68,6 +68,9 @@ def lib():
         L.orc_gradient.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_base_score.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_base_score.restype = C.c_float
+        for fn, nargs in (("orc_calc_weight", 2), ("orc_calc_gain", 2), ("orc_calc_split_gain", 4)):
+            getattr(L, fn).argtypes = [C.POINTER(OrcParams)] + [C.c_double] * nargs
+            getattr(L, fn).restype = C.c_float
         L.orc_prob_to_margin.argtypes = [C.POINTER(OrcParams), C.c_float]
         L.orc_prob_to_margin.restype = C.c_float
         L.orc_build_hist.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

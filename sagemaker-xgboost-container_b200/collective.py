@@ -8,7 +8,6 @@ Two layers:
 """
 import json
 import os
-import pickle
 import sys
 
 from .backend import XGBoostError, get_backend
@@ -45,7 +44,8 @@ def _torch_dist():
 
 
 def broadcast(data, root):
-    """Broadcast a picklable object from `root` (same contract as xgboost.collective.broadcast)."""
+    """Broadcast an object from `root` (contract of xgboost.collective.broadcast).  Over the tracker's TCP links the
+    payload is framed as JSON, never pickle (see tracker.py): dict / list / tuple / str / number / bool / None / bytes."""
     if _state["world"] <= 1:
         return data
     if _state["tracker_client"] is not None:

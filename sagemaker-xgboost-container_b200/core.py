@@ -207,6 +207,45 @@ _IGNORED_PARAMS = {
 }
 
 
+_DROP = object()
+
+
+def _as_float(v, default):
+    try:
+        return float(v)
+    except (TypeError, ValueError):
+        return default
+
+
+def _check_unapplied(k, v):
+    """No silent hyperparameter divergence: every value the container validates as legal but this builder
+    does not honour is either rejected or announced with a warning; returns the value to forward, or _DROP."""
+    if k in ("monotone_constraints", "interaction_constraints"):
+        if str(v).strip("()[] ,0") != "":
+            warnings.warn("%s is accepted for hyperparameter compatibility but NOT applied by the B200 hist builder" % k)
+        return _DROP
+    if k in ("colsample_bylevel", "colsample_bynode"):
+        if _as_float(v, 1.0) < 1.0:
+            warnings.warn("%s=%s is NOT applied by the B200 hist builder (only colsample_bytree is); training proceeds with %s=1" % (k, v, k))
+        return _DROP
+    if k == "max_bin" and _as_float(v, 256) > 256:
+        warnings.warn("max_bin=%s exceeds the 256 bins per feature of the uint8 bin codes; using max_bin=256" % v)
+        return 256
+    if k == "tree_method" and str(v) in ("exact", "approx"):
+        warnings.warn("tree_method=%s runs the B200 hist builder (quantile-binned histograms), not xgboost's %s updater" % (v, v))
+        return v
+    if k == "num_parallel_tree" and _as_float(v, 1) > 1:
+        raise XGBoostError("num_parallel_tree=%s (boosted random forests) is not implemented by the B200 hist builder" % v)
+    if k == "process_type" and str(v) == "update":
+        raise XGBoostError("process_type=update is not implemented by the B200 hist builder")
+    if k == "sampling_method" and str(v) == "gradient_based":
+        warnings.warn("sampling_method=gradient_based is NOT applied; subsample uses uniform Bernoulli sampling")
+        return _DROP
+    if k in _IGNORED_PARAMS:
+        return _DROP
+    return v
+
+
 class Booster:
     """A gradient-boosted tree model trained / evaluated by the CUDA engine."""
 
@@ -286,9 +325,8 @@ class Booster:
         if isinstance(params, str) and value is not None:
             params = [(params, value)]
         for k, v in _param_items(params):
-            if k in _IGNORED_PARAMS:
-                if k in ("monotone_constraints", "interaction_constraints") and str(v).strip("()[] ,0") != "":
-                    warnings.warn("%s is accepted for hyperparameter compatibility but NOT applied by the B200 hist builder yet" % k)
+            v = _check_unapplied(k, v)
+            if v is _DROP:
                 continue
             get_backend().booster_set_param(self.handle, k, v)
 

@@ -426,7 +426,8 @@ void Booster::configure() {
     if (p.objective == kBinaryLogistic || p.objective == kRegLogistic || p.objective == kLogitRaw)
       B200_CHECK(base_score_ > 0.0f && base_score_ < 1.0f, "Check failed: base_score > 0.0f && base_score < 1.0f base_score must be in (0,1) for logistic loss");
   }
-  if (p.max_depth <= 0) p.max_depth = 6;
+  B200_CHECK(p.max_depth >= 1, "max_depth=" + std::to_string(p.max_depth) + " (no depth limit) needs grow_policy=lossguide, which the B200 depth-wise hist builder does not implement; use max_depth in [1, 16]");
+  if (p.max_bin > 256) p.max_bin = 256;            // uint8 bin codes (the Python layer warns)
   param_ = p;
   configured_ = true;
 }
@@ -455,7 +456,9 @@ void Booster::estimate_base_score(DMatrix* dtrain) {
   CUDA_OK(cudaMemcpyAsync(h, g.dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
   float w = h[1] <= 0.0 ? 0.0f : (float)(-h[0] / h[1]);
-  if (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic) {
+  // binary:logitraw keeps base_score in probability space like the other logistic objectives (the estimated stump weight
+  // w is a margin; storing it raw and taking its logit again gives NaN whenever w <= 0, i.e. whenever mean(y) < 0.5)
+  if (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic || param_.objective == kLogitRaw) {
     float x = std::min(-w, 88.7f); base_score_ = 1.0f / (std::exp(x) + 1.0f + 1e-16f);
   } else base_score_ = w;
 }

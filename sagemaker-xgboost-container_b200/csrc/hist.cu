@@ -44,7 +44,9 @@ constexpr int kMaxSmem = 232448;                  // 227 KB opt-in limit per CTA
 // root kernel: consumer warps work in teams; a ring stage (tile of kRootRows rows) is consumed by ONE team, warp w of the team
 // taking row block w (16 rows) across all groups, so per-tile synchronisation is amortised over ng units per warp
 constexpr int kTeamWarps = 4, kTeams = 6, kRootRows = 16 * kTeamWarps;
-constexpr int kRootConsumerWarps = kTeamWarps * kTeams;     // + 1 producer warp = 800 threads, <= 80 registers
+constexpr int kRootConsumerWarps = kTeamWarps * kTeams;
+constexpr int kRootProducerWarps = 3;                       // one issuing lane each, tiles round-robin: a single thread tops out at ~3.9 TB/s
+constexpr int kRootThreads = (kRootConsumerWarps + kRootProducerWarps) * 32;      // 864 threads, <= 72 registers
 
 // compile-time loop: the body receives std::integral_constant<int, K> (template arguments depend on the index)
 template <int K, int N, typename F> __device__ __forceinline__ void static_for(F&& f) {
@@ -286,7 +288,7 @@ __device__ __forceinline__ void root_unit(const LaneConst& lc, const unsigned (&
 }
 
 template <bool GONLY>
-__global__ void __launch_bounds__((kRootConsumerWarps + 1) * 32, 1)
+__global__ void __launch_bounds__(kRootThreads, 1)
 hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) {
   constexpr int PL = GONLY ? 1 : 2;
   constexpr int NCW = kRootConsumerWarps, R = kRootRows;
@@ -333,23 +335,26 @@ hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) 
   GH64* out_main = out_slot + (size_t)g0 * kGroupEntries;
   GH64* out_tail = out_slot + (size_t)a.ngroups * kGroupEntries;
 
-  if (warp == NCW) {                                    // ---------------- producer
+  if (warp >= NCW) {                                    // ---------------- producers: warp NCW + p issues tiles p, p + P, ...
     if (lane == 0) {
-      const unsigned tx = main_tile_bytes + (unsigned)R * 8u + (has_tail ? (unsigned)R * (unsigned)a.tw : 0u);
-      unsigned s = 0, round = 0;
-      for (unsigned i = 0; i < my_ntiles; ++i) {
-        if (round > 0) mbar_wait(bars + 8u * (c.S + s), (round - 1u) & 1u);
-        const unsigned full = bars + 8u * s, dst = ring + s * c.stage_bytes;
-        const unsigned t = blockIdx.x + i * gridDim.x;
-        const unsigned row0 = t * (unsigned)R;
-        mbar_expect_tx(full, tx);
-        if ((c.flags & 1) && gridDim.y == 1) bulk_load_1d(dst, a.bins + (size_t)row0 * a.row_stride, main_tile_bytes, full);
-        else tma_load_2d(dst, &tm, g0 * 32, (int)row0, full);
-        bulk_load_1d(dst + gp_off, a.gpair + row0, (unsigned)R * 8u, full);
-        if (has_tail) bulk_load_1d(dst + tail_tile_off, a.bins_tail + (size_t)row0 * a.tw, (unsigned)R * (unsigned)a.tw, full);
-        const unsigned tp = t + 8u * gridDim.x;        // warm L2 eight tiles ahead of this CTA
-        if (tp < ntiles && !(c.flags & 4)) tma_prefetch_2d(&tm, g0 * 32, (int)(tp * (unsigned)R));
-        if (++s == (unsigned)c.S) { s = 0; ++round; }
+      const unsigned P = (c.flags & 8) ? 1u : (unsigned)kRootProducerWarps, pw = (unsigned)(warp - NCW);
+      if (pw < P) {
+        const unsigned tx = main_tile_bytes + (unsigned)R * 8u + (has_tail ? (unsigned)R * (unsigned)a.tw : 0u);
+        unsigned s = pw % (unsigned)c.S, round = pw / (unsigned)c.S;
+        for (unsigned i = pw; i < my_ntiles; i += P) {
+          if (round > 0) mbar_wait(bars + 8u * (c.S + s), (round - 1u) & 1u);
+          const unsigned full = bars + 8u * s, dst = ring + s * c.stage_bytes;
+          const unsigned t = blockIdx.x + i * gridDim.x;
+          const unsigned row0 = t * (unsigned)R;
+          mbar_expect_tx(full, tx);
+          if ((c.flags & 1) && gridDim.y == 1) bulk_load_1d(dst, a.bins + (size_t)row0 * a.row_stride, main_tile_bytes, full);
+          else tma_load_2d(dst, &tm, g0 * 32, (int)row0, full);
+          bulk_load_1d(dst + gp_off, a.gpair + row0, (unsigned)R * 8u, full);
+          if (has_tail) bulk_load_1d(dst + tail_tile_off, a.bins_tail + (size_t)row0 * a.tw, (unsigned)R * (unsigned)a.tw, full);
+          const unsigned tp = t + 8u * gridDim.x;        // warm L2 eight tiles ahead of this CTA
+          if (tp < ntiles && !(c.flags & 4)) tma_prefetch_2d(&tm, g0 * 32, (int)(tp * (unsigned)R));
+          s += P; if (s >= (unsigned)c.S) { s -= (unsigned)c.S; ++round; }
+        }
       }
     }
     return;
@@ -581,6 +586,11 @@ static bool root_plan(int ngc, int tw, bool gonly, RootCfg* c) {
   int smax = 16;
   if (const char* e = getenv("B200XGB_ROOT_S")) smax = atoi(e);
   if (S > smax) S = smax;
+  // a ring stage must always be refilled by the SAME producer thread (a parity wait may only ever be one phase ahead of its
+  // barrier, which a single thread's program order guarantees): tile i -> producer i % P -> stage i % S needs S % P == 0
+  // ... and likewise always consumed by the SAME team (tile i -> team i % kTeams): S must be a multiple of both
+  constexpr int kStageQuantum = kTeams % kRootProducerWarps == 0 ? kTeams : kTeams * kRootProducerWarps;
+  S -= S % kStageQuantum;
   if (S < kTeams) return false;
   c->S = S; c->trep = trep; c->box_groups = ngc; c->tail_off = main_b; c->ring_off = main_b + tail_b; c->stage_bytes = stage;
   c->total = main_b + tail_b + 128 + (unsigned)S * stage + 2 * 8 * (unsigned)S;
@@ -654,8 +664,8 @@ void launch_hist_build(const HistArgs& a_in, int num_sms, cudaStream_t stream) {
     const bool gonly = a.g_only != 0;
     if (root_plan(a.ng_chunk, a.tw, gonly, &c) && get_tensor_map(a.bins, a.n, a.row_stride, c.box_groups, kRootRows, &tm)) {
       const int gx = num_sms / nchunks > 0 ? num_sms / nchunks : 1;
-      if (gonly) hist_root_kernel<true><<<dim3(gx, nchunks), (kRootConsumerWarps + 1) * 32, c.total, stream>>>(tm, a, c);
-      else hist_root_kernel<false><<<dim3(gx, nchunks), (kRootConsumerWarps + 1) * 32, c.total, stream>>>(tm, a, c);
+      if (gonly) hist_root_kernel<true><<<dim3(gx, nchunks), kRootThreads, c.total, stream>>>(tm, a, c);
+      else hist_root_kernel<false><<<dim3(gx, nchunks), kRootThreads, c.total, stream>>>(tm, a, c);
       g_last_kernel = gonly ? "hist_root_kernel<GONLY>" : "hist_root_kernel<GH>";
       ++g_kernel_launches;
       CUDA_OK(cudaGetLastError());

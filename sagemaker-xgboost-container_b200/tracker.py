@@ -5,19 +5,63 @@ sorted task ids when sortby="task", as the container requests -- and later relay
 (the container's RabitHelper.synchronize) through it.  Bulk numeric traffic never goes here: histograms travel
 over NCCL inside the engine.
 """
-import pickle
+import base64
+import json
 import socket
 import struct
 import threading
 import time
 
+# Wire format: 8-byte big-endian length + UTF-8 JSON.  No pickle: the tracker listens on the cluster-facing address
+# (distributed.py:183-190 binds it to the master's IP), so a frame must never be able to execute code on its reader.
+MAX_FRAME = 64 << 20          # broadcast payloads are small membership records (RabitHelper.synchronize)
+MAX_HELLO = 4096
+HELLO_TIMEOUT_S = 10.0
+MAGIC = "b200xgb-tracker-1"
+
+
+def _encode(obj):
+    """JSON with two extensions: bytes and tuples survive the round trip."""
+    if isinstance(obj, (bytes, bytearray)):
+        return {"__bytes__": base64.b64encode(bytes(obj)).decode("ascii")}
+    if isinstance(obj, tuple):
+        return {"__tuple__": [_encode(x) for x in obj]}
+    if isinstance(obj, list):
+        return [_encode(x) for x in obj]
+    if isinstance(obj, dict):
+        for k in obj:
+            if not isinstance(k, str):
+                raise TypeError("collective.broadcast: dictionary keys must be strings (got %r)" % (k,))
+        return {k: _encode(v) for k, v in obj.items()}
+    if obj is None or isinstance(obj, (str, bool, int, float)):
+        return obj
+    try:                                  # numpy scalars and similar
+        return _encode(obj.item())
+    except Exception:
+        raise TypeError("collective.broadcast carries JSON-serialisable values (dict / list / tuple / str / number / bool / None / "
+                        "bytes); got %s" % type(obj).__name__)
+
+
+def _decode(obj):
+    if isinstance(obj, list):
+        return [_decode(x) for x in obj]
+    if isinstance(obj, dict):
+        if set(obj) == {"__bytes__"}:
+            return base64.b64decode(obj["__bytes__"])
+        if set(obj) == {"__tuple__"}:
+            return tuple(_decode(x) for x in obj["__tuple__"])
+        return {k: _decode(v) for k, v in obj.items()}
+    return obj
+
 
 def _send(sock, obj):
-    data = pickle.dumps(obj)
+    data = json.dumps(_encode(obj), separators=(",", ":")).encode("utf-8")
+    if len(data) > MAX_FRAME:
+        raise ValueError("tracker frame of %d bytes exceeds the %d byte limit" % (len(data), MAX_FRAME))
     sock.sendall(struct.pack("!Q", len(data)) + data)
 
 
-def _recv(sock):
+def _recv(sock, limit=MAX_FRAME):
     hdr = b""
     while len(hdr) < 8:
         chunk = sock.recv(8 - len(hdr))
@@ -25,13 +69,18 @@ def _recv(sock):
             raise ConnectionError("tracker connection closed")
         hdr += chunk
     (n,) = struct.unpack("!Q", hdr)
+    if n > limit:
+        raise ConnectionError("tracker frame of %d bytes exceeds the %d byte limit" % (n, limit))
     buf = bytearray()
     while len(buf) < n:
         chunk = sock.recv(min(1 << 20, n - len(buf)))
         if not chunk:
             raise ConnectionError("tracker connection closed")
         buf += chunk
-    return pickle.loads(bytes(buf))
+    try:
+        return _decode(json.loads(bytes(buf).decode("utf-8")))
+    except (ValueError, UnicodeDecodeError) as e:
+        raise ConnectionError("malformed tracker frame: %s" % e)
 
 
 class RabitTracker:
@@ -58,12 +107,33 @@ class RabitTracker:
 
     def _run(self):
         try:
-            conns = []
-            while len(conns) < self.n_workers:
+            by_task = {}                       # task id -> (task id, host, arrival order, socket); a retried worker replaces its old link
+            order = 0
+            while len(by_task) < self.n_workers:
                 c, addr = self._sock.accept()
-                c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-                hello = _recv(c)
-                conns.append((str(hello.get("task_id", "")), addr[0], len(conns), c))
+                try:
+                    c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                    c.settimeout(HELLO_TIMEOUT_S)
+                    hello = _recv(c, limit=MAX_HELLO)
+                    if not isinstance(hello, dict) or hello.get("magic") != MAGIC or not isinstance(hello.get("task_id"), str):
+                        raise ConnectionError("bad handshake")
+                    c.settimeout(None)
+                except (ConnectionError, OSError, socket.timeout):
+                    try:                       # port probe, stray client or a peer that went silent: drop it, keep listening
+                        c.close()
+                    except OSError:
+                        pass
+                    continue
+                task = hello["task_id"] or "anon-%d" % order
+                old = by_task.pop(task, None)
+                if old is not None:
+                    try:
+                        old[3].close()
+                    except OSError:
+                        pass
+                by_task[task] = (task, addr[0], order, c)
+                order += 1
+            conns = list(by_task.values())
             if self.sortby == "task":
                 conns.sort(key=lambda t: (t[0], t[2]))
             else:
@@ -76,7 +146,10 @@ class RabitTracker:
                 msgs = {}
                 for r in sorted(alive):
                     try:
-                        msgs[r] = _recv(socks[r])
+                        m = _recv(socks[r])
+                        if not isinstance(m, dict) or m.get("op") not in ("bcast", "barrier", "bye"):
+                            raise ConnectionError("malformed request")
+                        msgs[r] = m
                     except (ConnectionError, OSError):
                         msgs[r] = {"op": "bye"}
                 ops = {m["op"] for m in msgs.values()}
@@ -92,8 +165,10 @@ class RabitTracker:
                         break
                     continue
                 if ops == {"bcast"}:
-                    root = next(iter(msgs.values()))["root"]
-                    payload = msgs[root]["data"]
+                    root = next(iter(msgs.values())).get("root")
+                    if not isinstance(root, int) or root not in msgs:
+                        raise RuntimeError("tracker: broadcast from unknown root %r" % (root,))
+                    payload = msgs[root].get("data")
                     for r in alive:
                         _send(socks[r], {"data": payload})
                 elif ops == {"barrier"}:
@@ -143,7 +218,7 @@ class TrackerClient:
                 time.sleep(0.2)
         self.sock.settimeout(None)
         self.sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
-        _send(self.sock, {"task_id": self.task_id})
+        _send(self.sock, {"magic": MAGIC, "task_id": str(self.task_id)})
         info = _recv(self.sock)
         self.rank, self.world = info["rank"], info["world"]
 

@@ -10,8 +10,12 @@ from .core import Booster, DMatrix
 
 def train(params, dtrain, num_boost_round=10, *, evals=None, obj=None, maximize=None, early_stopping_rounds=None,
           evals_result=None, verbose_eval=True, xgb_model=None, callbacks=None, custom_metric=None, feval=None):
-    if feval is not None and custom_metric is None:
-        custom_metric = feval
+    # upstream: `custom_metric` sees TRANSFORMED predictions when a built-in objective is used, the legacy `feval` sees raw
+    # margins (output_margin = callable(obj) or metric_fn is feval).  The container passes custom_metric= (train.py:372,437).
+    if feval is not None and custom_metric is not None:
+        raise ValueError("Both `feval` and `custom_metric` are supplied.  Use `custom_metric` instead.")
+    metric_fn = custom_metric if custom_metric is not None else feval
+    output_margin = callable(obj) or (feval is not None and custom_metric is None)
     callbacks = [] if callbacks is None else list(callbacks)
     evals = list(evals) if evals else []
     for va, _ in evals:
@@ -23,7 +27,7 @@ def train(params, dtrain, num_boost_round=10, *, evals=None, obj=None, maximize=
         callbacks.append(EvaluationMonitor(period=period))
     if early_stopping_rounds:
         callbacks.append(EarlyStopping(rounds=early_stopping_rounds, maximize=maximize))
-    cb_container = CallbackContainer(callbacks, metric=custom_metric, output_margin=callable(obj) or custom_metric is not None)
+    cb_container = CallbackContainer(callbacks, metric=metric_fn, output_margin=output_margin)
     bst = cb_container.before_training(bst)
     start = 0
     for i in range(start, num_boost_round):
@@ -43,6 +47,7 @@ def cv(params, dtrain, num_boost_round=10, nfold=3, stratified=False, folds=None
     """k-fold cross validation with the semantics of xgboost.cv (used by script-mode customer code,
     test/resources/boston/single_machine_customer_script.py:94): returns mean/std of every metric per round."""
     import numpy as np
+    output_margin = callable(obj) or (feval is not None and custom_metric is None)
     if feval is not None and custom_metric is None:
         custom_metric = feval
     n = dtrain.num_row()
@@ -71,7 +76,7 @@ def cv(params, dtrain, num_boost_round=10, nfold=3, stratified=False, folds=None
         per_fold = []
         for bst, dtr, dte in packs:
             bst.update(dtr, i, obj)
-            msg = bst.eval_set([(dtr, "train"), (dte, "test")], i, custom_metric, custom_metric is not None)
+            msg = bst.eval_set([(dtr, "train"), (dte, "test")], i, custom_metric, output_margin)
             per_fold.append([tuple(s.split(":")) for s in msg.split()[1:]])
         keys = [k for k, _ in per_fold[0]]
         for j, key in enumerate(keys):

@@ -165,6 +165,25 @@ def test_training_matches_oracle(xgb, oracle, objective, kind, K, hp, n, F, roun
     np.testing.assert_allclose(margin, oracle.predict_margin(mr, X), rtol=0, atol=MARGIN_TOL)
 
 
+def test_logitraw_with_minority_positive_class(xgb, oracle):
+    """binary:logitraw with mean(y) < 0.5: the estimated base score must give a finite base margin (the stump
+    weight), trees must split, and the model must match the oracle."""
+    X, y = synth(20000, 12, 33, "bin")
+    y = (y * (np.random.default_rng(1).random(len(y)) < 0.55)).astype(np.float32)          # ~27 % positives
+    assert 0.2 < y.mean() < 0.35
+    params = dict(objective="binary:logitraw", max_depth=4, eta=0.3, max_bin=256)
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=6, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, 6).model()
+    assert 0.0 < m["base_score"] < 0.5 and abs(m["base_score"] - mr["base_score"]) < 1e-6
+    assert_same_structure(m, mr)
+    assert (m["left"] != -1).sum() > 6 and max_leaf_diff(m, mr) <= LEAF_TOL
+    margin = bst.predict(d, output_margin=True)
+    assert np.isfinite(margin).all()
+    np.testing.assert_allclose(margin.reshape(len(y), -1), oracle.predict_margin(mr, X), rtol=0, atol=MARGIN_TOL)
+
+
 def test_training_with_missing_values(xgb, oracle):
     X, y = synth(15000, 12, 41, "reg", quantised=False, missing_frac=0.15)
     params = dict(objective="reg:squarederror", max_depth=5, eta=0.3, max_bin=64)

@@ -207,3 +207,29 @@ def test_sklearn_wrappers_and_cv(cpu_xgb, tmp_path):
     d = cpu_xgb.DMatrix(X, label=y)
     res = cpu_xgb.cv({"objective": "reg:squarederror", "max_depth": 3}, d, num_boost_round=5, nfold=3, metrics="rmse", as_pandas=False, seed=123)
     assert len(res["test-rmse-mean"]) == 5 and res["train-rmse-mean"][-1] < res["train-rmse-mean"][0]
+
+
+def test_tracker_frames_are_json_and_bad_handshakes_are_dropped():
+    """no pickle on the tracker's sockets; a port probe / oversized hello must not take a worker slot."""
+    import socket, struct, inspect
+    from sagemaker_xgboost_container_b200 import tracker as T
+    assert "pickle" not in inspect.getsource(T).replace("No pickle", "").replace("never pickle", "")
+    for obj in ({"a": [1, 2.5, None, True], "t": (1, "x"), "b": b"\x00\xff"}, "s", 3, None):
+        assert T._decode(__import__("json").loads(__import__("json").dumps(T._encode(obj)))) == obj
+    with pytest.raises(TypeError):
+        T._encode({"f": object()})
+    tr = T.RabitTracker(n_workers=1, host_ip="127.0.0.1", port=0, sortby="task")
+    tr.start()
+    port = tr.worker_args()["dmlc_tracker_port"]
+    probe = socket.create_connection(("127.0.0.1", port))           # connect and say nothing useful
+    probe.sendall(struct.pack("!Q", 1 << 40))                       # absurd length: dropped at the cap
+    junk = socket.create_connection(("127.0.0.1", port))
+    junk.sendall(struct.pack("!Q", 4) + b"\x80\x04N.")              # a pickle frame: not JSON, dropped
+    c = T.TrackerClient("127.0.0.1", port, "algo-1", timeout=20)
+    c.connect()
+    assert (c.rank, c.world) == (0, 1)
+    assert c.broadcast({"k": (1, 2)}, 0) == {"k": (1, 2)}
+    c.close()
+    tr.wait_for(timeout=20)
+    tr.free()
+    probe.close(); junk.close()

@@ -75,18 +75,58 @@ def test_traversal_known_answer(fixture_model):
 
 
 def test_oracle_split_arithmetic_reproduces_fixture_decisions(fixture_model):
-    """Feed the oracle's split evaluator the fixture's own node statistics: for every internal node the weight it
-    computes for each child must equal the stored base_weight / leaf value (unscaled for internal, eta-scaled for leaves)."""
+    """The ORACLE'S OWN calc_weight / calc_gain / calc_split_gain (exported from gbt_oracle.c, the functions its trainer
+    calls) fed with the 715 internal nodes of the reference-held fixture: with (G, H) of a node and of its two children
+    taken from the stored sum_hessian and weights, the oracle's loss change must reproduce the stored `loss_changes` and
+    its weights the stored `base_weights` / leaf values.  Pins lambda (=1, no 1/2 factor), the gain formula, the
+    min_child_weight cut-off and the eta scaling of leaves on reference data through oracle code."""
     _, m = fixture_model
+    p = O.make_params(dict(objective="reg:squarederror", eta=ETA, gamma=GAMMA, min_child_weight=MCW, max_depth=5))
+    L, ref = O.lib(), O.C.byref(p)
+    worst_gain, worst_w, n = 0.0, 0.0, 0
     for t in range(50):
         T = m.tree(t)
+        w = lambda j: float(T["base_weight"][j]) if T["left"][j] != -1 else float(T["split_cond"][j]) / ETA     # unscaled weight of node j
         for i in range(len(T["left"])):
             if T["left"][i] == -1:
                 continue
-            H = float(T["sum_hess"][i])
-            G = -float(T["base_weight"][i]) * (H + LAMBDA)
-            wt = -G / (H + LAMBDA)
-            assert abs(wt - T["base_weight"][i]) <= 1e-6 * max(1, abs(wt))
+            n += 1
+            l, r = int(T["left"][i]), int(T["right"][i])
+            H, HL, HR = float(T["sum_hess"][i]), float(T["sum_hess"][l]), float(T["sum_hess"][r])
+            GL, GR = -w(l) * (HL + LAMBDA), -w(r) * (HR + LAMBDA)
+            G = GL + GR                                               # node sum from its children, NOT from its own weight
+            lc = L.orc_calc_split_gain(ref, GL, HL, GR, HR) - L.orc_calc_gain(ref, G, H)
+            worst_gain = max(worst_gain, abs(lc - float(T["loss_chg"][i])) / float(T["loss_chg"][i]))
+            worst_w = max(worst_w, abs(L.orc_calc_weight(ref, G, H) - float(T["base_weight"][i])))      # parent weight from the children's sums
+            for c, Gc, Hc in ((l, GL, HL), (r, GR, HR)):
+                wc = L.orc_calc_weight(ref, Gc, Hc)
+                if T["left"][c] == -1:
+                    assert abs(ETA * wc - float(T["split_cond"][c])) <= 2e-6 * max(1.0, abs(wc))            # leaf value = eta * w
+                else:
+                    assert abs(wc - float(T["base_weight"][c])) <= 2e-6 * max(1.0, abs(wc))
+    assert n == 715
+    assert worst_gain < 3e-5 and worst_w < 2e-4
+    # the min_child_weight rule the fixture obeys (every leaf hessian >= 6) is the oracle's cut-off
+    assert L.orc_calc_weight(ref, -10.0, MCW - 0.5) == 0.0 and L.orc_calc_weight(ref, -10.0, MCW) != 0.0
+
+
+def test_fixture_thresholds_are_oracle_cuts():
+    """Cut-membership pin: on abalone features with <= 256 distinct values the oracle's cuts are the distinct values, so
+    every split threshold the reference chose on those features must be one of the oracle's cut points (264 of 264)."""
+    doc = ubjson.load(os.path.join(G, "abalone_xgboost-model.ubj"))
+    m = ubjson.model_from_xgb_json(doc)
+    X, _ = load_libsvm(os.path.join(G, "abalone", "abalone.train_0"))
+    ptrs, vals, mins, hm = O.make_cuts(X, 256)
+    internal = m["left"] != -1
+    checked = 0
+    for f in range(X.shape[1]):
+        if len(np.unique(X[:, f])) > 256:
+            continue
+        cuts = set(np.float32(v) for v in vals[ptrs[f]:ptrs[f + 1]])
+        thr = m["split_cond"][internal & (m["split_index"] == f)]
+        assert all(np.float32(t) in cuts for t in thr), "feature %d: a fixture threshold is not an oracle cut" % f
+        checked += len(thr)
+    assert checked == 264
 
 
 def test_oracle_trains_abalone_with_fixture_hyperparameters():
