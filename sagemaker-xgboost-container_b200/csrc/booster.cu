@@ -283,7 +283,7 @@ struct GrowerImpl {
   DevBuf<unsigned char> tree_block;        // header + TreeArrays, copied to the host in one piece
   size_t tree_block_bytes = 0;
   DevBuf<GH64> hist_pool; DevBuf<unsigned> ridx0, ridx1, scratch;
-  DevBuf<float2> gpair, gp0, gp1; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
+  DevBuf<float2> gpair, gp0, gp1; DevBuf<unsigned> tl0, tl1; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
   DevBuf<DevNode> packed; std::vector<TreeGraph> graphs; std::vector<char> eager_done;
@@ -306,6 +306,7 @@ struct GrowerImpl {
     ridx0.alloc(n); ridx1.alloc(n);
     gpair.alloc((size_t)gp_stride * K + 512); gpair.zero(engine_stream()); gp0.alloc(n); gp1.alloc(n); err.alloc(1); dsum.alloc(4);
     root_h_cache.alloc(slot_stride);
+    tl0.alloc(tw == 4 ? n : 0); tl1.alloc(tw == 4 ? n : 0);
     const unsigned max_tiles = (unsigned)((n + kPartTile - 1) / kPartTile) + max_level_nodes + 1;
     scratch.alloc(3 * (size_t)max_level_nodes + 8);
     // ---- GrowState block
@@ -650,11 +651,14 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
     pa.ridx_next = (L & 1) ? g.ridx1.p : g.ridx0.p;
     pa.gp_cur = L == 0 ? g.gpair.p + (size_t)k * g.gp_stride : ((L & 1) ? g.gp0.p : g.gp1.p);
     pa.gp_next = (L & 1) ? g.gp1.p : g.gp0.p;
+    const bool carry_tail = bm.tw == 4;                     // the 4 tail bytes of a row ride along with its id instead of being gathered
+    pa.tl_cur = !carry_tail ? nullptr : (L == 0 ? reinterpret_cast<const unsigned*>(bm.bins_tail) : ((L & 1) ? g.tl0.p : g.tl1.p));
+    pa.tl_next = !carry_tail ? nullptr : ((L & 1) ? g.tl1.p : g.tl0.p);
     pa.has_missing = bm.has_missing; pa.level = L; pa.max_level_nodes = g.max_level_nodes;
     launch_partition(pa, max_tiles, 1 << L, s);
     // histograms of the next level: build the smaller children, all-reduce, subtract for the siblings
     CUDA_OK(cudaMemsetAsync(g.hist_pool.p + (size_t)next_base * g.slot_stride, 0, (size_t)next_half * g.slot_stride * sizeof(GH64), s));
-    ha.ridx = pa.ridx_next; ha.gpair = pa.gp_next; ha.accumulate_sum = 0;
+    ha.ridx = pa.ridx_next; ha.gpair = pa.gp_next; ha.tail_pos = pa.tl_next; ha.accumulate_sum = 0;
     ha.rows_counter = profile_ ? prof_rows_.p + 1 : nullptr;
     prof_begin(L + 1);
     launch_hist_build(ha, num_sms, s);

@@ -153,9 +153,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // a step is PRMT + LEA + one RED per plane, with the group / plane offset in the RED's immediate field.
 struct LaneConst { unsigned A[16]; unsigned S[4]; int qw; };
 
-__device__ __forceinline__ LaneConst make_lane_const(int lane, unsigned smem_base) {
+__device__ __forceinline__ LaneConst make_lane_const_rot(int rot, int half, unsigned smem_base) {
   LaneConst lc;
-  const int rot = lane >> 1, half = lane & 1;
   lc.qw = rot >> 2;
   const int qb = rot & 3;
 #pragma unroll
@@ -172,6 +171,8 @@ __device__ __forceinline__ LaneConst make_lane_const(int lane, unsigned smem_bas
   for (int i = 0; i < 4; ++i) asm volatile("" : "+r"(lc.S[i]));
   return lc;
 }
+// (16 rows x one group) unit: two lanes per row, rotation = row
+__device__ __forceinline__ LaneConst make_lane_const(int lane, unsigned smem_base) { return make_lane_const_rot(lane >> 1, lane & 1, smem_base); }
 
 // word rotation of a 16 B chunk held in registers: ww[jw] = w[(jw + qw) & 3]
 __device__ __forceinline__ void rotate_words(const LaneConst& lc, const uint4& w, unsigned (&ww)[4]) {
@@ -429,13 +430,23 @@ hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) 
 // ---------------------------------------------------------------------------------------------
 // Deeper levels (and the fallback for the root): rows gathered by row id, register-staged.
 // ---------------------------------------------------------------------------------------------
-struct Stage { unsigned id; float2 gh; };
+struct Stage { unsigned id; float2 gh; unsigned t0, t1; };
 
+// tail planes [bin][trep][tw] of the gather kernel: 32 KB (G + H, trep * tw = 16) fit next to three groups, 64 KB otherwise
+__host__ __device__ constexpr int gather_tail_replicas(int ng) { return ng >= 3 ? 4 : 8; }
+__host__ __device__ constexpr int gather_tail_bytes(int ng) { return ng >= 3 ? 32768 : 65536; }
+
+// Lane mapping: a row's 32*NG contiguous bytes are fetched by 2*NG adjacent lanes of ONE LDG.128 instruction (the sectors of
+// a row reach the L2 in one request, so DRAM serves them with whole 64 B bursts: requested by separate instructions a 96 B row
+// cost ~2.6 bursts), i.e. 16 / 8 / 5 rows per instruction for NG = 1 / 2 / 3 (NG = 3 leaves lanes 30, 31 idle).  Lane (row q,
+// chunk c) owns group c >> 1, half c & 1 and the slot rotation NG * q + (c >> 1): the <= 16 lanes that share a half have
+// distinct rotations, so every ATOMS instruction is still bank-conflict free.
 template <int NG, bool TAIL, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_gather_kernel(HistArgs a) {
+__global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_gather_kernel(HistArgs a) {
   constexpr int NWARPS = NTHREADS / 32;
-  constexpr int kItersPerWindow = kWindowRows / (kSuperRows * NWARPS);     // super-tiles per warp between overflow checks
-  constexpr int U = 2 * NG;                                                // (16-row sub-tile, group) units per super-tile
+  constexpr int LPR = 2 * NG, RPI = 32 / LPR, U = 2 * NG;                  // lanes per row, rows per instruction, units per super-tile
+  constexpr int SUP = RPI * U;                                             // positions per super-tile: 32, 32, 30
+  constexpr int kItersPerWindow = kWindowRows / (SUP * NWARPS);            // super-tiles per warp between overflow checks
   static_assert(kItersPerWindow >= 1, "window too small");
   extern __shared__ __align__(16) int smem[];                              // per group: G[8192] then H[8192]; then the tail planes
   const int nb = *a.build_count;
@@ -447,7 +458,8 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_g
   unsigned ceff = (T + kMinRowsPerCta - 1) / kMinRowsPerCta;
   ceff = ceff < 1 ? 1 : (ceff > C ? C : ceff);
   if (blockIdx.x >= ceff) return;
-  unsigned chunk = ((T + ceff - 1) / ceff + kSuperRows - 1) & ~(unsigned)(kSuperRows - 1);
+  unsigned chunk = (T + ceff - 1) / ceff;
+  chunk = (chunk + SUP - 1) / SUP * SUP;
   unsigned long long r0l = (unsigned long long)blockIdx.x * chunk;
   if (r0l >= T) return;
   unsigned r0 = (unsigned)r0l;
@@ -455,19 +467,23 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_g
   const int g0 = blockIdx.y * a.ng_chunk;
   const int ng_here = min(min(a.ng_chunk, NG), a.ngroups - g0);
   const bool has_tail = TAIL && a.tw > 0 && blockIdx.y == gridDim.y - 1;
-  const uint8_t* gbins = a.bins + (int64_t)g0 * kSlots;
   const float sg = a.scales[0], sh = a.scales[1];
   const unsigned smem_g = (unsigned)__cvta_generic_to_shared(smem);
   const int64_t row_stride = (int64_t)a.row_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const LaneConst lc = make_lane_const(lane, smem_g);
-  const int colbyte = (lane & 1) * 16, rowlane = lane >> 1;
+  const int q = lane / LPR, c = lane - q * LPR;                            // row inside a unit, 16 B chunk inside the row
+  const bool lane_on = q < RPI && (c >> 1) < ng_here;                       // idle lanes add zeros to a slot rotation nobody else uses
+  const LaneConst lc = make_lane_const_rot(q < RPI ? NG * q + (c >> 1) : 15, c & 1, smem_g + (unsigned)((q < RPI ? (c >> 1) : 0) * 2 * kPlaneBytes));
+  const uint8_t* gbins = a.bins + (int64_t)g0 * kSlots + c * 16;
   TailConst tc;
-  tc.tw = TAIL ? a.tw : 4; tc.base_g = smem_g + (unsigned)(NG * 2 * kPlaneBytes); tc.hplane_bytes = 256u * (unsigned)tc.tw * 4u;
-  tc.bin_stride = (unsigned)tc.tw * 4u; tc.rep_off = 0u;
+  constexpr int TREP = gather_tail_replicas(NG);          // replicas of the tail planes that fit next to the main planes
+  tc.tw = TAIL ? a.tw : 4;
+  const int trep = min(TREP, gather_tail_bytes(NG) / (2 * 256 * 4 * tc.tw));
+  tc.base_g = smem_g + (unsigned)(NG * 2 * kPlaneBytes); tc.hplane_bytes = 256u * (unsigned)(tc.tw * trep) * 4u;
+  tc.bin_stride = (unsigned)(tc.tw * trep) * 4u; tc.rep_off = (unsigned)((lane / tc.tw) % trep) * (unsigned)tc.tw * 4u;
 
   {
-    const int words4 = (NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * tc.tw * 4 : 0)) / 16;
+    const int words4 = (NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * tc.tw * trep * 4 : 0)) / 16;
     for (int i = threadIdx.x; i < words4; i += NTHREADS) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
   }
   __syncthreads();
@@ -476,7 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_g
   { int lo = 0, hi = nb; while (lo < hi) { int mid = (lo + hi) >> 1; if (a.build_prefix[mid + 1] > r0) hi = mid; else lo = mid + 1; } b = lo; }
 
   const size_t slot_entries = (size_t)a.ngroups * kGroupEntries + (size_t)256 * a.tw;
-  const Stage none{0xffffffffu, make_float2(0.f, 0.f)};
+  const Stage none{0xffffffffu, make_float2(0.f, 0.f), 0u, 0u};
   while (r0 < r1) {
     const unsigned nbeg = a.build_prefix[b], nend_node = a.build_prefix[b + 1];
     const unsigned nend = nend_node < r1 ? nend_node : r1;
@@ -487,38 +503,36 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_g
     GH64* out_tail = out_slot + (size_t)a.ngroups * kGroupEntries;
     long long accG = 0, accH = 0;
     const unsigned pa = seg + (r0 - nbeg), pb = seg + (nend - nbeg);
-    const unsigned nsuper = (pb - pa + kSuperRows - 1) / kSuperRows;
+    const unsigned nsuper = (pb - pa + SUP - 1) / SUP;
     const unsigned iters = (nsuper + NWARPS - 1) / NWARPS;          // same for every warp: barriers stay aligned
 
-    // Software pipeline per warp over super-tiles of 32 positions; it runs THROUGH the overflow-check barriers:
-    //   row ids + (g,h) two super-tiles ahead (coalesced, one position per lane);
-    //   bin chunks (LDG.128 per lane and unit) one super-tile ahead, ROLLING: the register of unit k is refilled with
-    //   unit k of the next super-tile right after it has been consumed (U + 1 loads in flight per lane at all times);
+    // Software pipeline per warp over super-tiles of SUP positions; it runs THROUGH the overflow-check barriers:
+    //   row ids + (g,h) + tail bytes two super-tiles ahead (coalesced, one position per lane);
+    //   bin chunks (one LDG.128 per lane and unit) one super-tile ahead, ROLLING: the register of unit k is refilled with
+    //   unit k of the next super-tile right after it has been consumed (U loads in flight per lane at all times);
     //   conflict-free ATOMS pairs now.
     auto load_ids = [&](unsigned st) -> Stage {
       Stage s_ = none;
-      unsigned p = pa + st * kSuperRows + lane;
-      if (st < nsuper && p < pb) { s_.id = a.ridx ? __ldg(a.ridx + p) : p; s_.gh = ldg_nc_f2(a.gpair + p); }
+      unsigned p = pa + st * SUP + lane;
+      if (lane < SUP && st < nsuper && p < pb) {
+        s_.id = a.ridx ? __ldg(a.ridx + p) : p; s_.gh = ldg_nc_f2(a.gpair + p);
+        if (TAIL && has_tail) {
+          if (a.tail_pos) s_.t0 = ldg_nc_u32(a.tail_pos + p);                       // tail bytes travel with the row ids (tw == 4)
+          else if (tc.tw == 4) s_.t0 = ldg_nc_u32(a.bins_tail + (int64_t)s_.id * 4);
+          else { const uint2 v = ldg_nc_v2(a.bins_tail + (int64_t)s_.id * 8); s_.t0 = v.x; s_.t1 = v.y; }
+        }
+      }
       return s_;
     };
     auto load_unit = [&](unsigned ids, int k) -> uint4 {
-      const int sub = k / NG, g = k - sub * NG;
-      const unsigned rid = __shfl_sync(0xffffffffu, ids, sub * 16 + rowlane);
-      return (rid != 0xffffffffu && g < ng_here) ? ldg_nc_v4(gbins + (int64_t)rid * row_stride + g * 32 + colbyte) : make_uint4(0, 0, 0, 0);
-    };
-    auto load_tail = [&](unsigned id, unsigned& t0, unsigned& t1) {
-      t0 = 0; t1 = 0;
-      if (has_tail && id != 0xffffffffu) {
-        if (tc.tw == 4) t0 = ldg_nc_u32(a.bins_tail + (int64_t)id * 4);
-        else { const uint2 v = ldg_nc_v2(a.bins_tail + (int64_t)id * 8); t0 = v.x; t1 = v.y; }
-      }
+      const unsigned rid = __shfl_sync(0xffffffffu, ids, q < RPI ? k * RPI + q : 0);
+      return (lane_on && rid != 0xffffffffu) ? ldg_nc_v4(gbins + (int64_t)rid * row_stride) : make_uint4(0, 0, 0, 0);
     };
     Stage cur = load_ids(warp);
     Stage nxt = load_ids(warp + NWARPS);
-    uint4 w[U]; unsigned t0 = 0, t1 = 0;
+    uint4 w[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) w[k] = load_unit(cur.id, k);
-    if (TAIL) load_tail(cur.id, t0, t1);
     for (unsigned it = 0; it < iters; ++it) {
       const unsigned s = warp + it * NWARPS;
       Stage nn = load_ids(s + 2 * NWARPS);
@@ -526,32 +540,30 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 2 : 3) : 1) hist_g
       const int gq_l = __float2int_rn(cur.gh.x * sg);
       const unsigned hq_l = (unsigned)__float2int_rn(cur.gh.y * sh);
       accG += gq_l; accH += hq_l;
-      static_for<0, U>([&](auto kc) {
-        constexpr int k = decltype(kc)::value, sub = k / NG, g = k - sub * NG;
-        if (active && g < ng_here) {
-          const int gq = __shfl_sync(0xffffffffu, gq_l, sub * 16 + rowlane);
-          const unsigned hq = __shfl_sync(0xffffffffu, hq_l, sub * 16 + rowlane);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (active) {
+          int gq = __shfl_sync(0xffffffffu, gq_l, q < RPI ? k * RPI + q : 0);
+          unsigned hq = __shfl_sync(0xffffffffu, hq_l, q < RPI ? k * RPI + q : 0);
+          if (!lane_on) { gq = 0; hq = 0; }
           unsigned ww[4];
           rotate_words(lc, w[k], ww);
-          accumulate16<false, g * 2 * kPlaneBytes>(lc, ww, gq, hq);
+          accumulate16<false, 0>(lc, ww, gq, hq);
         }
         w[k] = load_unit(nxt.id, k);
-      });
-      if (TAIL) {
-        if (active && has_tail) tail_accumulate<false>(tc, lane, t0, t1, gq_l, hq_l);
-        load_tail(nxt.id, t0, t1);
       }
+      if (TAIL) { if (active && has_tail) tail_accumulate<false>(tc, lane, cur.t0, cur.t1, gq_l, hq_l); }
       cur = nxt; nxt = nn;
       if ((it + 1) % kItersPerWindow == 0 && it + 1 < iters) {       // overflow check: at most kWindowRows rows since the last one
         __syncthreads();
         spill_main<2>(smem, ng_here, out_main, false, threadIdx.x, NTHREADS);
-        if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, 1, out_tail, false, threadIdx.x, NTHREADS);
+        if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, trep, out_tail, false, threadIdx.x, NTHREADS);
         __syncthreads();
       }
     }
     __syncthreads();
     spill_main<2>(smem, ng_here, out_main, true, threadIdx.x, NTHREADS);
-    if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, 1, out_tail, true, threadIdx.x, NTHREADS);
+    if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, trep, out_tail, true, threadIdx.x, NTHREADS);
     __syncthreads();
     if (a.accumulate_sum && blockIdx.y == 0) {
 #pragma unroll
@@ -634,7 +646,7 @@ static bool get_tensor_map(const uint8_t* bins, int64_t n, int row_stride, int b
 }
 
 template <int NG, bool TAIL, int NT> static void set_gather_attr() {
-  CUDA_OK(cudaFuncSetAttribute(hist_gather_kernel<NG, TAIL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * 8 * 4 : 0)));
+  CUDA_OK(cudaFuncSetAttribute(hist_gather_kernel<NG, TAIL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * 2 * kPlaneBytes + (TAIL ? gather_tail_bytes(NG) : 0)));
 }
 
 void hist_configure() {
@@ -650,7 +662,7 @@ void hist_configure() {
 
 template <int NG, bool TAIL, int NT>
 static void launch_gather(const HistArgs& a, int gx, int nchunks, cudaStream_t stream) {
-  const int smem = NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * a.tw * 4 : 0);
+  const int smem = NG * 2 * kPlaneBytes + (TAIL ? gather_tail_bytes(NG) : 0);
   hist_gather_kernel<NG, TAIL, NT><<<dim3(gx, nchunks), NT, smem, stream>>>(a);
 }
 
@@ -677,7 +689,7 @@ void launch_hist_build(const HistArgs& a_in, int num_sms, cudaStream_t stream) {
   const bool tail = a.tw > 0;
   const int ng = a.ng_chunk;
   if (ng == 1) {
-    const int per_sm = tail ? 2 : 3;
+    const int per_sm = tail ? 1 : 3;          // 64 KB of planes (+ 64 KB of replicated tail planes) per CTA
     const int gx = (num_sms * per_sm + nchunks - 1) / nchunks;
     if (tail) launch_gather<1, true, 256>(a, gx, nchunks, stream); else launch_gather<1, false, 256>(a, gx, nchunks, stream);
   } else {

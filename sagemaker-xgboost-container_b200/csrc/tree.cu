@@ -403,12 +403,15 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(PartArgs a) {
   const unsigned pt = p0 + threadIdx.x * 8;
   __shared__ unsigned s_rid[kPartTile];
   __shared__ float2 s_gp[kPartTile];
+  __shared__ unsigned s_tl[kPartTile];
   __shared__ unsigned s_w[8];
-  unsigned rows[8]; float2 gp[8]; unsigned char fl[8]; unsigned mine = 0;
+  const bool has_tl = a.tl_cur != nullptr;
+  unsigned rows[8]; float2 gp[8]; unsigned tl[8]; unsigned char fl[8]; unsigned mine = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     unsigned p = pt + j;
-    if (p < p1) { rows[j] = a.ridx_cur ? a.ridx_cur[p] : p; gp[j] = a.gp_cur[p]; fl[j] = gs.flags[p]; mine += fl[j]; } else { rows[j] = 0; gp[j] = make_float2(0.f, 0.f); fl[j] = 2; }
+    if (p < p1) { rows[j] = a.ridx_cur ? a.ridx_cur[p] : p; gp[j] = a.gp_cur[p]; tl[j] = has_tl ? a.tl_cur[p] : 0u; fl[j] = gs.flags[p]; mine += fl[j]; }
+    else { rows[j] = 0; gp[j] = make_float2(0.f, 0.f); tl[j] = 0u; fl[j] = 2; }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned x = mine;
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(PartArgs a) {
     if (fl[j] == 2) continue;
     unsigned jj = threadIdx.x * 8 + j;
     unsigned slot = fl[j] ? lbefore++ : tile_left + (jj - lbefore);
-    s_rid[slot] = rows[j]; s_gp[slot] = gp[j];
+    s_rid[slot] = rows[j]; s_gp[slot] = gp[j]; if (has_tl) s_tl[slot] = tl[j];
   }
   __syncthreads();
   // lefts go to [b + toff, ...), rights to [b + nl + (tile start - toff), ...): two contiguous, coalesced streams
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(PartArgs a) {
     unsigned dest = k < tile_left ? dl + k : dr + (k - tile_left);
     a.ridx_next[dest] = s_rid[k];
     a.gp_next[dest] = s_gp[k];
+    if (has_tl) a.tl_next[dest] = s_tl[k];
   }
 }
 

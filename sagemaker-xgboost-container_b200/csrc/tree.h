@@ -24,12 +24,14 @@ struct ApplyArgs {
 struct PartArgs {
   GrowState gs; TreeArrays tree; const uint8_t* bins_col; int64_t n; const unsigned* ridx_cur; unsigned* ridx_next;
   const float2* gp_cur; float2* gp_next;      // (g,h) pairs travel with the row ids (position order)
+  const unsigned* tl_cur; unsigned* tl_next;  // ... and so do the 4 tail bin bytes of a row (nullptr when there is no 4-wide tail)
   int has_missing, level, max_level_nodes;
 };
 
 struct HistArgs {
   const uint8_t* bins;          // main: row-major [n][ngroups*32 B]
   const uint8_t* bins_tail;     // tail: row-major [n][tw B], nullptr when tw == 0
+  const unsigned* tail_pos;     // tw == 4 only: the rows' tail words by POSITION (they travel with the row ids); nullptr = gather from bins_tail
   int64_t n;
   int row_stride;               // ngroups * 32
   int tw;                       // tail width in bytes (0, 4, 8)

@@ -35,6 +35,30 @@ def test_main_unit_is_bank_conflict_free_and_covers_the_unit():
     assert len(seen) == 16 * 32 and set(seen.values()) == {1}
 
 
+def test_gather_kernel_row_contiguous_mapping_is_conflict_free():
+    """hist_gather_kernel: 2*NG adjacent lanes fetch one row's 32*NG contiguous bytes (16 / 8 / 5 rows per instruction);
+    lane (row q, chunk c) = group c >> 1, half c & 1, rotation NG * q + (c >> 1); NG = 3 idles lanes 30, 31 on rotation 15."""
+    for NG in (1, 2, 3):
+        LPR, RPI = 2 * NG, 32 // (2 * NG)
+        seen = {}
+        for jw, jb in itertools.product(range(4), range(4)):
+            banks = set()
+            for lane in range(32):
+                q, c = lane // LPR, lane % LPR
+                on = q < RPI
+                role = dict(rot=(NG * q + (c >> 1)) if on else 15, half=c & 1)
+                k, slot = step_target(role, jw, jb)
+                bank = slot % 32                               # group plane offsets are multiples of 32 words
+                assert bank not in banks, (NG, jw, jb, lane)
+                banks.add(bank)
+                if on:
+                    key = (q, c >> 1, slot)
+                    seen[key] = seen.get(key, 0) + 1
+                    assert (c & 1) * 16 + k == slot            # byte k of chunk c is slot 16 * half + k of group c >> 1
+            assert len(banks) == 32
+        assert len(seen) == RPI * NG * 32 and set(seen.values()) == {1}
+
+
 def test_replicated_tail_is_bank_conflict_free_and_covers_the_unit():
     for tw in (4, 8):
         trep = 32 // tw                                        # plane [bin][trep][tw] int32
@@ -67,7 +91,7 @@ def test_fixed_point_window_cannot_overflow_int32():
     GRAD_BITS, HESS_BITS, WINDOW, SPILL = 18, 19, 8064, 1 << 24       # engine.h / hist.cu constants
     assert (SPILL - 1) + WINDOW * (1 << GRAD_BITS) < 2 ** 31           # signed gradient plane
     assert (SPILL - 1) + WINDOW * (1 << HESS_BITS) < 2 ** 32           # unsigned hessian plane
-    for nwarps in (8, 24):                                             # gather kernel: super-tiles of 32 rows per warp between checks
-        assert (WINDOW // (32 * nwarps)) * 32 * nwarps <= WINDOW
+    for sup, nwarps in ((32, 8), (32, 24), (30, 24)):                  # gather kernel: super-tiles of 32 / 30 rows per warp between checks
+        assert (WINDOW // (sup * nwarps)) * sup * nwarps <= WINDOW
     for R in (64, 128, 192, 256):                                      # root kernel: whole tiles between checks
         assert (WINDOW // R) * R <= WINDOW
