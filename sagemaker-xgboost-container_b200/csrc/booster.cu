@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include "comm.h"
 
 namespace b200 {
@@ -53,7 +54,7 @@ void DMatrix::finish_upload(float missing) {
   if (use_missing) launch_replace_missing(X.p, count, missing, s);
   unsigned long long c = 0;
   CUDA_OK(cudaMemcpyAsync(&c, cnt.p, 8, cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
+  Comm::get().sync_stream(s);
   has_missing = c > 0;
 }
 
@@ -117,7 +118,7 @@ std::unique_ptr<DMatrix> DMatrix::slice(const int* idx, int64_t len) const {
     int grid = (int)std::min<int64_t>((len * F + 255) / 256, 148 * 16);
     gather_rows_kernel<<<grid, 256, 0, s>>>(X.p, F, didx.p, len, dm->X.p); ++g_kernel_launches;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaStreamSynchronize(s));
+    Comm::get().sync_stream(s);
   }
   auto take = [&](const std::vector<float>& src, size_t per_row) { std::vector<float> o; if (src.empty()) return o; o.resize(len * per_row);
     for (int64_t i = 0; i < len; ++i) for (size_t k = 0; k < per_row; ++k) o[i * per_row + k] = src[(size_t)idx[i] * per_row + k]; return o; };
@@ -131,7 +132,7 @@ void DMatrix::set_float_info(const std::string& field, const float* v, size_t le
   cudaStream_t s = engine_stream();
   auto put = [&](std::vector<float>& h, DevBuf<float>& d) {
     h.assign(v, v + len); d.alloc(len);
-    if (len) { CUDA_OK(cudaMemcpyAsync(d.p, h.data(), sizeof(float) * len, cudaMemcpyHostToDevice, s)); CUDA_OK(cudaStreamSynchronize(s)); }
+    if (len) { CUDA_OK(cudaMemcpyAsync(d.p, h.data(), sizeof(float) * len, cudaMemcpyHostToDevice, s)); Comm::get().sync_stream(s); }
   };
   if (field == "label") put(labels, d_labels);
   else if (field == "weight") {
@@ -166,7 +167,7 @@ void DMatrix::bin_with_cuts() {
   launch_bin(X.p, n, F, ngroups, tw, d_cut_ptrs.p, d_cut_vals.p, bins.p, bins_tail.p, s);
   bins_col.alloc((size_t)std::max(F, 1) * n);
   launch_transpose_bins(bins.p, bins_tail.p, n, F, ngroups, tw, bins_col.p, s);
-  CUDA_OK(cudaStreamSynchronize(s));
+  Comm::get().sync_stream(s);
   binned = true;
 }
 
@@ -193,7 +194,7 @@ void DMatrix::ensure_binned(int max_bin) {
       DevBuf<unsigned> flag; flag.alloc(1); unsigned v = (unsigned)hm;
       CUDA_OK(cudaMemcpyAsync(flag.p, &v, 4, cudaMemcpyHostToDevice, s));
       comm.allreduce_max_u32(flag.p, 1, s);
-      CUDA_OK(cudaMemcpyAsync(&v, flag.p, 4, cudaMemcpyDeviceToHost, s)); CUDA_OK(cudaStreamSynchronize(s));
+      CUDA_OK(cudaMemcpyAsync(&v, flag.p, 4, cudaMemcpyDeviceToHost, s)); Comm::get().sync_stream(s);
       has_missing = v != 0;
     }
     std::vector<FeatureSummary> local;
@@ -213,7 +214,7 @@ void DMatrix::ensure_binned(int max_bin) {
     comm.allgather_bytes(dsend.p, drecv.p, sendbuf.size(), s);
     std::vector<unsigned char> all(sendbuf.size() * W);
     CUDA_OK(cudaMemcpyAsync(all.data(), drecv.p, all.size(), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    Comm::get().sync_stream(s);
     std::vector<FeatureSummary> merged(F);
     for (int f = 0; f < F; ++f) {
       std::vector<std::pair<float, double>> pts;
@@ -271,7 +272,16 @@ struct PinnedPool {
 };
 
 struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds; int world, root_mode; int64_t n; };
-struct TreeGraph { cudaGraphExec_t exec = nullptr; TreeGraphKey key; long long launches = 0; TreeGraph() { memset(&key, 0, sizeof key); } };
+// The per-tree launch sequence as CUDA graphs.  On one GPU it is a single graph; with NCCL it is cut into SEGMENTS at every
+// collective (root + one per level): the segments are replayed as graphs and the all-reduces are issued between them as
+// ordinary stream operations, so no NCCL call is ever captured (a capture with lazily connecting NCCL channels hung an
+// 8-rank run in round 1) while a tree still costs ~2 host operations per level instead of ~13.
+struct TreeGraph {
+  std::vector<cudaGraphExec_t> segs; std::vector<std::function<void()>> colls;      // colls[i] runs after segs[i]
+  TreeGraphKey key; long long launches = 0;
+  TreeGraph() { memset(&key, 0, sizeof key); }
+  void destroy() { for (auto e : segs) if (e) cudaGraphExecDestroy(e); segs.clear(); colls.clear(); }
+};
 
 struct GrowerImpl {
   int64_t n = 0; int ngroups = 0, tw = 0, max_depth = 0, max_nodes = 0, cap_nodes = 0, max_level_nodes = 0, region = 0;
@@ -287,13 +297,14 @@ struct GrowerImpl {
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
   DevBuf<DevNode> packed; std::vector<TreeGraph> graphs; std::vector<char> eager_done;
+  TreeGraph* capturing = nullptr;          // set while enqueue_tree runs under stream capture: collectives cut the capture
 
   void ensure(int64_t n_, int ngroups_, int tw_, int max_depth_, int K) {
     const int64_t stride_ = (n_ + 63) & ~(int64_t)63;
     if (n == n_ && ngroups == ngroups_ && tw == tw_ && max_depth == max_depth_ && gpair.n >= (size_t)stride_ * K + 512) return;
     B200_CHECK(max_depth_ >= 1 && max_depth_ <= kMaxDepth, "max_depth must be in [1, 16] for the B200 depth-wise hist builder");
     n = n_; ngroups = ngroups_; tw = tw_; max_depth = max_depth_; gp_stride = stride_; root_h_valid = false;
-    for (auto& tg : graphs) if (tg.exec) { cudaGraphExecDestroy(tg.exec); tg.exec = nullptr; }
+    for (auto& tg : graphs) tg.destroy();
     max_nodes = (1 << (max_depth + 1)) - 1;
     cap_nodes = (max_nodes + 15) & ~15;
     max_level_nodes = 1 << (max_depth - 1);
@@ -455,7 +466,7 @@ void Booster::estimate_base_score(DMatrix* dtrain) {
   Comm::get().allreduce_sum_f64(g.dsum.p, 2, s);
   double h[2];
   CUDA_OK(cudaMemcpyAsync(h, g.dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
+  Comm::get().sync_stream(s);
   float w = h[1] <= 0.0 ? 0.0f : (float)(-h[0] / h[1]);
   // binary:logitraw keeps base_score in probability space like the other logistic objectives (the estimated stump weight
   // w is a margin; storing it raw and taking its logit again gives NaN whenever w <= 0, i.e. whenever mean(y) < 0.5)
@@ -510,11 +521,11 @@ void Booster::upload_model() {
       size_t cap = std::max<size_t>(d_nodes.n * 2, d_nodes_used + nn + 4096);
       DevBuf<DevNode> nb; nb.alloc(cap);
       if (d_nodes_used) CUDA_OK(cudaMemcpyAsync(nb.p, d_nodes.p, sizeof(DevNode) * d_nodes_used, cudaMemcpyDeviceToDevice, s));
-      CUDA_OK(cudaStreamSynchronize(s));
+      Comm::get().sync_stream(s);
       std::swap(nb.p, d_nodes.p); std::swap(nb.n, d_nodes.n);
     }
     CUDA_OK(cudaMemcpyAsync(d_nodes.p + d_nodes_used, nodes.data(), sizeof(DevNode) * nn, cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    Comm::get().sync_stream(s);
     h_tree_offset[t] = (int64_t)d_nodes_used; h_tree_offset[t + 1] = (int64_t)d_nodes_used + nn;
     d_nodes_used += nn; on_device_[t] = 1; d_trees_uploaded = 0;
   }
@@ -523,7 +534,7 @@ void Booster::upload_model() {
     // offsets are per-tree starts (trees trained on the device have fixed-capacity slots, so starts are not cumulative)
     CUDA_OK(cudaMemcpyAsync(d_tree_offset.p, h_tree_offset.data(), sizeof(int64_t) * (nt + 1), cudaMemcpyHostToDevice, s));
     if (nt) CUDA_OK(cudaMemcpyAsync(d_tree_info.p, tree_info_.data(), sizeof(int) * nt, cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    Comm::get().sync_stream(s);
     d_trees_uploaded = nt;
   }
 }
@@ -631,9 +642,22 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   prof_end();
   if (root_mode == 1) { snapshot_h_kernel<<<148, 256, 0, s>>>(g.hist_pool.p, g.root_h_cache.p, g.slot_stride); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
   ha.g_only = 0;
-  if (comm.distributed()) {
-    comm.allreduce_sum_i64(g.hist_pool.p, g.slot_stride * 2, s);
-    comm.allreduce_sum_i64(g.gs.node_sum, 2, s);
+  // a collective: issued directly, or (under capture) closes the current graph segment and is remembered for the replay
+  auto collective = [&](std::function<void()> f) {
+    if (!comm.distributed()) return;
+    if (!g.capturing) { f(); return; }
+    cudaGraph_t graph = nullptr;
+    CUDA_OK(cudaStreamEndCapture(s, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_OK(e);
+    g.capturing->segs.push_back(exec); g.capturing->colls.push_back(f);
+    CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  };
+  {
+    GH64* pool = g.hist_pool.p; GH64* nsum = g.gs.node_sum; const size_t cnt = g.slot_stride * 2;
+    collective([pool, nsum, cnt, s]() { Comm::get().allreduce_sum_i64(pool, cnt, s); Comm::get().allreduce_sum_i64(nsum, 2, s); });
   }
   EvalArgs ea{}; ea.hist_pool = g.hist_pool.p; ea.gs = g.gs; ea.cut_ptrs = dtrain->d_cut_ptrs.p; ea.feat_mask = mask; ea.p = pd; ea.F = bm.F;
   ea.ngroups = bm.ngroups; ea.tw = bm.tw; ea.ntail = bm.ntail; ea.has_missing = bm.has_missing; ea.level = 0; ea.max_level_nodes = g.max_level_nodes;
@@ -663,7 +687,10 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
     prof_begin(L + 1);
     launch_hist_build(ha, num_sms, s);
     prof_end();
-    if (comm.distributed()) comm.allreduce_sum_i64(g.hist_pool.p + (size_t)next_base * g.slot_stride, (size_t)next_half * g.slot_stride * 2, s);
+    {
+      GH64* lvl = g.hist_pool.p + (size_t)next_base * g.slot_stride; const size_t cnt = (size_t)next_half * g.slot_stride * 2;
+      collective([lvl, cnt, s]() { Comm::get().allreduce_sum_i64(lvl, cnt, s); });
+    }
     launch_subtract(g.gs, g.hist_pool.p, g.slot_stride, next_half, s);
     ea.level = L + 1;
     launch_eval(ea, 1 << (L + 1), s);
@@ -686,19 +713,16 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     std::string m = colsample_mask(param_.seed, tree_index, dtrain->F, param_.colsample_bytree);
     g.feat_mask.ensure(m.size());
     CUDA_OK(cudaMemcpyAsync(g.feat_mask.p, m.data(), m.size(), cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    Comm::get().sync_stream(s);
     mask = g.feat_mask.p;
   }
   g.packed.ensure((size_t)g.cap_nodes);
   static const bool no_graph = getenv("B200XGB_NO_GRAPH") != nullptr;
-  // Graph replay is used on a single GPU only: capturing NCCL collectives (lazy channel set-up inside a capture) hung an
-  // 8-rank run in round 1, so multi-rank training issues the same sequence directly until that is understood.
-  // B200XGB_GRAPH_MULTI=1 (experiment knob): capture also with NCCL, but only after each class has run one tree eagerly
-  // so that every collective of the sequence has already set up its channels outside a capture.
-  static const bool graph_multi = getenv("B200XGB_GRAPH_MULTI") != nullptr;
+  static const bool no_graph_multi = getenv("B200XGB_NO_GRAPH_MULTI") != nullptr;      // multi-rank: issue every launch directly
   const bool dist = Comm::get().distributed();
   if ((int)g.eager_done.size() <= k) g.eager_done.resize(k + 1, 0);
-  const bool eager_first = dist && graph_multi && !g.eager_done[k];
+  // the first tree of every class runs eagerly when ranks are connected: NCCL sets up its channels on first use
+  const bool eager_first = dist && !g.eager_done[k];
   // constant-hessian root pass: eligible when every row has h == 1 in every round
   static const bool no_consth = getenv("B200XGB_NO_CONSTH") != nullptr;
   const bool consth = !no_consth && param_.objective == kSquaredError && param_.num_class == 1 && dtrain->weights.empty() &&
@@ -708,7 +732,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     if (g.root_h_valid && g.root_h_uid == dtrain->uid && g.root_h_version == dtrain->binned_version) root_mode = 2;
     else root_mode = 1;
   }
-  if (profile_ || no_graph || (dist && !graph_multi) || eager_first || root_mode == 1) {
+  if (profile_ || no_graph || (dist && no_graph_multi) || eager_first || root_mode == 1) {
     g.eager_done[k] = 1;
     enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p, root_mode);
     if (root_mode == 1) { g.root_h_valid = true; g.root_h_uid = dtrain->uid; g.root_h_version = dtrain->binned_version; }
@@ -721,20 +745,28 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     key.bins = dtrain->bins.p; key.bins_col = dtrain->bins_col.p; key.cuts = dtrain->d_cut_vals.p;     // re-binning invalidates the capture
     key.max_leaves = param_.max_leaves; key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
     key.mcw = param_.min_child_weight; key.mds = param_.max_delta_step; key.world = Comm::get().world(); key.n = dtrain->n;
-    if (!tg.exec || memcmp(&tg.key, &key, sizeof key) != 0) {
-      if (tg.exec) { cudaGraphExecDestroy(tg.exec); tg.exec = nullptr; }
-      cudaGraph_t graph = nullptr;
+    if (tg.segs.empty() || memcmp(&tg.key, &key, sizeof key) != 0) {
+      tg.destroy();
       const long long launches_before = g_kernel_launches;
       CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      g.capturing = &tg;
+      cudaGraph_t graph = nullptr;
       try { enqueue_tree(dtrain, cache.margin.p, k, mask, g.packed.p, root_mode); }
-      catch (...) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+      catch (...) { g.capturing = nullptr; cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); tg.destroy(); throw; }
+      g.capturing = nullptr;
       CUDA_OK(cudaStreamEndCapture(s, &graph));
-      CUDA_OK(cudaGraphInstantiate(&tg.exec, graph, 0));
-      CUDA_OK(cudaGraphDestroy(graph));
+      cudaGraphExec_t exec = nullptr;
+      cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { tg.destroy(); CUDA_OK(e); }
+      tg.segs.push_back(exec);
       tg.key = key; tg.launches = g_kernel_launches - launches_before;
       g_kernel_launches = launches_before;               // capture enqueued nothing
     }
-    CUDA_OK(cudaGraphLaunch(tg.exec, s));
+    for (size_t i = 0; i < tg.segs.size(); ++i) {
+      CUDA_OK(cudaGraphLaunch(tg.segs[i], s));
+      if (i < tg.colls.size()) tg.colls[i]();
+    }
     g_kernel_launches += tg.launches;
   }
 
@@ -744,7 +776,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     size_t cap = std::max<size_t>(d_nodes.n * 2, need + 64 * (size_t)g.cap_nodes);
     DevBuf<DevNode> nb; nb.alloc(cap);
     if (d_nodes_used) CUDA_OK(cudaMemcpyAsync(nb.p, d_nodes.p, sizeof(DevNode) * d_nodes_used, cudaMemcpyDeviceToDevice, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    Comm::get().sync_stream(s);
     std::swap(nb.p, d_nodes.p); std::swap(nb.n, d_nodes.n);
   }
   CUDA_OK(cudaMemcpyAsync(d_nodes.p + d_nodes_used, g.packed.p, sizeof(DevNode) * (size_t)g.cap_nodes, cudaMemcpyDeviceToDevice, s));
@@ -801,13 +833,13 @@ std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, c
         compute_auc_device(c.margin.p, dm->d_labels.p, dm->weights.empty() ? nullptr : dm->d_weights.p, dm->n, logistic, grower_->dsum.p, s);
         double h3[3];
         CUDA_OK(cudaMemcpyAsync(h3, grower_->dsum.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-        CUDA_OK(cudaStreamSynchronize(s));
+        Comm::get().sync_stream(s);
         double pair[2] = {h3[0], h3[1] * h3[2]};
         if (Comm::get().distributed()) {
           CUDA_OK(cudaMemcpyAsync(grower_->dsum.p, pair, 2 * sizeof(double), cudaMemcpyHostToDevice, s));
           Comm::get().allreduce_sum_f64(grower_->dsum.p, 2, s);
           CUDA_OK(cudaMemcpyAsync(pair, grower_->dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-          CUDA_OK(cudaStreamSynchronize(s));
+          Comm::get().sync_stream(s);
         }
         B200_CHECK(pair[1] > 0.0, "Check failed: !auc_error AUC: the dataset only contains pos or neg samples");
         char buf[64]; snprintf(buf, sizeof buf, "%.17g", pair[0] / pair[1]);
@@ -825,7 +857,7 @@ std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, c
       Comm::get().allreduce_sum_f64(grower_->dsum.p, 2, s);
       double h[2];
       CUDA_OK(cudaMemcpyAsync(h, grower_->dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-      CUDA_OK(cudaStreamSynchronize(s));
+      Comm::get().sync_stream(s);
       double v = h[1] == 0.0 ? h[0] : h[0] / h[1];
       if (mname == "rmse") v = std::sqrt(v);
       char buf[64]; snprintf(buf, sizeof buf, "%.17g", v);
@@ -863,7 +895,7 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
     launch_predict(pa, s);
     std::vector<int> h((size_t)n * nt);
     if (!h.empty()) CUDA_OK(cudaMemcpyAsync(h.data(), leaf.p, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    Comm::get().sync_stream(s);
     out->resize(h.size());
     for (size_t i = 0; i < h.size(); ++i) (*out)[i] = (float)h[i];
     shape->assign({(uint64_t)n, (uint64_t)nt});
@@ -884,7 +916,7 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
   }
   out->resize((size_t)n * out_cols);
   if (!out->empty()) CUDA_OK(cudaMemcpyAsync(out->data(), (type == 0 && param_.objective == kSoftmax) ? cls.p : margin.p, sizeof(float) * out->size(), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
+  Comm::get().sync_stream(s);
   if (out_cols == 1 && !strict_shape) shape->assign({(uint64_t)n});
   else shape->assign({(uint64_t)n, (uint64_t)out_cols});
 }
@@ -933,7 +965,7 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   hist_out->resize(g.slot_stride * 2);
   CUDA_OK(cudaMemcpyAsync(hist_out->data(), g.hist_pool.p, sizeof(GH64) * g.slot_stride, cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaMemcpyAsync(scales_out, g.gs.scales, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
+  Comm::get().sync_stream(s);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
 }
 
@@ -944,7 +976,7 @@ void Booster::cached_margin(DMatrix* dm, std::vector<float>* out) {
   bring_cache_up_to_date(dm, c);
   out->resize((size_t)dm->n * param_.num_class);
   if (!out->empty()) CUDA_OK(cudaMemcpyAsync(out->data(), c.margin.p, sizeof(float) * out->size(), cudaMemcpyDeviceToHost, s));
-  CUDA_OK(cudaStreamSynchronize(s));
+  Comm::get().sync_stream(s);
 }
 
 void Booster::set_profile(bool on) {
@@ -966,7 +998,7 @@ void Booster::prof_end() {
 }
 std::string Booster::get_profile() {
   cudaStream_t s = engine_stream();
-  CUDA_OK(cudaStreamSynchronize(s));
+  Comm::get().sync_stream(s);
   double root_ms = 0, deep_ms = 0; long long root_n = 0, deep_n = 0;
   for (auto& e : prof_events_) { float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, e.a, e.b)); if (e.level == 0) { root_ms += ms; ++root_n; } else { deep_ms += ms; ++deep_n; } }
   unsigned long long rows[2] = {0, 0};

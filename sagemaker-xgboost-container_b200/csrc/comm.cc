@@ -2,7 +2,10 @@
 #include "comm.h"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include "engine.h"
 
 namespace b200 {
@@ -16,6 +19,8 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
 };
 NcclApi& api() {
   static NcclApi a;
@@ -27,6 +32,7 @@ NcclApi& api() {
 #define L(sym, field) a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.h, sym)); B200_CHECK(a.field != nullptr, std::string("libnccl: missing symbol ") + sym)
   L("ncclGetUniqueId", GetUniqueId); L("ncclCommInitRank", CommInitRank); L("ncclCommDestroy", CommDestroy);
   L("ncclAllReduce", AllReduce); L("ncclAllGather", AllGather); L("ncclBroadcast", Broadcast); L("ncclGetErrorString", GetErrorString);
+  L("ncclCommGetAsyncError", CommGetAsyncError); L("ncclCommAbort", CommAbort);
 #undef L
   return a;
 }
@@ -67,6 +73,29 @@ void Comm::allreduce_max_u32(void* buf, size_t count, cudaStream_t s) {
 void Comm::allgather_bytes(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s) {
   if (world_ <= 1) { if (send != recv) CUDA_OK(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, s)); return; }
   NCCL_OK(api().AllGather(send, recv, bytes_per_rank, ncclUint8, static_cast<ncclComm_t>(comm_), s));
+}
+void Comm::sync_stream(cudaStream_t s) {
+  if (world_ <= 1 || !comm_) { CUDA_OK(cudaStreamSynchronize(s)); return; }
+  static const double limit = [] { const char* e = getenv("B200XGB_COLLECTIVE_TIMEOUT"); double v = e ? atof(e) : 600.0; return v > 0 ? v : 600.0; }();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spin = 0;; ++spin) {
+    cudaError_t q = cudaStreamQuery(s);
+    if (q == cudaSuccess) return;
+    if (q != cudaErrorNotReady) CUDA_OK(q);
+    if ((spin & 63) == 63) {
+      ncclResult_t ar = ncclSuccess;
+      ncclResult_t r = api().CommGetAsyncError(static_cast<ncclComm_t>(comm_), &ar);
+      const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (r != ncclSuccess || (ar != ncclSuccess && ar != ncclInProgress) || waited > limit) {
+        const std::string why = r != ncclSuccess ? api().GetErrorString(r) : (ar != ncclSuccess && ar != ncclInProgress) ? api().GetErrorString(ar)
+                                : "no progress for " + std::to_string((int)waited) + " s (B200XGB_COLLECTIVE_TIMEOUT)";
+        api().CommAbort(static_cast<ncclComm_t>(comm_)); comm_ = nullptr;
+        const int r_ = rank_; rank_ = 0; world_ = 1;
+        throw Error("NCCL collective failed on rank " + std::to_string(r_) + ": " + why + "; the communicator was aborted");
+      }
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+  }
 }
 void Comm::broadcast_bytes(void* buf, size_t bytes, int root, cudaStream_t s) {
   if (world_ <= 1 || bytes == 0) return;

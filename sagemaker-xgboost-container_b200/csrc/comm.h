@@ -27,6 +27,10 @@ class Comm {
   void allreduce_max_u32(void* buf, size_t count, cudaStream_t s);
   void allgather_bytes(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
   void broadcast_bytes(void* buf, size_t bytes, int root, cudaStream_t s);
+  // Wait for `s` like cudaStreamSynchronize, but while ranks are connected poll the communicator for asynchronous errors
+  // and give up after B200XGB_COLLECTIVE_TIMEOUT seconds (default 600): a failed or hung collective aborts the
+  // communicator and surfaces as an Error (-> XGBoostError) instead of blocking the job for ever.
+  void sync_stream(cudaStream_t s);
  private:
   int rank_ = 0, world_ = 1;
   void* comm_ = nullptr;
