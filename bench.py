@@ -8,9 +8,9 @@
 metric  : boosting rounds/sec (BASELINE.json) on synthetic 50M x 100 reg:squarederror, 256 bins, max_depth 6.
 step    : one boosting round (one tree) over the whole matrix.
 value   : K / device time of K rounds, inputs resident in HBM (CUDA events on the engine stream, max over ranks).
-e2e     : the same through the public Python API with HOST buffers: DMatrix(numpy) [H2D + quantile cuts + binning],
-          then per round Booster.update + Booster.eval_set (D2H of the metric), reported for a 200-round job:
-          200 / (ingest + 200 * step).
+e2e     : MEASURED: a whole 200-round job through the public API from pinned HOST buffers -- xgb.DMatrix(numpy) [H2D],
+          xgb.train(..., evals=[(dtrain, "train")]) [cuts + binning + 200 x (update + eval with a D2H of the metric)] --
+          wall clock, max over ranks; value = 200 / wall.  The ingest breakdown is reported beside it.
 roofline: histogram-build kernel, root launch (all rows): algorithmic bytes rows*(F+8) / mean launch time measured with
           CUDA events inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
 """
@@ -28,7 +28,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PROFILE_ROUNDS = 3
-JOB_ROUNDS = 200          # rounds of the end-to-end job the ingest cost is amortised over (BASELINE config 2 uses 200)
 
 
 def parse_args():
@@ -44,7 +43,9 @@ def parse_args():
     ap.add_argument("--max-depth", type=int, default=6)
     ap.add_argument("--max-bin", type=int, default=256)
     ap.add_argument("--seed", type=int, default=43)
-    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=4_000_000, help="rows of the cpu_baseline leg of the default arm")
+    ap.add_argument("--reference-rows", type=int, default=10_000_000, help="rows of the --impl reference arm (same generator, first blocks)")
+    ap.add_argument("--job-rounds", type=int, default=200)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
@@ -167,14 +168,35 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def oracle_rounds_per_sec(a, Xs, ys, steps, warmup):
-    """Time the CPU restatement of the reference's hist path on a bounded sample (all host threads)."""
+def host_threads():
+    """Threads the CPU arm uses: every core this process may run on (never inherited from OMP_NUM_THREADS: torchrun sets it to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def gen_host_sample(a, S):
+    """First S rows of the workload, from the SAME generator and seed as the GPU arm (gen_block_torch, block by block)."""
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    xs, ys = [], []
+    for b in range((S + BLOCK - 1) // BLOCK):
+        rows = min(BLOCK, a.rows - b * BLOCK, S - b * BLOCK)
+        xb, yb = gen_block_torch(b, min(BLOCK, a.rows - b * BLOCK), a.cols, a.seed, a.objective, max(a.num_class, 1), dev)
+        xs.append(xb[:rows].cpu().numpy()); ys.append(yb[:rows].cpu().numpy())
+    return np.ascontiguousarray(np.concatenate(xs)), np.ascontiguousarray(np.concatenate(ys)), str(dev.type)
+
+
+def oracle_rounds_per_sec(a, Xs, ys, steps, warmup, threads):
+    """Time the CPU restatement of the reference's hist path on a bounded sample with an explicit thread count."""
     from oracle import gbt_oracle as O
+    O.set_num_threads(threads)
     t0 = time.time()
     cuts = O.make_cuts(Xs, a.max_bin)
     bins = O.bin_matrix(Xs, cuts[0], cuts[1])
     ingest = time.time() - t0
-    tr = O.Trainer(params_of(a), bins=bins, cuts=cuts, y=ys)
+    tr = O.Trainer(dict(params_of(a), nthread=threads), bins=bins, cuts=cuts, y=ys)
     for _ in range(warmup):
         tr.update()
     t0 = time.time()
@@ -186,37 +208,43 @@ def oracle_rounds_per_sec(a, Xs, ys, steps, warmup):
 
 def run_reference(a):
     """--impl reference: the reference's own CPU hist implementation.  xgboost==3.0.5 is not installable in this image
-    (no network, no wheel), so this arm times the oracle port of that path on the host cores, on a bounded sample."""
+    (no network, no wheel), so this arm times the oracle port of that path on the host cores: same generator and seed
+    as the GPU arm, a stated row sample, an explicit thread count."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rng = np.random.default_rng(a.seed)
-    S = min(a.rows, a.cpu_sample_rows)
-    X = rng.standard_normal((S, a.cols), dtype=np.float32)
-    X = (np.round(np.clip(X, -4, 4 - 1 / 32) * 32) / 32).astype(np.float32)
-    beta = (rng.standard_normal(a.cols) / np.sqrt(a.cols)).astype(np.float32)
-    if a.objective.startswith("binary"):
-        y = (1 / (1 + np.exp(-(X @ beta + 0.5 * rng.standard_normal(S).astype(np.float32)))) > rng.random(S)).astype(np.float32)
-    elif a.objective.startswith("multi"):
-        bk = (rng.standard_normal((a.cols, a.num_class)) / np.sqrt(a.cols)).astype(np.float32)
-        y = np.argmax(X @ bk + rng.standard_normal((S, a.num_class)).astype(np.float32), axis=1).astype(np.float32)
-    else:
-        y = (X @ beta + 0.1 * rng.standard_normal(S).astype(np.float32)).astype(np.float32)
-    rps_sample, ingest_s, cores = oracle_rounds_per_sec(a, X, y, a.steps, a.warmup)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    threads = host_threads()
+    S = min(a.rows, a.reference_rows)
+    X, y, gen_dev = gen_host_sample(a, S)
+    rps_sample, ingest_s, cores = oracle_rounds_per_sec(a, X, y, a.steps, a.warmup, threads)
     scale = S / a.rows
     value = rps_sample * scale
-    sample = "%d of %d rows (oracle port of the xgboost CPU hist path, OpenMP), rounds/s scaled by %d/%d" % (S, a.rows, S, a.rows)
+    sample = ("first %d of %d rows of the GPU arm's workload (same generator and seed, generated on %s), %d timed rounds after %d warm-up, "
+              "oracle port of the xgboost CPU hist path with %d OpenMP threads; rounds/s scaled linearly in rows (x %d/%d)"
+              % (S, a.rows, gen_dev, a.steps, a.warmup, cores, S, a.rows))
     ingest_full = ingest_s / scale
-    e2e = JOB_ROUNDS / (ingest_full + JOB_ROUNDS / value)
+    e2e = a.job_rounds / (ingest_full + a.job_rounds / value)
     print(json.dumps({
         "impl": "reference", "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic %dx%d %s hist max_bin=%d max_depth=%d" % (a.rows, a.cols, a.objective, a.max_bin, a.max_depth),
-                   "params": params_of(a)},
+                   "params": params_of(a), "sample_rows": S, "sample_ms_per_step": 1000.0 / rps_sample},
         "cpu_baseline": {"value": value, "unit": "rounds/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": e2e, "unit": "rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def model_hash(be, bst):
+    """sha256 over the trained trees (structure, thresholds, leaf values): identical at every GPU count by construction."""
+    import hashlib
+    m = be.booster_export_model(bst.handle)
+    h = hashlib.sha256()
+    for k in ("tree_offset", "tree_info", "left", "right", "split_index", "split_bin", "default_left", "split_cond"):
+        h.update(np.ascontiguousarray(m[k]).tobytes())
+    return h.hexdigest()[:16], int(len(m["tree_info"]))
 
 
 def predict_section(xgb, be, device, peak):
@@ -314,6 +342,7 @@ def main():
     launches = be.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
+    mhash, mtrees = model_hash(be, bst)           # after warm-up + timed rounds: the same trees at every N
     # per-kernel CUDA-event timing of the histogram launches: the timed region above replays a CUDA graph per tree, so the
     # events bracket the same launches issued directly for PROFILE_ROUNDS further rounds right after it (same state, same data)
     be.booster_set_profile(bst.handle, True)
@@ -335,18 +364,18 @@ def main():
     deep_bytes = prof["deep_hist_rows"] * (F + 8 + 4)          # deeper levels also read a 4 B row id per row
     all_gbs = (prof["root_hist_rows"] * (F + 8) + deep_bytes) / ((prof["root_hist_ms"] + prof["deep_hist_ms"]) * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_hist_root_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_hist_root_traffic.json")
     if os.path.exists(tp) and world == 1:
         tj = json.load(open(tp))
         if tj.get("workload") == "synthetic %dx%d" % (a.rows, a.cols):
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # per launch, from the committed ncu capture
-    roofline = {"bound": "hbm", "kernel": "hist_build_kernel (root launch, all rows of the rank)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "hist_root_kernel<G-only> (root launch, all rows of the rank; constant-hessian objective: H plane cached)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": root_bytes, "ms_per_launch": root_ms,
                 "all_hist_launches_gbs": all_gbs, "all_hist_launches_frac": all_gbs / peak,
                 "hist_share_of_step": (prof["root_hist_ms"] + prof["deep_hist_ms"]) / PROFILE_ROUNDS / (ms / a.steps),
                 "timing": "CUDA events around each hist launch over %d rounds run right after the timed region (direct launches; the timed region replays CUDA graphs)" % PROFILE_ROUNDS}
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with host buffers: a whole job, measured
     e2e = None
     if not a.no_e2e:
         del dtrain, bst
@@ -358,35 +387,30 @@ def main():
         barrier()
         t0 = time.perf_counter()
         d2 = xgb.DMatrix(Xn, label=y_host)                       # H2D of the feature matrix happens here
-        b2 = xgb.Booster(params, [d2])
-        b2.update(d2, 0)                                         # first round: cuts + binning + round 0
-        msg = b2.eval_set([(d2, "train")], 0)
         be.synchronize()
-        t_first = time.perf_counter() - t0
+        t_h2d = time.perf_counter() - t0
+        res = {}
+        b2 = xgb.train(params, d2, num_boost_round=a.job_rounds, evals=[(d2, "train")], evals_result=res, verbose_eval=False)
+        be.synchronize()
+        t_job = time.perf_counter() - t0
         barrier()
-        t0 = time.perf_counter()
-        for i in range(1, a.steps + 1):
-            b2.update(d2, i)
-            msg = b2.eval_set([(d2, "train")], i)               # D2H: the metric of the round
-        be.synchronize()
-        t_steps = (time.perf_counter() - t0) / a.steps
-        t_first = max_over_ranks(t_first); t_steps = max_over_ranks(t_steps)
-        ingest = max(0.0, t_first - t_steps)
-        e2e_value = JOB_ROUNDS / (ingest + JOB_ROUNDS * t_steps)
-        e2e = {"value": e2e_value, "unit": "rounds/s", "h2d_bytes_per_step": int(Xn.nbytes + y_host.nbytes) // JOB_ROUNDS,
-               "d2h_bytes_per_step": 16, "ingest_s": ingest, "step_s": t_steps, "job_rounds": JOB_ROUNDS, "last_eval": msg,
-               "note": "DMatrix from pinned host numpy; ingest (H2D + cuts + binning) amortised over a %d-round job" % JOB_ROUNDS}
+        t_job = max_over_ranks(t_job); t_h2d = max_over_ranks(t_h2d)
+        last = list(res["train"].items())[0]
+        e2e = {"value": a.job_rounds / t_job, "unit": "rounds/s", "h2d_bytes_per_step": int(Xn.nbytes + y_host.nbytes) // a.job_rounds,
+               "d2h_bytes_per_step": 16, "job_rounds": a.job_rounds, "job_wall_s": t_job,
+               "ingest": {"h2d_s": t_h2d, "cuts_bin_and_rounds_s": t_job - t_h2d, "est_rounds_s": a.job_rounds * (ms / a.steps) / 1000.0},
+               "last_eval": "[%d]\ttrain-%s:%.17g" % (a.job_rounds - 1, last[0], last[1][-1]),
+               "note": "measured wall clock of xgb.DMatrix(pinned host numpy) + xgb.train(%d rounds, evals=[train]) incl. H2D, cuts, binning and the per-round metric D2H" % a.job_rounds}
         del d2, b2
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         S = min(a.rows, a.cpu_sample_rows)
-        dev_cpu = torch.device("cpu")
-        xs, ys = gen_block_torch(0, min(S, BLOCK), a.cols, a.seed, a.objective, max(a.num_class, 1), device)
-        xs, ys = xs.cpu().numpy(), ys.cpu().numpy()
-        rps, ingest_s, cores = oracle_rounds_per_sec(a, xs, ys, 3, 1)
+        xs, ys, _ = gen_host_sample(a, S)
+        threads = host_threads()
+        rps, ingest_s, cores = oracle_rounds_per_sec(a, xs, ys, 3, 1, threads)
         cpu = {"value": rps * len(xs) / a.rows, "unit": "rounds/s", "cores": cores, "kind": "port",
-               "sample": "first %d of %d rows, 3 timed rounds after 1 warm-up, scaled linearly in rows" % (len(xs), a.rows)}
+               "sample": "first %d of %d rows (same generator and seed), 3 timed rounds after 1 warm-up, %d OpenMP threads, scaled linearly in rows" % (len(xs), a.rows, cores)}
 
     predict = None
     if rank == 0 and world == 1 and not a.no_predict:
@@ -401,8 +425,10 @@ def main():
                        "rows_per_gpu": (a.rows + world - 1) // world, "parallelism": "rows sharded x%d, per-level int64 histogram NCCL all-reduce" % world,
                        "l2": "inputs (%.1f GB of bins per GPU) exceed the 126 MB L2" % ((r1 - r0) * 32 * ((a.cols + 31) // 32) / 1e9),
                        "arithmetic": "f32 gradients rounded to a 2^-k fixed-point grid, int32 shared-memory partial sums, int64 histograms (exact), f64/f32 split gains",
+                       "rounds_timed": "rounds %d..%d of a fresh booster (the rows of the built children shrink from ~50 %% to ~23 %% of N per level over the first rounds)" % (a.warmup, a.warmup + a.steps - 1),
                        "params": params},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "predict": predict,
+            "model_hash": mhash, "model_trees": mtrees,
         }
         print(json.dumps(out))
     if dist is not None:

@@ -518,6 +518,56 @@ static int new_node(OrcModel* m, int64_t base, int parent) {
 /* Grow one tree on gradient column k.  [UPSTREAM src/tree/updater_quantile_hist.cc, src/tree/driver.h,
  * src/tree/hist/histogram.h (subtraction trick, build the child with the smaller hessian sum),
  * src/common/partition_builder.h (stable partition, bin <= split_bin -> left)] */
+/* Stable partition of the row segment [begin, begin + count) by the split (feature f, bin sb, default direction dl):
+ * lefts first, rights after, both in their original order.  [UPSTREAM src/common/partition_builder.h]  Parallel over
+ * row blocks (count, prefix, scatter), so that the CPU baseline scales with the host's cores like upstream's does. */
+static void partition_segment(OrcTrainer* t, int64_t begin, int64_t count, int f, int sb, int dl, int64_t* nl_out) {
+  const int F = t->F;
+  uint32_t* seg = t->ridx + begin; uint32_t* tmp = t->ridx_tmp;
+  int nt = 1;
+#ifdef _OPENMP
+  nt = omp_get_max_threads();
+#endif
+  if (count < 262144) nt = 1; else if ((int64_t)nt > count / 65536) nt = (int)(count / 65536);
+  if (nt <= 1) {
+    int64_t nl = 0, nr = 0;
+    for (int64_t i = 0; i < count; ++i) {
+      uint32_t r = seg[i]; uint8_t b = t->bins[(int64_t)r * F + f];
+      int go_left = (t->has_missing && b == ORC_MISSING_BIN) ? dl : ((int)b <= sb);
+      if (go_left) seg[nl++] = r; else tmp[nr++] = r;
+    }
+    memcpy(seg + nl, tmp, sizeof(uint32_t) * (size_t)nr);
+    *nl_out = nl; return;
+  }
+  int64_t* cntl = (int64_t*)calloc((size_t)nt + 1, sizeof(int64_t));
+  const int64_t blk = (count + nt - 1) / nt;
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int th = 0; th < nt; ++th) {
+    int64_t i0 = th * blk, i1 = i0 + blk < count ? i0 + blk : count, c = 0;
+    for (int64_t i = i0; i < i1; ++i) {
+      uint8_t b = t->bins[(int64_t)seg[i] * F + f];
+      c += (t->has_missing && b == ORC_MISSING_BIN) ? dl : ((int)b <= sb);
+    }
+    cntl[th + 1] = c;
+  }
+  for (int th = 0; th < nt; ++th) cntl[th + 1] += cntl[th];
+  const int64_t nl = cntl[nt];
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+  for (int th = 0; th < nt; ++th) {
+    int64_t i0 = th * blk, i1 = i0 + blk < count ? i0 + blk : count;
+    int64_t ol = cntl[th], orr = nl + (i0 - cntl[th]);
+    for (int64_t i = i0; i < i1; ++i) {
+      uint32_t r = seg[i]; uint8_t b = t->bins[(int64_t)r * F + f];
+      int go_left = (t->has_missing && b == ORC_MISSING_BIN) ? dl : ((int)b <= sb);
+      if (go_left) tmp[ol++] = r; else tmp[orr++] = r;
+    }
+  }
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int64_t i = 0; i < count; ++i) seg[i] = tmp[i];
+  free(cntl);
+  *nl_out = nl;
+}
+
 static void grow_tree(OrcTrainer* t, int k, int tree_index) {
   const OrcParams* p = &t->p;
   const int K = p->num_class > 1 ? p->num_class : 1;
@@ -588,13 +638,8 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
       /* stable partition of the node's row segment */
       int f = c->split.findex, sb = c->split.split_bin, dl = c->split.default_left;
       int64_t nl = 0, nr = 0;
-      for (int64_t i = 0; i < c->count; ++i) {
-        uint32_t r = t->ridx[c->begin + i];
-        uint8_t b = t->bins[(int64_t)r * F + f];
-        int go_left = (t->has_missing && b == ORC_MISSING_BIN) ? dl : ((int)b <= sb);
-        if (go_left) t->ridx[c->begin + nl++] = r; else t->ridx_tmp[nr++] = r;
-      }
-      memcpy(t->ridx + c->begin + nl, t->ridx_tmp, sizeof(uint32_t) * (size_t)nr);
+      partition_segment(t, c->begin, c->count, f, sb, dl, &nl);
+      nr = c->count - nl;
       /* children candidates */
       int child_ok = 1;
       if (p->max_depth > 0 && c->depth + 1 >= p->max_depth) child_ok = 0;
@@ -715,6 +760,13 @@ void orc_predict(const float* X, int64_t n, int32_t F, int32_t K, int32_t n_tree
   }
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

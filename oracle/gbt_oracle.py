@@ -330,3 +330,9 @@ def transform(model, margins):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n):
+    """Explicit OpenMP thread count for every oracle entry point (bench.py sets it: torchrun exports OMP_NUM_THREADS=1)."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()

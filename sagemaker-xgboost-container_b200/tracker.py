@@ -83,6 +83,23 @@ def _recv(sock, limit=MAX_FRAME):
         raise ConnectionError("malformed tracker frame: %s" % e)
 
 
+def _alive(sock):
+    """False once the peer has closed its end (a zero-byte peek); a quiet but open link counts as alive."""
+    try:
+        sock.setblocking(False)
+        try:
+            return sock.recv(1, socket.MSG_PEEK) != b""
+        except (BlockingIOError, InterruptedError):
+            return True
+        except OSError:
+            return False
+    finally:
+        try:
+            sock.setblocking(True)
+        except OSError:
+            pass
+
+
 class RabitTracker:
     def __init__(self, n_workers, host_ip="127.0.0.1", port=0, sortby="host", timeout=0):
         self.n_workers = int(n_workers)
@@ -107,9 +124,9 @@ class RabitTracker:
 
     def _run(self):
         try:
-            by_task = {}                       # task id -> (task id, host, arrival order, socket); a retried worker replaces its old link
+            conns = []                         # (task id, host, arrival order, socket)
             order = 0
-            while len(by_task) < self.n_workers:
+            while len(conns) < self.n_workers:
                 c, addr = self._sock.accept()
                 try:
                     c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
@@ -124,16 +141,20 @@ class RabitTracker:
                     except OSError:
                         pass
                     continue
-                task = hello["task_id"] or "anon-%d" % order
-                old = by_task.pop(task, None)
-                if old is not None:
-                    try:
-                        old[3].close()
-                    except OSError:
-                        pass
-                by_task[task] = (task, addr[0], order, c)
+                task = hello["task_id"]
+                # a worker that retried its CommunicatorContext left a dead link behind: the new one takes its place.  Live
+                # links with the same task id are kept (the container derives the id from hosts.index(host), which repeats
+                # when several workers share a host name, test/unit/test_distributed.py:26).
+                for i, old in enumerate(conns):
+                    if old[0] == task and not _alive(old[3]):
+                        try:
+                            old[3].close()
+                        except OSError:
+                            pass
+                        conns.pop(i)
+                        break
+                conns.append((task, addr[0], order, c))
                 order += 1
-            conns = list(by_task.values())
             if self.sortby == "task":
                 conns.sort(key=lambda t: (t[0], t[2]))
             else:
