@@ -516,7 +516,8 @@ void Booster::upload_model() {
     const HostTree& h = trees_[t];
     const int nn = h.num_nodes();
     std::vector<DevNode> nodes(nn);
-    for (int i = 0; i < nn; ++i) { nodes[i].cond = h.split_cond[i]; nodes[i].left = h.left[i]; nodes[i].right = h.right[i]; nodes[i].fidx_dl = (unsigned)h.split_index[i] | ((unsigned)h.default_left[i] << 31); }
+    for (int i = 0; i < nn; ++i) { nodes[i].cond = h.split_cond[i]; nodes[i].left = h.left[i]; nodes[i].right = h.right[i]; nodes[i].fidx_dl = (unsigned)h.split_index[i] | ((unsigned)h.default_left[i] << 31);
+      if (h.left[i] >= 0 && h.right[i] != h.left[i] + 1) children_adjacent_ = false; }     // foreign model: the tiled predictor assumes sibling pairs
     if (d_nodes_used + nn > d_nodes.n) {
       size_t cap = std::max<size_t>(d_nodes.n * 2, d_nodes_used + nn + 4096);
       DevBuf<DevNode> nb; nb.alloc(cap);
@@ -563,6 +564,7 @@ void Booster::bring_cache_up_to_date(DMatrix* dm, PredCache& c) {
     upload_model();
     PredictArgs pa{}; pa.X = dm->X.p; pa.n = dm->n; pa.F = dm->F; pa.nodes = d_nodes.p; pa.tree_offset = d_tree_offset.p; pa.tree_info = d_tree_info.p;
     pa.tree_begin = c.trees_applied; pa.tree_end = nt; pa.K = K; pa.margin = c.margin.p; pa.leaf = nullptr;
+    pa.h_tree_offset = h_tree_offset.data(); pa.has_nan = dm->has_missing ? 1 : 0; pa.children_adjacent = children_adjacent_ ? 1 : 0;
     launch_predict(pa, s);
     c.trees_applied = nt;
   }
@@ -888,6 +890,7 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
   const int64_t n = dm->n;
   PredictArgs pa{}; pa.X = dm->X.p; pa.n = n; pa.F = dm->F; pa.nodes = d_nodes.p; pa.tree_offset = d_tree_offset.p; pa.tree_info = d_tree_info.p;
   pa.tree_begin = tb; pa.tree_end = te; pa.K = K;
+  pa.h_tree_offset = h_tree_offset.data(); pa.has_nan = dm->has_missing ? 1 : 0; pa.children_adjacent = children_adjacent_ ? 1 : 0;
   if (type == 6) {
     const int nt = te - tb;
     DevBuf<int> leaf; leaf.alloc((size_t)n * std::max(nt, 1));

@@ -125,6 +125,7 @@ class Booster {
   std::map<uint64_t, PredCache> caches_;
   struct GrowerImpl* grower_ = nullptr;
   bool labels_checked_ = false;
+  bool children_adjacent_ = true;               // every tree on the device has right child == left child + 1
   bool profile_ = false;
   struct ProfEvent { cudaEvent_t a, b; int level; };
   std::vector<ProfEvent> prof_events_;

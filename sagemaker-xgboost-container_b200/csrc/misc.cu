@@ -2,6 +2,9 @@
 // SURVEY.md section 8a rows A5, A5b, A6 (binning half), A11, A12.  Formulas restate upstream xgboost
 // (src/objective/regression_loss.h, multiclass_obj.cu, src/data/gradient_index.cc, src/predictor/cpu_predictor.cc,
 // src/metric/elementwise_metric.cu, multiclass_metric.cu) as written down in oracle/gbt_oracle.c.
+#include <algorithm>
+#include <cstdlib>
+#include <utility>
 #include "engine.h"
 #include "misc.h"
 
@@ -169,6 +172,70 @@ __global__ void __launch_bounds__(256) predict_kernel(PredictArgs a) {
   if (a.K == 1 && a.margin) a.margin[r] = acc;
 }
 
+// Block-cooperative predictor (BASELINE config 5): a CTA stages a tile of rows into shared memory with coalesced loads
+// (the thread-per-row kernel above gathers 4 B at a time from a 4*F-byte row: 1 % of HBM peak in round 1) and keeps the
+// trees there too, 8 B per node, so a traversal step is two LDS.  With T trees of depth D a row costs ~8*T*D instructions
+// against 4*F bytes: beyond T*D ~ 100 the kernel is issue-bound, not HBM-bound (DESIGN.md "predictor").
+struct PNode { float cond; unsigned w; };            // w = left child (16 bit, 0xffff = leaf) | feature << 16 | default_left << 31
+
+template <bool HAS_NAN, bool LEAF_OUT>
+__global__ void __launch_bounds__(1024) predict_tiled_kernel(PredictArgs a, int tree_lo, int tree_hi, int pitch, int rows_per_tile, int64_t num_tiles) {
+  extern __shared__ __align__(16) unsigned char psm[];
+  const int nt_chunk = tree_hi - tree_lo;
+  int* s_toff = reinterpret_cast<int*>(psm);                                   // [nt_chunk + 1] node offsets inside s_nodes
+  PNode* s_nodes = reinterpret_cast<PNode*>(psm + (((size_t)(nt_chunk + 1) * 4 + 15) & ~(size_t)15));
+  __shared__ int s_total;
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int t = 0; t < nt_chunk; ++t) { s_toff[t] = off; off += (int)(a.tree_offset[tree_lo + t + 1] - a.tree_offset[tree_lo + t]); }
+    s_toff[nt_chunk] = off; s_total = off;
+  }
+  __syncthreads();
+  for (int t = 0; t < nt_chunk; ++t) {
+    const DevNode* src = a.nodes + a.tree_offset[tree_lo + t];
+    const int cnt = s_toff[t + 1] - s_toff[t];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const DevNode d = src[i];
+      PNode p; p.cond = d.cond;
+      p.w = (d.left < 0 ? 0xffffu : (unsigned)d.left) | ((d.fidx_dl & 0x7fffu) << 16) | (d.fidx_dl & 0x80000000u);
+      s_nodes[s_toff[t] + i] = p;
+    }
+  }
+  float* s_x = reinterpret_cast<float*>(s_nodes + s_total);
+  const int F = a.F, K = a.K, nt_all = a.tree_end - a.tree_begin;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * rows_per_tile;
+    const int rows = (int)((a.n - r0 < rows_per_tile) ? a.n - r0 : rows_per_tile);
+    __syncthreads();                                                            // trees staged / previous tile consumed
+    const float* src = a.X + r0 * F;
+    const int total = rows * F;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) { const int r = i / F, f = i - r * F; s_x[r * pitch + f] = __ldg(src + i); }
+    __syncthreads();
+    for (int rl = threadIdx.x; rl < rows; rl += blockDim.x) {
+      const float* x = s_x + rl * pitch;
+      const int64_t r = r0 + rl;
+      float acc = (!LEAF_OUT && K == 1) ? a.margin[r] : 0.f;
+      for (int t = 0; t < nt_chunk; ++t) {
+        const PNode* tn = s_nodes + s_toff[t];
+        int nid = 0;
+        PNode nd = tn[0];
+        while ((nd.w & 0xffffu) != 0xffffu) {
+          const float v = x[(nd.w >> 16) & 0x7fffu];
+          const int left = (int)(nd.w & 0xffffu);
+          bool go_left = v < nd.cond;
+          if (HAS_NAN) { if (isnan(v)) go_left = (nd.w >> 31) != 0; }
+          nid = go_left ? left : left + 1;                                      // children are allocated as adjacent pairs
+          nd = tn[nid];
+        }
+        if (LEAF_OUT) a.leaf[r * nt_all + (tree_lo - a.tree_begin) + t] = nid;
+        else if (K == 1) acc += nd.cond;
+        else a.margin[r * K + a.tree_info[tree_lo + t]] += nd.cond;
+      }
+      if (!LEAF_OUT && K == 1) a.margin[r] = acc;
+    }
+  }
+}
+
 // margins -> predictions (PredTransform), in place
 __global__ void __launch_bounds__(256) transform_kernel(float* m, int64_t n, int K, int objective, float* out_class) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,8 +334,59 @@ void launch_replace_missing(float* X, int64_t count, float missing, cudaStream_t
   if (count == 0) return;
   replace_missing_kernel<<<grid_for(count), 256, 0, s>>>(X, count, missing); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
+// host-side plan of the tiled predictor: trees are cut into chunks that fit in shared memory next to a row tile
 void launch_predict(const PredictArgs& a, cudaStream_t s) {
   if (a.n == 0 || a.tree_end <= a.tree_begin) return;
+  static const bool legacy = getenv("B200XGB_PREDICT_LEGACY") != nullptr;
+  const bool ok = !legacy && a.h_tree_offset != nullptr && a.F <= 32767 && a.children_adjacent;
+  const int pitch = a.F | 1;                                       // odd pitch: threads of a warp (rows) hit different banks for the same feature
+  const size_t kSmem = 220 * 1024;
+  if (ok && (size_t)pitch * 4 * 32 + 64 * 1024 <= kSmem) {
+    static bool attr = false;
+    if (!attr) {
+      CUDA_OK(cudaFuncSetAttribute(predict_tiled_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      CUDA_OK(cudaFuncSetAttribute(predict_tiled_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      CUDA_OK(cudaFuncSetAttribute(predict_tiled_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      CUDA_OK(cudaFuncSetAttribute(predict_tiled_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      attr = true;
+    }
+    const size_t node_budget = 96 * 1024;                          // bytes of packed nodes per chunk
+    int lo = a.tree_begin;
+    bool fits = true;
+    std::vector<std::pair<int, int>> chunks;
+    while (lo < a.tree_end) {
+      int hi = lo; size_t bytes = 0;
+      while (hi < a.tree_end) {
+        const int64_t nn = a.h_tree_offset[hi + 1] - a.h_tree_offset[hi];
+        if (nn > 65534) { fits = false; break; }
+        if (bytes + (size_t)nn * 8 > node_budget && hi > lo) break;
+        if ((size_t)nn * 8 > node_budget) { fits = false; break; }
+        bytes += (size_t)nn * 8; ++hi;
+      }
+      if (!fits) break;
+      chunks.emplace_back(lo, hi); lo = hi;
+    }
+    if (fits) {
+      for (auto& ch : chunks) {
+        size_t node_bytes = 0;
+        for (int t = ch.first; t < ch.second; ++t) node_bytes += (size_t)(a.h_tree_offset[t + 1] - a.h_tree_offset[t]) * 8;
+        const size_t head = (((size_t)(ch.second - ch.first + 1) * 4 + 15) & ~(size_t)15) + node_bytes;
+        int rows = (int)((kSmem - head) / ((size_t)pitch * 4));
+        rows = rows > 1024 ? 1024 : (rows / 32) * 32;
+        const int threads = rows >= 1024 ? 1024 : (rows >= 512 ? 512 : 256);
+        if (rows > threads) rows = threads;                        // one row per thread and tile
+        const int64_t tiles = (a.n + rows - 1) / rows;
+        const int grid = (int)std::min<int64_t>(tiles, 148 * (threads == 1024 ? 1 : 2048 / threads));
+        const size_t smem = head + (size_t)rows * pitch * 4;
+        if (a.leaf) { if (a.has_nan) predict_tiled_kernel<true, true><<<grid, threads, smem, s>>>(a, ch.first, ch.second, pitch, rows, tiles);
+                      else predict_tiled_kernel<false, true><<<grid, threads, smem, s>>>(a, ch.first, ch.second, pitch, rows, tiles); }
+        else { if (a.has_nan) predict_tiled_kernel<true, false><<<grid, threads, smem, s>>>(a, ch.first, ch.second, pitch, rows, tiles);
+               else predict_tiled_kernel<false, false><<<grid, threads, smem, s>>>(a, ch.first, ch.second, pitch, rows, tiles); }
+        ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+      }
+      return;
+    }
+  }
   predict_kernel<<<(unsigned)((a.n + 255) / 256), 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_transform(float* m, int64_t n, int K, int objective, float* out_class, cudaStream_t s) {

@@ -25,6 +25,9 @@ struct PredictArgs {
   int tree_begin, tree_end, K;
   float* margin;            // n x K, pre-initialised with the base margin; may be nullptr
   int* leaf;                // n x (tree_end - tree_begin); may be nullptr
+  const int64_t* h_tree_offset;   // host copy of tree_offset (plans the shared-memory tree chunks); nullptr = thread-per-row kernel
+  int has_nan;              // the matrix contains missing values
+  int children_adjacent;    // right child == left child + 1 in every tree (true for every tree this engine trains)
 };
 
 enum Metric : int { kMetricRmse = 0, kMetricMae = 1, kMetricLogloss = 2, kMetricError = 3, kMetricMerror = 4, kMetricMlogloss = 5,

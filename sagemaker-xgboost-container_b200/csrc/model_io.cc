@@ -81,7 +81,7 @@ JPtr Booster::model_to_json() {
 void Booster::reset_model() {
   sync_model();
   trees_.clear(); tree_info_.clear(); pending_.clear(); on_device_.clear(); h_tree_offset.clear();
-  d_nodes_used = 0; d_trees_uploaded = 0; caches_.clear(); ++model_version_;
+  d_nodes_used = 0; d_trees_uploaded = 0; caches_.clear(); ++model_version_; children_adjacent_ = true;
 }
 
 template <typename T, typename F> static std::vector<T> num_vec(const JValue& a, F conv) {
