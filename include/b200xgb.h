@@ -112,6 +112,14 @@ XGB_DLL int XGCommunicatorGetUniqueId(const char** out_hex);
 XGB_DLL int XGB200DMatrixGetCuts(DMatrixHandle handle, int max_bin, bst_ulong* n_ptrs, const int** ptrs, bst_ulong* n_vals,
                          const float** vals, const float** mins, int* has_missing);
 XGB_DLL int XGB200DMatrixSetCuts(DMatrixHandle handle, const int* ptrs, bst_ulong n_ptrs, const float* vals, const float* mins);
+/* Serving input path: a CSV request body parsed on the device into the DMatrix.  Replaces the Python
+ * split + np.array(...).astype(float) of encoder.csv_to_dmatrix (encoder.py:35-52, reached from serve_utils.py:121-131).
+ * `text` is the stripped payload ('\n' between rows, `delimiter` between fields, empty field = NaN).  *status: 0 = parsed,
+ * 1 = rows of different lengths, 2 = a field the exact device fast path cannot decide (caller parses on the host);
+ * *out is NULL unless *status == 0. */
+XGB_DLL int XGB200DMatrixCreateFromCSV(const char* text, bst_ulong len, char delimiter, int* status, DMatrixHandle* out);
+/* the float32 feature matrix as the engine holds it (row-major n x F, NaN = missing), for bit-exact checks of the input paths */
+XGB_DLL int XGB200DMatrixGetRaw(DMatrixHandle handle, float* out_row_major);
 /* binned feature blocks back on the host in plain row-major n x F order (for bit-exact checks of the binning kernel) */
 XGB_DLL int XGB200DMatrixGetBins(DMatrixHandle handle, int max_bin, uint8_t* out_row_major);
 /* flat tree arrays of the model; any pointer may be NULL. tree_offset has num_trees+1 entries. */
@@ -130,6 +138,8 @@ XGB_DLL int XGB200BuildRootHistogram(BoosterHandle handle, DMatrixHandle dmat, c
 XGB_DLL int XGB200BuildHistogramEx(BoosterHandle handle, DMatrixHandle dmat, const float* gpair, int repeats, int mode,
                              const unsigned* row_ids, bst_ulong n_ids, int64_t* out_hist, float* scales, float* out_ms,
                              const char** out_kernel);
+/* mean device time (CUDA events) of the predictor kernel alone over `repeats` launches on `dmat` */
+XGB_DLL int XGB200BoosterPredictKernelMs(BoosterHandle handle, DMatrixHandle dmat, int repeats, float* out_ms);
 /* raw margins of the prediction cache the trainer keeps for `dmat` (n x num_class), brought up to date first */
 XGB_DLL int XGB200BoosterGetCachedMargin(BoosterHandle handle, DMatrixHandle dmat, float* out);
 /* CUDA-event stopwatch on the engine's stream: Start records an event, Stop records another, waits, returns ms */

@@ -90,6 +90,22 @@ class CudaBackend:
         self._check(self.lib.XGDMatrixCreateFromCudaArrayInterface(_cstr(json.dumps(iface)), _cstr(json.dumps(cfg)), C.byref(h)))
         return h
 
+    def dmatrix_get_raw(self, h):
+        n, F = self.dmatrix_num_row(h), self.dmatrix_num_col(h)
+        out = np.empty(n * F, np.float32)
+        self._check(self.lib.XGB200DMatrixGetRaw(h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def dmatrix_from_csv(self, payload, delimiter=","):
+        """Device-side CSV parse (csv.cu).  Returns (handle, status); handle is None unless status == 0."""
+        if isinstance(payload, str):
+            payload = payload.encode("utf-8")
+        h = C.c_void_p()
+        st = C.c_int(0)
+        self._check(self.lib.XGB200DMatrixCreateFromCSV(C.c_char_p(payload), C.c_ulong(len(payload)), C.c_char(delimiter.encode("ascii")),
+                                                        C.byref(st), C.byref(h)))
+        return (h if st.value == 0 else None), int(st.value)
+
     def dmatrix_free(self, h):
         self._check(self.lib.XGDMatrixFree(h))
 
@@ -325,6 +341,11 @@ class CudaBackend:
                                                     C.c_ulong(n_ids), hist.ctypes.data_as(C.POINTER(C.c_int64)),
                                                     scales.ctypes.data_as(C.POINTER(C.c_float)), C.byref(ms), C.byref(name)))
         return hist, scales, float(ms.value), (name.value or b"").decode()
+
+    def booster_predict_kernel_ms(self, bh, dh, repeats=5):
+        ms = C.c_float()
+        self._check(self.lib.XGB200BoosterPredictKernelMs(bh, dh, C.c_int(repeats), C.byref(ms)))
+        return float(ms.value)
 
     def booster_cached_margin(self, bh, dh, K):
         n = self.dmatrix_num_row(dh)

@@ -893,7 +893,7 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
   pa.h_tree_offset = h_tree_offset.data(); pa.has_nan = dm->has_missing ? 1 : 0; pa.children_adjacent = children_adjacent_ ? 1 : 0;
   if (type == 6) {
     const int nt = te - tb;
-    DevBuf<int> leaf; leaf.alloc((size_t)n * std::max(nt, 1));
+    DevBuf<int>& leaf = pred_leaf_; leaf.ensure((size_t)n * std::max(nt, 1));
     pa.margin = nullptr; pa.leaf = leaf.p;
     launch_predict(pa, s);
     std::vector<int> h((size_t)n * nt);
@@ -904,7 +904,7 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
     shape->assign({(uint64_t)n, (uint64_t)nt});
     return;
   }
-  DevBuf<float> margin; margin.alloc((size_t)n * K);
+  DevBuf<float>& margin = pred_margin_; margin.ensure((size_t)n * K);          // scratch kept across calls: no cudaMalloc / cudaFree per request
   if (!dm->base_margin.empty()) {
     B200_CHECK(dm->base_margin.size() == (size_t)n * K, "base_margin size does not match rows x groups");
     CUDA_OK(cudaMemcpyAsync(margin.p, dm->d_base_margin.p, sizeof(float) * n * K, cudaMemcpyDeviceToDevice, s));
@@ -912,9 +912,9 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
   pa.margin = margin.p; pa.leaf = nullptr;
   launch_predict(pa, s);
   int out_cols = K;
-  DevBuf<float> cls;
+  DevBuf<float>& cls = pred_cls_;
   if (type == 0) {
-    if (param_.objective == kSoftmax) { cls.alloc(n); launch_transform(margin.p, n, K, param_.objective, cls.p, s); out_cols = 1; }
+    if (param_.objective == kSoftmax) { cls.ensure(n); launch_transform(margin.p, n, K, param_.objective, cls.p, s); out_cols = 1; }
     else launch_transform(margin.p, n, K, param_.objective, nullptr, s);
   }
   out->resize((size_t)n * out_cols);
@@ -970,6 +970,30 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   CUDA_OK(cudaMemcpyAsync(scales_out, g.gs.scales, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
   Comm::get().sync_stream(s);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+// device time of the predictor kernel alone (margins of all trees into the scratch buffer), for the roofline line of bench.py
+float Booster::debug_predict_kernel_ms(DMatrix* dm, int repeats) {
+  configure();
+  cudaStream_t s = engine_stream();
+  upload_model();
+  const int K = param_.num_class;
+  pred_margin_.ensure((size_t)dm->n * K);
+  PredictArgs pa{}; pa.X = dm->X.p; pa.n = dm->n; pa.F = dm->F; pa.nodes = d_nodes.p; pa.tree_offset = d_tree_offset.p; pa.tree_info = d_tree_info.p;
+  pa.tree_begin = 0; pa.tree_end = (int)trees_.size(); pa.K = K; pa.margin = pred_margin_.p; pa.leaf = nullptr;
+  pa.h_tree_offset = h_tree_offset.data(); pa.has_nan = dm->has_missing ? 1 : 0; pa.children_adjacent = children_adjacent_ ? 1 : 0;
+  cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  float total = 0.f;
+  for (int r = 0; r < std::max(1, repeats); ++r) {
+    launch_fill(pred_margin_.p, dm->n * K, base_margin(), s);
+    CUDA_OK(cudaEventRecord(e0, s));
+    launch_predict(pa, s);
+    CUDA_OK(cudaEventRecord(e1, s));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, e0, e1)); total += ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return total / std::max(1, repeats);
 }
 
 void Booster::cached_margin(DMatrix* dm, std::vector<float>* out) {

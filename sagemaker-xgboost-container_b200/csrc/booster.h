@@ -35,6 +35,8 @@ class DMatrix {
   DMatrix();
   static std::unique_ptr<DMatrix> from_dense(const float* data, int64_t nrow, int ncol, float missing);
   static std::unique_ptr<DMatrix> from_device(const float* dptr, int64_t nrow, int ncol, float missing);
+  // serving path: CSV text parsed on the device (csv.cu); status 0 ok, 1 ragged rows, 2 needs the host parser
+  static std::unique_ptr<DMatrix> from_csv_text(const char* text, int64_t len, char delim, int* status);
   static std::unique_ptr<DMatrix> from_csr(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr, size_t nelem, size_t ncol);
   std::unique_ptr<DMatrix> slice(const int* idx, int64_t len) const;
   void set_float_info(const std::string& field, const float* v, size_t len);
@@ -43,8 +45,8 @@ class DMatrix {
   void set_cuts(const HostCuts& c);                   // external cuts (shared with the oracle in tests)
   BinnedMatrix binned_view() const { BinnedMatrix b; b.bins = bins.p; b.bins_tail = tw ? bins_tail.p : nullptr; b.bins_col = bins_col.p; b.n = n; b.F = F;
     b.ngroups = ngroups; b.tw = tw; b.ntail = ntail; b.has_missing = has_missing; return b; }
- private:
   void finish_upload(float missing);
+ private:
   void bin_with_cuts();
 };
 
@@ -93,6 +95,7 @@ class Booster {
   // introspection used by tests/bench (build-specific C-ABI entry points)
   void sync_model();                              // materialise pending trees on the host
   void cached_margin(DMatrix* dm, std::vector<float>* out);   // the trainer's prediction cache for dm
+  float debug_predict_kernel_ms(DMatrix* dm, int repeats);
   const std::vector<HostTree>& trees() { sync_model(); return trees_; }
   const std::vector<int>& tree_info() const { return tree_info_; }
   float base_score() const { return base_score_; }
@@ -125,6 +128,7 @@ class Booster {
   std::map<uint64_t, PredCache> caches_;
   struct GrowerImpl* grower_ = nullptr;
   bool labels_checked_ = false;
+  DevBuf<float> pred_margin_, pred_cls_; DevBuf<int> pred_leaf_;      // predict() scratch, grown on demand
   bool children_adjacent_ = true;               // every tree on the device has right child == left child + 1
   bool profile_ = false;
   struct ProfEvent { cudaEvent_t a, b; int level; };

@@ -312,6 +312,21 @@ static void hist_to_feature_major(const DMatrix* dm, const std::vector<long long
     }
   }
 }
+int XGB200DMatrixGetRaw(DMatrixHandle handle, float* out_row_major) {
+  API_BEGIN();
+  DMatrix* dm = DM(handle);
+  if (dm->n * dm->F > 0) CUDA_OK(cudaMemcpy(out_row_major, dm->X.p, sizeof(float) * (size_t)dm->n * dm->F, cudaMemcpyDeviceToHost));
+  API_END();
+}
+int XGB200DMatrixCreateFromCSV(const char* text, bst_ulong len, char delimiter, int* status, DMatrixHandle* out) {
+  API_BEGIN();
+  int st = 0;
+  auto dm = DMatrix::from_csv_text(text, (int64_t)len, delimiter, &st);
+  if (status) *status = st;
+  *out = nullptr;
+  if (st == 0) { auto box = new DMatrixBox(); box->dm = std::move(dm); *out = box; }
+  API_END();
+}
 int XGB200BuildRootHistogram(BoosterHandle handle, DMatrixHandle dmat, const float* gpair, int repeats, int64_t* out_hist, float* scales, float* out_ms) {
   API_BEGIN();
   DMatrix* dm = DM(dmat);
@@ -330,6 +345,11 @@ int XGB200BuildHistogramEx(BoosterHandle handle, DMatrixHandle dmat, const float
   hist_to_feature_major(dm, h, out_hist);
   if (scales) memcpy(scales, sc, sizeof sc);
   if (out_kernel) *out_kernel = hist_last_kernel();
+  API_END();
+}
+int XGB200BoosterPredictKernelMs(BoosterHandle handle, DMatrixHandle dmat, int repeats, float* out_ms) {
+  API_BEGIN();
+  *out_ms = BST(handle)->debug_predict_kernel_ms(DM(dmat), repeats);
   API_END();
 }
 int XGB200BoosterGetCachedMargin(BoosterHandle handle, DMatrixHandle dmat, float* out) {

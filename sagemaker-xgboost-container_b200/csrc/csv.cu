@@ -1,0 +1,139 @@
+// csv.cu -- device-side CSV -> float32 matrix for the serving path.
+// Replaces the Python split + np.array(...).astype(float) of the container's encoder.csv_to_dmatrix (encoder.py:31-52),
+// reached from algorithm_mode/serve_utils.py:121-131 (parse_content_data) for every text/csv invocation request.
+//
+// Semantics kept from that code path: rows are separated by '\n' (payload already stripped of leading/trailing
+// whitespace), fields by one delimiter character, an empty field is NaN, every row must have the same number of
+// fields, a field is what Python's float() accepts (decimal, exponent, inf/nan in any case).  Values take the same two
+// roundings: text -> nearest double (Clinger's exact fast path: <= 19 significant digits below 2^53 and |exp10| <= 22,
+// one IEEE multiply or divide) -> nearest float32 (what xgb.DMatrix does with a float64 array).  A field outside the fast
+// path (or malformed) raises a flag and the caller falls back to the host parser, so results never differ.
+//
+// Kernels: (1) newline positions (flag + CUB select), (2) one thread per row walks its fields.  Text is read once from
+// HBM (L1-cached byte loads; rows are short and contiguous per thread).
+#include <cub/cub.cuh>
+#include <cstring>
+#include "booster.h"
+
+namespace b200 {
+
+struct IsNewline {
+  const char* text;
+  __host__ __device__ bool operator()(const int64_t& i) const { return text[i] == '\n'; }
+};
+
+__device__ __forceinline__ bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r'; }
+
+__device__ __forceinline__ char lower(char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + 32) : c; }
+
+// parse [p, e) as a Python-float literal; returns false when the token is malformed or needs the slow path
+__device__ bool parse_field(const char* p, const char* e, float* out) {
+  while (p < e && is_space(*p)) ++p;
+  while (e > p && is_space(e[-1])) --e;
+  if (p == e) { *out = __int_as_float(0x7fc00000); return true; }                 // empty field -> NaN (encoder.py:31-32)
+  bool neg = false;
+  if (*p == '+' || *p == '-') { neg = *p == '-'; ++p; if (p == e) return false; }
+  const int len = (int)(e - p);
+  if (len == 3 && lower(p[0]) == 'n' && lower(p[1]) == 'a' && lower(p[2]) == 'n') { *out = __int_as_float(0x7fc00000); return true; }
+  if ((len == 3 && lower(p[0]) == 'i' && lower(p[1]) == 'n' && lower(p[2]) == 'f') ||
+      (len == 8 && lower(p[0]) == 'i' && lower(p[1]) == 'n' && lower(p[2]) == 'f' && lower(p[3]) == 'i' && lower(p[4]) == 'n' && lower(p[5]) == 'i' &&
+       lower(p[6]) == 't' && lower(p[7]) == 'y')) { *out = neg ? __int_as_float(0xff800000) : __int_as_float(0x7f800000); return true; }
+  unsigned long long mant = 0; int digits = 0, sig = 0, exp10 = 0; bool any = false, dropped = false;
+  while (p < e && *p >= '0' && *p <= '9') {
+    any = true;
+    if (sig < 19) { mant = mant * 10ull + (unsigned)(*p - '0'); if (mant != 0) ++sig; } else { ++exp10; if (*p != '0') dropped = true; }
+    ++p; ++digits;
+  }
+  if (p < e && *p == '.') {
+    ++p;
+    while (p < e && *p >= '0' && *p <= '9') {
+      any = true;
+      if (sig < 19) { mant = mant * 10ull + (unsigned)(*p - '0'); if (mant != 0) ++sig; --exp10; } else if (*p != '0') dropped = true;
+      ++p;
+    }
+  }
+  if (!any) return false;
+  if (p < e && (*p == 'e' || *p == 'E')) {
+    ++p; bool eneg = false;
+    if (p < e && (*p == '+' || *p == '-')) { eneg = *p == '-'; ++p; }
+    if (p == e) return false;
+    int ev = 0;
+    while (p < e && *p >= '0' && *p <= '9') { if (ev < 100000) ev = ev * 10 + (*p - '0'); ++p; }
+    exp10 += eneg ? -ev : ev;
+  }
+  if (p != e) return false;                                                       // trailing junk (Python's float() would raise)
+  if (mant == 0) { *out = neg ? -0.0f : 0.0f; return true; }
+  if (dropped || mant >= (1ull << 53) || exp10 > 22 || exp10 < -22) return false;   // outside the exact fast path: host parser decides
+  const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  double d = (double)mant;                                                        // exact: mant < 2^53
+  d = exp10 >= 0 ? d * p10[exp10] : d / p10[-exp10];                              // one correctly rounded IEEE operation
+  *out = (float)(neg ? -d : d);
+  return true;
+}
+
+// one thread per row: row r covers [start, end) where start = r ? nl[r-1] + 1 : 0 and end = r < n-1 ? nl[r] : len
+__global__ void __launch_bounds__(256) csv_parse_kernel(const char* text, int64_t len, const int64_t* nl, int64_t n, int F, char delim, float* out, int* err) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const char* p = text + (r ? nl[r - 1] + 1 : 0);
+  const char* e = text + (r < n - 1 ? nl[r] : len);
+  float* o = out + r * F;
+  int f = 0;
+  const char* tok = p;
+  for (const char* q = p;; ++q) {
+    if (q == e || *q == delim) {
+      if (f < F) { float v; if (!parse_field(tok, q, &v)) { atomicMax(err, 2); v = 0.f; } o[f] = v; }
+      ++f; tok = q + 1;
+      if (q == e) break;
+    }
+  }
+  if (f != F) atomicMax(err, 1);                                                   // ragged row
+}
+
+// returns 0 = ok, 1 = ragged rows, 2 = a field outside the exact fast path / malformed (caller falls back to the host parser)
+int parse_csv_device(const char* h_text, int64_t len, char delim, int F, int64_t* n_rows_out, DevBuf<float>* X, cudaStream_t s) {
+  DevBuf<char> d_text; d_text.alloc((size_t)len + 1);
+  CUDA_OK(cudaMemcpyAsync(d_text.p, h_text, (size_t)len, cudaMemcpyHostToDevice, s));
+  // newline positions
+  DevBuf<int64_t> d_nl; d_nl.alloc((size_t)len / 2 + 2);                           // a row has at least one char + '\n' unless empty; bounded below
+  DevBuf<int64_t> d_cnt; d_cnt.alloc(1);
+  cub::CountingInputIterator<int64_t> idx(0);
+  IsNewline pred{d_text.p};
+  size_t tmp_bytes = 0;
+  // upper bound on newlines is len; allocate exactly after counting with a first select into a null output is not possible, so size for len
+  d_nl.alloc((size_t)len + 1);
+  CUDA_OK(cub::DeviceSelect::If(nullptr, tmp_bytes, idx, d_nl.p, d_cnt.p, len, pred, s));
+  DevBuf<unsigned char> tmp; tmp.alloc(tmp_bytes);
+  CUDA_OK(cub::DeviceSelect::If(tmp.p, tmp_bytes, idx, d_nl.p, d_cnt.p, len, pred, s));
+  ++g_kernel_launches;
+  int64_t nnl = 0;
+  CUDA_OK(cudaMemcpyAsync(&nnl, d_cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  const int64_t n = nnl + 1;
+  *n_rows_out = n;
+  X->alloc((size_t)n * F);
+  DevBuf<int> d_err; d_err.alloc(1); d_err.zero(s);
+  csv_parse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_text.p, len, d_nl.p, n, F, delim, X->p, d_err.p); ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
+  int err = 0;
+  CUDA_OK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return err;
+}
+
+std::unique_ptr<DMatrix> DMatrix::from_csv_text(const char* text, int64_t len, char delim, int* status) {
+  // columns from the first line (the container sniffs the delimiter there too, encoder.py:46-48)
+  int F = 1;
+  for (int64_t i = 0; i < len && text[i] != '\n'; ++i) if (text[i] == delim) ++F;
+  auto dm = std::make_unique<DMatrix>();
+  cudaStream_t s = engine_stream();
+  int64_t n = 0;
+  *status = parse_csv_device(text, len, delim, F, &n, &dm->X, s);
+  if (*status != 0) return nullptr;
+  B200_CHECK(n < (int64_t)0x7fffffff, "DMatrix: more than 2^31-1 rows per GPU are not supported");
+  dm->n = n; dm->F = F;
+  dm->finish_upload(std::nanf(""));
+  return dm;
+}
+
+}  // namespace b200

@@ -1,0 +1,76 @@
+"""Serving input path of the container on the device (BASELINE config 5).
+
+Mirrors, with the same names / arguments / error behaviour, the two reference functions a `text/csv` invocation goes through:
+
+    encoder.csv_to_dmatrix(input, dtype=None)                              encoder.py:35-52
+    serve_utils.predict(model, model_format, dtest, input_content_type,   algorithm_mode/serve_utils.py:200-262
+                        objective=None)
+
+`csv_to_dmatrix` hands the request body to the engine, which parses it on the GPU straight into the DMatrix
+(XGB200DMatrixCreateFromCSV, csrc/csv.cu) instead of `str.split` + `np.array(...).astype(float)` on the host; bodies the exact
+device fast path cannot decide (e.g. 30-digit literals) take the reference's own host route, so values never differ.
+`predict` is the container's single-model / ensemble logic over `Booster.predict`.  INTEGRATION.md shows the two-line change
+in encoder.py that routes the container through this module.
+"""
+import csv
+import logging
+
+import numpy as np
+
+from .backend import XGBoostError, get_backend
+from .core import Booster, DMatrix
+
+MULTI_SOFTMAX = "multi:softmax"        # constants/xgb_constants.py
+BINARY_HINGE = "binary:hinge"
+
+
+def _sniff_delimiter(first_line):
+    sniffed = csv.Sniffer().sniff(first_line[:512]).delimiter          # encoder.py:46-47
+    return "," if sniffed.isalnum() else sniffed
+
+
+def _host_csv_to_array(csv_string, delimiter, dtype):
+    """The reference's own route (encoder.py:31-32,50)."""
+    rows = [["nan" if x == "" else x for x in line.split(delimiter)] for line in csv_string.split("\n")]
+    return np.array(rows).astype(dtype)
+
+
+def csv_to_dmatrix(input, dtype=None):
+    """Convert a CSV object (str, or bytes encoded as UTF-8, already stripped of leading / trailing newlines) to a DMatrix."""
+    raw = input if isinstance(input, bytes) else input.encode("utf-8")
+    first = raw.split(b"\n", 1)[0].decode("utf-8")
+    delimiter = _sniff_delimiter(first)
+    logging.info("Determined delimiter of CSV input is '{}'".format(delimiter))
+    be = get_backend()
+    if len(delimiter) == 1 and ord(delimiter) < 128 and hasattr(be, "dmatrix_from_csv"):
+        handle, status = be.dmatrix_from_csv(raw, delimiter)
+        if status == 0:
+            return DMatrix._from_handle(handle)
+        if status == 1:          # numpy raises on ragged rows as well (inhomogeneous shape)
+            raise ValueError("setting an array element with a sequence. The requested array has an inhomogeneous shape: rows of the CSV payload have different numbers of fields")
+    return DMatrix(_host_csv_to_array(raw.decode("utf-8"), delimiter, float if dtype is None else dtype))
+
+
+def _predict_one(booster, dtest):
+    best_iteration = getattr(booster, "best_ntree_limit", 0)          # serve_utils.py:228-250
+    try:
+        best_iteration = int(best_iteration) if best_iteration is not None else 0
+    except (TypeError, ValueError):
+        best_iteration = 0
+    if best_iteration > 0:
+        return booster.predict(dtest, iteration_range=(0, best_iteration), validate_features=False)
+    return booster.predict(dtest, validate_features=False)
+
+
+def predict(model, model_format, dtest, input_content_type, objective=None):
+    """Single model: Booster.predict.  List of models: vote (multi:softmax / binary:hinge) or mean of the members."""
+    if isinstance(model, list):
+        ensemble = [_predict_one(b, dtest) for b in model]
+        if objective in (MULTI_SOFTMAX, BINARY_HINGE):
+            from scipy import stats
+            return stats.mode(ensemble).mode[0]
+        return np.mean(ensemble, axis=0)
+    return _predict_one(model, dtest)
+
+
+__all__ = ["csv_to_dmatrix", "predict", "Booster", "DMatrix", "XGBoostError"]
