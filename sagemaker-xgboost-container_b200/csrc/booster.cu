@@ -353,6 +353,11 @@ struct GrowerImpl {
   }
 };
 
+// ranks must agree on the fixed-point grid; shards of one job may straddle the small-matrix threshold, so distributed
+// training always uses the large-matrix grid
+static int job_grad_bits(int64_t n) { return Comm::get().distributed() ? kGradBits : grad_bits_for(n); }
+static int job_window_rows(int64_t n) { return Comm::get().distributed() ? kWindowRows : window_rows_for(n); }
+
 static TrainParamDev to_dev(const TrainParam& p) {
   TrainParamDev d; d.eta = p.eta; d.lambda = p.lambda; d.alpha = p.alpha; d.gamma = p.gamma; d.min_child_weight = p.min_child_weight;
   d.max_delta_step = p.max_delta_step; d.max_depth = p.max_depth; d.max_leaves = p.max_leaves; return d;
@@ -611,7 +616,7 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
   ga.row_offset = (int64_t)Comm::get().rank() << 40;
   launch_gradient(ga, s);
   Comm::get().allreduce_max_u32(g.gs.absmax, 2, s);
-  launch_scales(g.gs, s);
+  launch_scales(g.gs, job_grad_bits(dtrain->n), s);
 
   for (int k = 0; k < K; ++k) grow_one_tree(dtrain, cache, k, round * K + k);
 }
@@ -637,7 +642,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   ha.gpair = g.gpair.p + (size_t)k * g.gp_stride; ha.ridx = nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups;
-  ha.accumulate_sum = 1; ha.g_only = root_mode == 2 ? 1 : 0;
+  ha.accumulate_sum = 1; ha.g_only = root_mode == 2 ? 1 : 0; ha.window_rows = job_window_rows(dtrain->n);
   ha.rows_counter = profile_ ? prof_rows_.p : nullptr;
   prof_begin(0);
   launch_hist_build(ha, num_sms, s);
@@ -945,13 +950,13 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   for (int64_t i = 0; i < rows; ++i) { mg = std::max(mg, std::fabs(gpair_host[2 * i])); mh = std::max(mh, gpair_host[2 * i + 1]); }
   unsigned am[2]; memcpy(&am[0], &mg, 4); memcpy(&am[1], &mh, 4);
   CUDA_OK(cudaMemcpyAsync(g.gs.absmax, am, 8, cudaMemcpyHostToDevice, s));
-  launch_scales(g.gs, s);
+  launch_scales(g.gs, job_grad_bits(dm->n), s);
   const BinnedMatrix bm = dm->binned_view();
   HistArgs ha{}; ha.bins = bm.bins; ha.bins_tail = bm.bins_tail; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.tw = bm.tw; ha.gpair = g.gpair.p;
   ha.ridx = row_ids ? g.ridx0.p : nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups; ha.accumulate_sum = 1;
-  ha.force_gather = mode == 1 ? 1 : 0; ha.g_only = mode == 2 ? 1 : 0;
+  ha.force_gather = mode == 1 ? 1 : 0; ha.g_only = mode == 2 ? 1 : 0; ha.window_rows = job_window_rows(dm->n);
   g.root_h_valid = false;                       // the debug entry point overwrites gpair and the root slot
   cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
   float total = 0.f;

@@ -90,33 +90,60 @@ __global__ void __launch_bounds__(256) csv_parse_kernel(const char* text, int64_
   if (f != F) atomicMax(err, 1);                                                   // ragged row
 }
 
+// newline count: 16 B per thread per step
+__global__ void __launch_bounds__(256) count_newlines_kernel(const char* text, int64_t len, unsigned long long* out) {
+  unsigned long long c = 0;
+  const int64_t nvec = len / 16;
+  const uint4* v = reinterpret_cast<const uint4*>(text);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 w = v[i];
+    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned x = ws[k] ^ 0x0a0a0a0au;                                     // zero byte <=> '\n'
+      c += __popc(((x - 0x01010101u) & ~x & 0x80808080u));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (int64_t i = nvec * 16; i < len; ++i) c += text[i] == '\n';
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// request-sized scratch kept across calls (a serving process parses one body after another): no cudaMalloc per request
+struct CsvScratch { DevBuf<char> text; DevBuf<int64_t> nl; DevBuf<unsigned char> tmp; DevBuf<unsigned long long> cnt; DevBuf<int> err; };
+static CsvScratch& csv_scratch() { static thread_local CsvScratch s; return s; }
+
 // returns 0 = ok, 1 = ragged rows, 2 = a field outside the exact fast path / malformed (caller falls back to the host parser)
 int parse_csv_device(const char* h_text, int64_t len, char delim, int F, int64_t* n_rows_out, DevBuf<float>* X, cudaStream_t s) {
-  DevBuf<char> d_text; d_text.alloc((size_t)len + 1);
-  CUDA_OK(cudaMemcpyAsync(d_text.p, h_text, (size_t)len, cudaMemcpyHostToDevice, s));
-  // newline positions
-  DevBuf<int64_t> d_nl; d_nl.alloc((size_t)len / 2 + 2);                           // a row has at least one char + '\n' unless empty; bounded below
-  DevBuf<int64_t> d_cnt; d_cnt.alloc(1);
-  cub::CountingInputIterator<int64_t> idx(0);
-  IsNewline pred{d_text.p};
-  size_t tmp_bytes = 0;
-  // upper bound on newlines is len; allocate exactly after counting with a first select into a null output is not possible, so size for len
-  d_nl.alloc((size_t)len + 1);
-  CUDA_OK(cub::DeviceSelect::If(nullptr, tmp_bytes, idx, d_nl.p, d_cnt.p, len, pred, s));
-  DevBuf<unsigned char> tmp; tmp.alloc(tmp_bytes);
-  CUDA_OK(cub::DeviceSelect::If(tmp.p, tmp_bytes, idx, d_nl.p, d_cnt.p, len, pred, s));
-  ++g_kernel_launches;
-  int64_t nnl = 0;
-  CUDA_OK(cudaMemcpyAsync(&nnl, d_cnt.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CsvScratch& sc = csv_scratch();
+  sc.text.ensure((size_t)len + 16); sc.cnt.ensure(2); sc.err.ensure(1);
+  CUDA_OK(cudaMemcpyAsync(sc.text.p, h_text, (size_t)len, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemsetAsync(sc.cnt.p, 0, 16, s));
+  CUDA_OK(cudaMemsetAsync(sc.err.p, 0, 4, s));
+  count_newlines_kernel<<<148 * 8, 256, 0, s>>>(sc.text.p, len, sc.cnt.p); ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
+  unsigned long long nnl = 0;
+  CUDA_OK(cudaMemcpyAsync(&nnl, sc.cnt.p, sizeof(nnl), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
-  const int64_t n = nnl + 1;
+  const int64_t n = (int64_t)nnl + 1;
   *n_rows_out = n;
+  sc.nl.ensure((size_t)nnl + 1);
+  if (nnl > 0) {                                                                   // positions of the newlines, in order
+    cub::CountingInputIterator<int64_t> idx(0);
+    IsNewline pred{sc.text.p};
+    size_t tmp_bytes = 0;
+    long long* d_num = reinterpret_cast<long long*>(sc.cnt.p + 1);
+    CUDA_OK(cub::DeviceSelect::If(nullptr, tmp_bytes, idx, sc.nl.p, d_num, len, pred, s));
+    sc.tmp.ensure(tmp_bytes);
+    CUDA_OK(cub::DeviceSelect::If(sc.tmp.p, tmp_bytes, idx, sc.nl.p, d_num, len, pred, s));
+    ++g_kernel_launches;
+  }
   X->alloc((size_t)n * F);
-  DevBuf<int> d_err; d_err.alloc(1); d_err.zero(s);
-  csv_parse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_text.p, len, d_nl.p, n, F, delim, X->p, d_err.p); ++g_kernel_launches;
+  csv_parse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc.text.p, len, sc.nl.p, n, F, delim, X->p, sc.err.p); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
   int err = 0;
-  CUDA_OK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaMemcpyAsync(&err, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
   return err;
 }

@@ -40,8 +40,15 @@ constexpr int kSlots = 32;            // feature slots per group == bytes per ro
 constexpr int kBins = 256;            // bins per feature (uint8 codes); code 255 = missing when has_missing
 constexpr int kGroupEntries = kBins * kSlots;          // (bin, slot) accumulators per feature group
 constexpr int kMissingBin = 255;
-constexpr int kGradBits = 18;         // |g_q| <= 2^18, h_q <= 2^19: one 4096-row window cannot overflow int32
-constexpr int kHessBits = 19;
+// Fixed-point grid of the gradients: |g_q| <= 2^bits, h_q <= 2^(bits+1), and a CTA checks its int32 accumulators for overflow
+// every `window` rows with window * 2^bits + 2^24 < 2^31.  Large matrices use 18 bits / 8064 rows; matrices up to 2^20 rows
+// (where one-row leaves with large gradients are common and the extra overflow checks cost nothing measurable) use
+// 21 bits / 1008 rows, which keeps even a single-row leaf within 1e-5 of the double-precision reference.
+constexpr int kGradBits = 18, kWindowRows = 8064;
+constexpr int kGradBitsSmall = 21, kWindowRowsSmall = 1008;
+constexpr int64_t kSmallMatrixRows = 1 << 20;
+inline int grad_bits_for(int64_t n) { return n <= kSmallMatrixRows ? kGradBitsSmall : kGradBits; }
+inline int window_rows_for(int64_t n) { return n <= kSmallMatrixRows ? kWindowRowsSmall : kWindowRows; }
 constexpr int kMaxDepth = 16;
 
 struct GH64 { long long g, h; };      // exact fixed-point gradient/hessian sums

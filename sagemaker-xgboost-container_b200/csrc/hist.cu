@@ -36,7 +36,6 @@
 namespace b200 {
 
 constexpr int kSuperRows = 32;
-constexpr int kWindowRows = 8064;                 // rows per CTA between overflow checks: 8064 * 2^18 + 2^24 < 2^31
 constexpr int kMinRowsPerCta = 4096;              // do not pay a flush for fewer rows than this
 constexpr int kSpillThreshold = 1 << 24;
 constexpr int kPlaneBytes = kGroupEntries * 4;    // 32 KB
@@ -373,7 +372,7 @@ hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) 
   tc.bin_stride = (unsigned)a.tw * (unsigned)c.trep * 4u;
   tc.rep_off = has_tail ? (unsigned)((lane / a.tw) % c.trep) * (unsigned)a.tw * 4u : 0u;
   const unsigned rowl = (unsigned)(wit << 4) + (unsigned)(lane >> 1);          // this lane's row inside a tile
-  const unsigned tiles_per_window = kWindowRows / R;
+  const unsigned tiles_per_window = (unsigned)a.window_rows / R;
   long long accG = 0, accH = 0;
   unsigned i = (unsigned)team, s = (unsigned)team, ph = 0;                      // c.S >= kTeams (root_plan)
   for (unsigned wstart = 0;; wstart += tiles_per_window) {
@@ -446,8 +445,8 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
   constexpr int NWARPS = NTHREADS / 32;
   constexpr int LPR = 2 * NG, RPI = 32 / LPR, U = 2 * NG;                  // lanes per row, rows per instruction, units per super-tile
   constexpr int SUP = RPI * U;                                             // positions per super-tile: 32, 32, 30
-  constexpr int kItersPerWindow = kWindowRows / (SUP * NWARPS);            // super-tiles per warp between overflow checks
-  static_assert(kItersPerWindow >= 1, "window too small");
+  static_assert(kWindowRowsSmall / (SUP * NWARPS) >= 1, "window too small");
+  const unsigned iters_per_window = (unsigned)a.window_rows / (SUP * NWARPS);   // super-tiles per warp between overflow checks
   extern __shared__ __align__(16) int smem[];                              // per group: G[8192] then H[8192]; then the tail planes
   const int nb = *a.build_count;
   if (nb <= 0) return;
@@ -554,7 +553,7 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
       }
       if (TAIL) { if (active && has_tail) tail_accumulate<false>(tc, lane, cur.t0, cur.t1, gq_l, hq_l); }
       cur = nxt; nxt = nn;
-      if ((it + 1) % kItersPerWindow == 0 && it + 1 < iters) {       // overflow check: at most kWindowRows rows since the last one
+      if ((it + 1) % iters_per_window == 0 && it + 1 < iters) {       // overflow check: at most kWindowRows rows since the last one
         __syncthreads();
         spill_main<2>(smem, ng_here, out_main, false, threadIdx.x, NTHREADS);
         if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, trep, out_tail, false, threadIdx.x, NTHREADS);

@@ -215,21 +215,38 @@ __global__ void __launch_bounds__(1024) predict_tiled_kernel(PredictArgs a, int 
       const float* x = s_x + rl * pitch;
       const int64_t r = r0 + rl;
       float acc = (!LEAF_OUT && K == 1) ? a.margin[r] : 0.f;
-      for (int t = 0; t < nt_chunk; ++t) {
-        const PNode* tn = s_nodes + s_toff[t];
-        int nid = 0;
-        PNode nd = tn[0];
-        while ((nd.w & 0xffffu) != 0xffffu) {
-          const float v = x[(nd.w >> 16) & 0x7fffu];
-          const int left = (int)(nd.w & 0xffffu);
-          bool go_left = v < nd.cond;
-          if (HAS_NAN) { if (isnan(v)) go_left = (nd.w >> 31) != 0; }
-          nid = go_left ? left : left + 1;                                      // children are allocated as adjacent pairs
-          nd = tn[nid];
-        }
+      auto step = [&](const PNode* tn, int& nid, PNode& nd) {
+        const float v = x[(nd.w >> 16) & 0x7fffu];
+        const int left = (int)(nd.w & 0xffffu);
+        bool go_left = v < nd.cond;
+        if (HAS_NAN) { if (isnan(v)) go_left = (nd.w >> 31) != 0; }
+        nid = go_left ? left : left + 1;                                        // children are allocated as adjacent pairs
+        nd = tn[nid];
+      };
+      auto emit = [&](int t, int nid, const PNode& nd) {
         if (LEAF_OUT) a.leaf[r * nt_all + (tree_lo - a.tree_begin) + t] = nid;
-        else if (K == 1) acc += nd.cond;
+        else if (K == 1) acc += nd.cond;                                        // fp32, in tree order (== the reference's sequential sum)
         else a.margin[r * K + a.tree_info[tree_lo + t]] += nd.cond;
+      };
+      int t = 0;
+      for (; t + 4 <= nt_chunk; t += 4) {                                       // four independent traversals in flight hide the LDS latency
+        const PNode* tn[4]; int nid[4]; PNode nd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tn[j] = s_nodes + s_toff[t + j]; nid[j] = 0; nd[j] = tn[j][0]; }
+        bool any = true;
+        while (any) {
+          any = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if ((nd[j].w & 0xffffu) != 0xffffu) { step(tn[j], nid[j], nd[j]); any = true; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) emit(t + j, nid[j], nd[j]);
+      }
+      for (; t < nt_chunk; ++t) {
+        const PNode* tn = s_nodes + s_toff[t];
+        int nid = 0; PNode nd = tn[0];
+        while ((nd.w & 0xffffu) != 0xffffu) step(tn, nid, nd);
+        emit(t, nid, nd);
       }
       if (!LEAF_OUT && K == 1) a.margin[r] = acc;
     }

@@ -60,13 +60,13 @@ __global__ void init_tree_kernel(GrowState gs, TreeArrays t, unsigned n, int roo
 
 // Fixed-point scales from the all-reduced max|g|, max h of this round: power-of-two so that
 // quantisation is pure rounding to a binary grid and the inverse scaling is exact.
-__global__ void scales_kernel(GrowState gs) {
+__global__ void scales_kernel(GrowState gs, int grad_bits) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float mg = __uint_as_float(gs.absmax[0]), mh = __uint_as_float(gs.absmax[1]);
   int eg = 0, eh = 0;
   if (mg > 0.f && isfinite(mg)) frexpf(mg, &eg);     // mg < 2^eg
   if (mh > 0.f && isfinite(mh)) frexpf(mh, &eh);
-  float sg = ldexpf(1.0f, kGradBits - eg), sh = ldexpf(1.0f, kHessBits - eh);
+  float sg = ldexpf(1.0f, grad_bits - eg), sh = ldexpf(1.0f, grad_bits + 1 - eh);
   gs.scales[0] = sg; gs.scales[1] = sh; gs.scales[2] = 1.0f / sg; gs.scales[3] = 1.0f / sh;
 }
 
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(256) subtract_kernel(GrowState gs, GH64* pool,
 void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s) {
   init_tree_kernel<<<1, 32, 0, s>>>(gs, t, n, root_slot, max_level_nodes); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
-void launch_scales(const GrowState& gs, cudaStream_t s) { scales_kernel<<<1, 32, 0, s>>>(gs); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
+void launch_scales(const GrowState& gs, int grad_bits, cudaStream_t s) { scales_kernel<<<1, 32, 0, s>>>(gs, grad_bits); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s) {
   dim3 grid(max_nodes_level, a.ngroups + (a.tw > 0 ? 1 : 0)); eval_kernel<<<grid, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }

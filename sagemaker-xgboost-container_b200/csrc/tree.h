@@ -49,6 +49,7 @@ struct HistArgs {
   int ng_chunk;                 // groups per blockIdx.y chunk (set by the launcher)
   int accumulate_sum;
   int g_only;                   // constant-hessian root pass: accumulate G only (the slot already holds the cached H plane)
+  int window_rows;              // rows a CTA may accumulate between two int32 overflow checks (engine.h window_rows_for)
   int force_gather;             // tests / profiling: use hist_gather_kernel even for the contiguous root pass
   unsigned long long* rows_counter;   // optional: += rows processed by this launch (profiling)
 };
@@ -57,7 +58,7 @@ void launch_hist_build(const HistArgs& a, int num_sms, cudaStream_t stream);
 void hist_configure();     // one-time function attributes (must happen outside stream capture)
 const char* hist_last_kernel();   // name of the kernel variant the last launch used (profiling / tests)
 void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int root_slot, int max_level_nodes, cudaStream_t s);
-void launch_scales(const GrowState& gs, cudaStream_t s);
+void launch_scales(const GrowState& gs, int grad_bits, cudaStream_t s);
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s);
 void launch_apply(const ApplyArgs& a, cudaStream_t s);
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s);

@@ -88,10 +88,11 @@ def test_tile_reads_are_bank_conflict_free():
 
 
 def test_fixed_point_window_cannot_overflow_int32():
-    GRAD_BITS, HESS_BITS, WINDOW, SPILL = 18, 19, 8064, 1 << 24       # engine.h / hist.cu constants
-    assert (SPILL - 1) + WINDOW * (1 << GRAD_BITS) < 2 ** 31           # signed gradient plane
-    assert (SPILL - 1) + WINDOW * (1 << HESS_BITS) < 2 ** 32           # unsigned hessian plane
-    for sup, nwarps in ((32, 8), (32, 24), (30, 24)):                  # gather kernel: super-tiles of 32 / 30 rows per warp between checks
-        assert (WINDOW // (sup * nwarps)) * sup * nwarps <= WINDOW
-    for R in (64, 128, 192, 256):                                      # root kernel: whole tiles between checks
-        assert (WINDOW // R) * R <= WINDOW
+    SPILL = 1 << 24
+    for GRAD_BITS, WINDOW in ((18, 8064), (21, 1008)):                 # engine.h: large matrices / matrices up to 2^20 rows
+        HESS_BITS = GRAD_BITS + 1
+        assert (SPILL - 1) + WINDOW * (1 << GRAD_BITS) < 2 ** 31       # signed gradient plane
+        assert (SPILL - 1) + WINDOW * (1 << HESS_BITS) < 2 ** 32       # unsigned hessian plane
+        for sup, nwarps in ((32, 8), (32, 24), (30, 24)):              # gather kernel: super-tiles of 32 / 30 rows per warp between checks
+            assert WINDOW // (sup * nwarps) >= 1 and (WINDOW // (sup * nwarps)) * sup * nwarps <= WINDOW
+        assert WINDOW // 64 >= 1 and (WINDOW // 64) * 64 <= WINDOW     # root kernel: whole 64-row tiles between checks
