@@ -301,8 +301,6 @@ def predict_section(xgb, be, device, peak):
 
 def main():
     a = parse_args()
-    os.environ.setdefault("OMP_PROC_BIND", "spread")          # CPU arms: pinned OpenMP threads (must be set before libgomp starts)
-    os.environ.setdefault("OMP_PLACES", "cores")
     if a.watchdog_seconds > 0:
         def _bail():
             sys.stderr.write("bench.py: watchdog fired after %d s, exiting\n" % a.watchdog_seconds)
@@ -357,8 +355,10 @@ def main():
     l0 = be.launch_count()
     barrier()
     be.timer_start()
+    t_host0 = time.perf_counter()
     for _ in range(a.steps):
         bst.update(dtrain, it); it += 1
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / a.steps       # CPU time to ENQUEUE a round (graph launches + collectives)
     ms = be.timer_stop()
     barrier()
     launches = be.launch_count() - l0
@@ -426,13 +426,19 @@ def main():
         del d2, b2
 
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
-        S = min(a.rows, a.cpu_sample_rows)
-        xs, ys, _ = gen_host_sample(a, S)
-        threads = host_threads()
-        rps, ingest_s, cores = oracle_rounds_per_sec(a, xs, ys, 3, 1, threads)
-        cpu = {"value": rps * len(xs) / a.rows, "unit": "rounds/s", "cores": cores, "kind": "port",
-               "sample": "first %d of %d rows (same generator and seed), 3 timed rounds after 1 warm-up, %d OpenMP threads, scaled linearly in rows" % (len(xs), a.rows, cores)}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        # the CPU leg runs as its own process (the reference arm on a smaller sample): OpenMP thread binding must be in the
+        # environment before libgomp starts, and must NOT be in the environment of the GPU ranks (it would pin every
+        # rank's launching thread onto the same core)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1", "--rows", str(a.rows), "--cols", str(a.cols),
+               "--objective", a.objective, "--num-class", str(a.num_class), "--max-depth", str(a.max_depth), "--max-bin", str(a.max_bin), "--seed", str(a.seed),
+               "--reference-rows", str(min(a.rows, a.cpu_sample_rows)), "--watchdog-seconds", "600"]
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS")}
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+        try:
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception:
+            cpu = {"value": None, "unit": "rounds/s", "cores": 0, "kind": "port", "sample": "cpu leg failed: %s" % (r.stderr[-300:] or r.stdout[-300:])}
 
     predict = None
     if rank == 0 and world == 1 and not a.no_predict:
@@ -450,7 +456,7 @@ def main():
                        "rounds_timed": "rounds %d..%d of a fresh booster (the rows of the built children shrink from ~50 %% to ~23 %% of N per level over the first rounds)" % (a.warmup, a.warmup + a.steps - 1),
                        "params": params},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "predict": predict,
-            "model_hash": mhash, "model_trees": mtrees,
+            "model_hash": mhash, "model_trees": mtrees, "host_enqueue_ms_per_step": host_ms,
         }
         print(json.dumps(out))
     if dist is not None:

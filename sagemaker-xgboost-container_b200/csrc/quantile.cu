@@ -17,7 +17,8 @@ __global__ void extract_col_kernel(const float* X, int64_t n, int F, int f, cons
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     float v = X[r * F + f];
     bool nan = isnan(v);
-    keys[r] = nan ? __int_as_float(0x7f800000) : v;      // NaN -> +inf: sorts last
+    keys[r] = nan ? __int_as_float(0x7f800000) : (v == 0.f ? 0.f : v);      // NaN -> +inf: sorts last; -0.0 -> +0.0 so that the
+                                                                            // representative of the zero run (a cut value) does not depend on sort order / rank count
     if (wout) wout[r] = nan ? 0.f : (w ? w[r] : 1.f);
   }
 }
