@@ -118,6 +118,11 @@ XGB_DLL int XGB200DMatrixSetCuts(DMatrixHandle handle, const int* ptrs, bst_ulon
  * 1 = rows of different lengths, 2 = a field the exact device fast path cannot decide (caller parses on the host);
  * *out is NULL unless *status == 0. */
 XGB_DLL int XGB200DMatrixCreateFromCSV(const char* text, bst_ulong len, char delimiter, int* status, DMatrixHandle* out);
+/* Training loaders to the device: the text of a CSV channel ("<dir>?format=csv&label_column=0[&weight_column=1]",
+ * data_utils.py:289-318) parsed on the GPU; label_column / weight_column (-1 = none) become the "label" / "weight" float
+ * info, the other columns the feature matrix.  Same status convention as XGB200DMatrixCreateFromCSV. */
+XGB_DLL int XGB200DMatrixCreateFromCSVEx(const char* text, bst_ulong len, char delimiter, int label_column, int weight_column,
+                             int* status, DMatrixHandle* out);
 /* the float32 feature matrix as the engine holds it (row-major n x F, NaN = missing), for bit-exact checks of the input paths */
 XGB_DLL int XGB200DMatrixGetRaw(DMatrixHandle handle, float* out_row_major);
 /* binned feature blocks back on the host in plain row-major n x F order (for bit-exact checks of the binning kernel) */

@@ -96,6 +96,14 @@ class CudaBackend:
         self._check(self.lib.XGB200DMatrixGetRaw(h, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
+    def dmatrix_from_csv_labeled(self, payload, delimiter=",", label_column=-1, weight_column=-1):
+        """Device-side parse of a training CSV channel; (handle, status) like dmatrix_from_csv."""
+        h = C.c_void_p()
+        st = C.c_int(0)
+        self._check(self.lib.XGB200DMatrixCreateFromCSVEx(C.c_char_p(payload), C.c_ulong(len(payload)), C.c_char(delimiter.encode("ascii")),
+                                                          C.c_int(label_column), C.c_int(weight_column), C.byref(st), C.byref(h)))
+        return (h if st.value == 0 else None), int(st.value)
+
     def dmatrix_from_csv(self, payload, delimiter=","):
         """Device-side CSV parse (csv.cu).  Returns (handle, status); handle is None unless status == 0."""
         if isinstance(payload, str):

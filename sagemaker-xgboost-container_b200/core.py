@@ -40,7 +40,9 @@ class DMatrix:
             raise XGBoostError("categorical features are not supported on the B200 hist path")
         be = get_backend()
         miss = np.nan if missing is None else float(missing)
-        if isinstance(data, (str, os.PathLike)):
+        if isinstance(data, (str, os.PathLike)) and self._try_device_csv(os.fspath(data), be):
+            pass
+        elif isinstance(data, (str, os.PathLike)):
             X, y, w = load_uri(os.fspath(data))
             if _is_scipy_sparse(X):
                 self.handle = be.dmatrix_from_csr(X.indptr, X.indices, X.data, X.shape[1])
@@ -80,6 +82,32 @@ class DMatrix:
             self.feature_names = feature_names
         if feature_types is not None:
             self.feature_types = feature_types
+
+    def _try_device_csv(self, uri, be):
+        """CSV channels go to the device as TEXT and are parsed there (csrc/csv.cu) -- no dense float32 host copy.  Returns
+        False (host loader takes over) for other formats, backends without the entry point, or text the exact device fast
+        path cannot decide (blank lines inside a file, >19-digit literals, ragged rows: the host loader reports those)."""
+        from .data import parse_uri, _list_files
+        if not hasattr(be, "dmatrix_from_csv_labeled"):
+            return False
+        path, q = parse_uri(uri)
+        fmt = q.get("format") or ("csv" if os.path.splitext(path)[1].lower() == ".csv" else "libsvm")
+        delim = q.get("delimiter", ",")
+        if fmt != "csv" or len(delim) != 1 or ord(delim) >= 128:
+            return False
+        chunks = []
+        for f in _list_files(path):
+            with open(f, "rb") as fh:
+                b = fh.read().strip()
+            if b:
+                chunks.append(b.replace(b"\r\n", b"\n"))
+        if not chunks:
+            return False
+        handle, status = be.dmatrix_from_csv_labeled(b"\n".join(chunks), delim, int(q.get("label_column", -1)), int(q.get("weight_column", -1)))
+        if status != 0:
+            return False
+        self.handle = handle
+        return True
 
     @classmethod
     def _from_handle(cls, handle):

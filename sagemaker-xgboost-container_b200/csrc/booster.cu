@@ -833,8 +833,7 @@ std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, c
       std::string base = mname;
       if (mname.rfind("error@", 0) == 0) { base = "error"; ma.threshold = std::stof(mname.substr(6)); }
       if (base == "auc") {
-        // experimental until validated on hardware (written after the round-1 GPU budget was spent)
-        B200_CHECK(getenv("B200XGB_EXPERIMENTAL") != nullptr, "Unknown metric function auc (implemented in auc.cu but not yet validated on hardware; set B200XGB_EXPERIMENTAL=1 to use it)");
+        // validated on hardware against sklearn.metrics.roc_auc_score (tests/test_gpu_parity.py::test_auc_matches_sklearn)
         B200_CHECK(param_.num_class <= 1, "auc is implemented for binary / regression-style predictions only");
         const int logistic = (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic) ? 1 : 0;
         compute_auc_device(c.margin.p, dm->d_labels.p, dm->weights.empty() ? nullptr : dm->d_weights.p, dm->n, logistic, grower_->dsum.p, s);

@@ -318,6 +318,15 @@ int XGB200DMatrixGetRaw(DMatrixHandle handle, float* out_row_major) {
   if (dm->n * dm->F > 0) CUDA_OK(cudaMemcpy(out_row_major, dm->X.p, sizeof(float) * (size_t)dm->n * dm->F, cudaMemcpyDeviceToHost));
   API_END();
 }
+int XGB200DMatrixCreateFromCSVEx(const char* text, bst_ulong len, char delimiter, int label_column, int weight_column, int* status, DMatrixHandle* out) {
+  API_BEGIN();
+  int st = 0;
+  auto dm = DMatrix::from_csv_text_labeled(text, (int64_t)len, delimiter, label_column, weight_column, &st);
+  if (status) *status = st;
+  *out = nullptr;
+  if (st == 0) { auto box = new DMatrixBox(); box->dm = std::move(dm); *out = box; }
+  API_END();
+}
 int XGB200DMatrixCreateFromCSV(const char* text, bst_ulong len, char delimiter, int* status, DMatrixHandle* out) {
   API_BEGIN();
   int st = 0;

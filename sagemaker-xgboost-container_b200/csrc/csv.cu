@@ -148,6 +148,46 @@ int parse_csv_device(const char* h_text, int64_t len, char delim, int F, int64_t
   return err;
 }
 
+// training channels (data_utils.py:289-318: "?format=csv&label_column=0[&weight_column=1]"): the label / weight columns
+// leave the parsed matrix on the device, the remaining columns are compacted in place order
+__global__ void __launch_bounds__(256) split_columns_kernel(const float* in, int64_t n, int Fin, int label_col, int weight_col, float* out, float* y, float* w) {
+  const int Fout = Fin - (label_col >= 0 ? 1 : 0) - (weight_col >= 0 ? 1 : 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * Fin; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Fin; const int c = (int)(i - r * Fin);
+    const float v = in[i];
+    if (c == label_col) y[r] = v;
+    else if (c == weight_col) w[r] = v;
+    else out[r * Fout + c - (label_col >= 0 && c > label_col ? 1 : 0) - (weight_col >= 0 && c > weight_col ? 1 : 0)] = v;
+  }
+}
+
+std::unique_ptr<DMatrix> DMatrix::from_csv_text_labeled(const char* text, int64_t len, char delim, int label_col, int weight_col, int* status) {
+  int Fin = 1;
+  for (int64_t i = 0; i < len && text[i] != '\n'; ++i) if (text[i] == delim) ++Fin;
+  B200_CHECK(label_col < Fin && weight_col < Fin && (label_col < 0 || label_col != weight_col), "CSV: label_column / weight_column out of range");
+  cudaStream_t s = engine_stream();
+  DevBuf<float> raw; int64_t n = 0;
+  *status = parse_csv_device(text, len, delim, Fin, &n, &raw, s);
+  if (*status != 0) return nullptr;
+  B200_CHECK(n < (int64_t)0x7fffffff, "DMatrix: more than 2^31-1 rows per GPU are not supported");
+  auto dm = std::make_unique<DMatrix>();
+  const int Fout = Fin - (label_col >= 0 ? 1 : 0) - (weight_col >= 0 ? 1 : 0);
+  dm->n = n; dm->F = Fout;
+  dm->X.alloc((size_t)n * std::max(Fout, 0));
+  DevBuf<float> dy, dw; dy.alloc(label_col >= 0 ? n : 0); dw.alloc(weight_col >= 0 ? n : 0);
+  const int grid = (int)std::min<int64_t>((n * Fin + 255) / 256, 148 * 32);
+  split_columns_kernel<<<grid, 256, 0, s>>>(raw.p, n, Fin, label_col, weight_col, dm->X.p, dy.p, dw.p); ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
+  std::vector<float> hy(label_col >= 0 ? n : 0), hw(weight_col >= 0 ? n : 0);
+  if (!hy.empty()) CUDA_OK(cudaMemcpyAsync(hy.data(), dy.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+  if (!hw.empty()) CUDA_OK(cudaMemcpyAsync(hw.data(), dw.p, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  dm->finish_upload(std::nanf(""));
+  if (!hy.empty()) dm->set_float_info("label", hy.data(), hy.size());
+  if (!hw.empty()) dm->set_float_info("weight", hw.data(), hw.size());
+  return dm;
+}
+
 std::unique_ptr<DMatrix> DMatrix::from_csv_text(const char* text, int64_t len, char delim, int* status) {
   // columns from the first line (the container sniffs the delimiter there too, encoder.py:46-48)
   int F = 1;

@@ -266,6 +266,22 @@ def test_eval_metrics_match_numpy(xgb):
     assert abs(res["train"]["rmse"][-1] - np.sqrt(np.mean((p - y) ** 2))) < 1e-6
 
 
+@pytest.mark.parametrize("weighted", [False, True])
+def test_auc_matches_sklearn(xgb, weighted):
+    """Native `auc` (the one HPO metric the container does not compute itself, train_utils.py:45-76) against
+    sklearn.metrics.roc_auc_score, with tied predictions (shallow trees give few distinct scores) and sample weights."""
+    from sklearn.metrics import roc_auc_score
+    X, y = synth(30000, 10, 91, "bin")
+    w = np.random.default_rng(4).random(len(y)).astype(np.float32) + 0.1 if weighted else None
+    d = xgb.DMatrix(X, label=y, weight=w)
+    res = {}
+    bst = xgb.train(dict(objective="binary:logistic", max_depth=2, eta=0.5, eval_metric=["auc", "logloss"]), d, num_boost_round=3,
+                    evals=[(d, "train")], evals_result=res, verbose_eval=False)
+    p = bst.predict(d)
+    assert len(np.unique(p)) < 200                                   # many ties
+    assert abs(res["train"]["auc"][-1] - roc_auc_score(y, p, sample_weight=w)) < 1e-9
+
+
 def test_label_errors_surface_as_xgboost_error(xgb):
     X, y = synth(200, 4, 81, "reg")
     d = xgb.DMatrix(X, label=y * 10)

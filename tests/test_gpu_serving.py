@@ -76,3 +76,25 @@ def test_serving_predict_matches_direct_predict(xgb):
     np.testing.assert_array_equal(p, bst.predict(xgb.DMatrix(X[:300])))
     ens = serving.predict([bst, bst], ["xgb_format"] * 2, dtest, "text/csv", objective="binary:logistic")
     np.testing.assert_allclose(ens, p, rtol=0, atol=1e-7)
+
+
+def test_training_csv_channel_is_parsed_on_the_device_like_the_host_loader(xgb, tmp_path):
+    """data_utils.py:289-318: a directory of CSV files, label in column 0, optional weight in column 1 (csv_weights=1)."""
+    from sagemaker_xgboost_container_b200.data import load_uri
+    rng = np.random.default_rng(3)
+    d = tmp_path / "train"
+    d.mkdir()
+    for i in range(3):
+        A = np.round(rng.standard_normal((700 + i, 9)) * 10 ** rng.integers(-3, 4, size=(1, 9)), 5)
+        A[:, 1] = np.abs(A[:, 1]) + 0.5          # weights must be non-negative
+        lines = [",".join("" if (r + c) % 53 == 0 and c > 1 else repr(float(v)) for c, v in enumerate(row)) for r, row in enumerate(A)]
+        (d / ("part-%d.csv" % i)).write_text("\n".join(lines) + "\n")
+    uri = "%s?format=csv&label_column=0&delimiter=,&weight_column=1" % d
+    dm = xgb.DMatrix(uri)
+    X, y, w = load_uri(uri)
+    be = xgb.get_backend()
+    got = be.dmatrix_get_raw(dm.handle).reshape(dm.num_row(), dm.num_col())
+    assert got.shape == X.shape
+    np.testing.assert_array_equal(np.nan_to_num(got, nan=-777.0), np.nan_to_num(X, nan=-777.0))
+    np.testing.assert_array_equal(dm.get_label(), y)
+    np.testing.assert_array_equal(dm.get_weight(), w)
