@@ -165,6 +165,14 @@ void DMatrix::bin_with_cuts() {
   CUDA_OK(cudaMemsetAsync(bins.p + (size_t)n * ngroups * kSlots, 0, (size_t)512 * ngroups * kSlots, s));
   if (tw) CUDA_OK(cudaMemsetAsync(bins_tail.p + (size_t)n * tw, 0, (size_t)512 * tw, s));
   launch_bin(X.p, n, F, ngroups, tw, d_cut_ptrs.p, d_cut_vals.p, bins.p, bins_tail.p, s);
+  gather_stride = ngroups * kSlots;
+  bins_gather.release();
+  static const bool no_aligned = getenv("B200XGB_NO_ALIGNED_ROWS") != nullptr;
+  if (ngroups * kSlots == 96 && !no_aligned) {           // 96 B rows straddle 128 B DRAM lines half of the time: the gathered levels read an aligned copy
+    gather_stride = 128;
+    bins_gather.alloc((size_t)n * 128 + 128);
+    launch_pad_rows(bins.p, n, 96, bins_gather.p, 128, s);
+  }
   bins_col.alloc((size_t)std::max(F, 1) * n);
   launch_transpose_bins(bins.p, bins_tail.p, n, F, ngroups, tw, bins_col.p, s);
   Comm::get().sync_stream(s);
@@ -639,6 +647,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   else CUDA_OK(cudaMemsetAsync(g.hist_pool.p, 0, g.slot_stride * sizeof(GH64), s));
 
   HistArgs ha{}; ha.bins = bm.bins; ha.bins_tail = bm.bins_tail; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.tw = bm.tw;
+  ha.bins_gather = bm.bins_gather; ha.gather_stride = bm.gather_stride;
   ha.gpair = g.gpair.p + (size_t)k * g.gp_stride; ha.ridx = nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups;
@@ -952,6 +961,7 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   launch_scales(g.gs, job_grad_bits(dm->n), s);
   const BinnedMatrix bm = dm->binned_view();
   HistArgs ha{}; ha.bins = bm.bins; ha.bins_tail = bm.bins_tail; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.tw = bm.tw; ha.gpair = g.gpair.p;
+  ha.bins_gather = bm.bins_gather; ha.gather_stride = bm.gather_stride;
   ha.ridx = row_ids ? g.ridx0.p : nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups; ha.accumulate_sum = 1;

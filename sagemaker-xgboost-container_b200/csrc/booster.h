@@ -28,7 +28,7 @@ class DMatrix {
   // binned representation (built on first use as a training matrix)
   bool binned = false; int binned_max_bin = 0;
   HostCuts cuts; DevBuf<int> d_cut_ptrs; DevBuf<float> d_cut_vals, d_min_vals;
-  DevBuf<uint8_t> bins, bins_tail, bins_col; int ngroups = 0, tw = 0, ntail = 0;   // engine.h BinnedMatrix layout
+  DevBuf<uint8_t> bins, bins_tail, bins_col, bins_gather; int ngroups = 0, tw = 0, ntail = 0, gather_stride = 0;   // engine.h BinnedMatrix layout
   uint64_t binned_version = 0;                        // bumped by every (re)binning: invalidates captured graphs / cached planes
   uint64_t uid;                                       // identity for prediction caches
 
@@ -46,6 +46,7 @@ class DMatrix {
   void ensure_binned(int max_bin);
   void set_cuts(const HostCuts& c);                   // external cuts (shared with the oracle in tests)
   BinnedMatrix binned_view() const { BinnedMatrix b; b.bins = bins.p; b.bins_tail = tw ? bins_tail.p : nullptr; b.bins_col = bins_col.p; b.n = n; b.F = F;
+    b.bins_gather = bins_gather.p ? bins_gather.p : bins.p; b.gather_stride = gather_stride;
     b.ngroups = ngroups; b.tw = tw; b.ntail = ntail; b.has_missing = has_missing; return b; }
   void finish_upload(float missing);
  private:

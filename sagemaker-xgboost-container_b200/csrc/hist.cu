@@ -468,12 +468,14 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
   const bool has_tail = TAIL && a.tw > 0 && blockIdx.y == gridDim.y - 1;
   const float sg = a.scales[0], sh = a.scales[1];
   const unsigned smem_g = (unsigned)__cvta_generic_to_shared(smem);
-  const int64_t row_stride = (int64_t)a.row_stride;
+  // gathered passes read the line-aligned copy of the rows; the contiguous pass (ridx == nullptr) the packed one
+  const bool aligned = a.ridx != nullptr && a.bins_gather != nullptr;
+  const int64_t row_stride = aligned ? (int64_t)a.gather_stride : (int64_t)a.row_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane / LPR, c = lane - q * LPR;                            // row inside a unit, 16 B chunk inside the row
   const bool lane_on = q < RPI && (c >> 1) < ng_here;                       // idle lanes add zeros to a slot rotation nobody else uses
   const LaneConst lc = make_lane_const_rot(q < RPI ? NG * q + (c >> 1) : 15, c & 1, smem_g + (unsigned)((q < RPI ? (c >> 1) : 0) * 2 * kPlaneBytes));
-  const uint8_t* gbins = a.bins + (int64_t)g0 * kSlots + c * 16;
+  const uint8_t* gbins = (aligned ? a.bins_gather : a.bins) + (int64_t)g0 * kSlots + c * 16;
   TailConst tc;
   constexpr int TREP = gather_tail_replicas(NG);          // replicas of the tail planes that fit next to the main planes
   tc.tw = TAIL ? a.tw : 4;

@@ -113,6 +113,21 @@ __global__ void __launch_bounds__(256) bin_kernel(const float* X, int64_t n, int
   }
 }
 
+// rows re-laid at `dst_stride` bytes (whole 128 B lines for 96 B rows): 16 B per thread
+__global__ void __launch_bounds__(256) pad_rows_kernel(const uint8_t* src, int64_t n, int src_stride, uint8_t* dst, int dst_stride) {
+  const int cpr = dst_stride / 16, spr = src_stride / 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * cpr; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cpr; const int c = (int)(i - r * cpr);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c < spr) v = reinterpret_cast<const uint4*>(src + r * src_stride)[c];
+    reinterpret_cast<uint4*>(dst + r * dst_stride)[c] = v;
+  }
+}
+void launch_pad_rows(const uint8_t* src, int64_t n, int src_stride, uint8_t* dst, int dst_stride, cudaStream_t s) {
+  if (n == 0) return;
+  pad_rows_kernel<<<148 * 16, 256, 0, s>>>(src, n, src_stride, dst, dst_stride); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+}
+
 // column-major copy [F][n] of the binned matrix (used by the 1-byte-per-row consumers: partition, cache update)
 __global__ void __launch_bounds__(256) transpose_bins_kernel(const uint8_t* bins, const uint8_t* bins_tail, int64_t n, int F, int ngroups, int tw, uint8_t* bins_col) {
   __shared__ uint8_t tile[256][kSlots + 1];

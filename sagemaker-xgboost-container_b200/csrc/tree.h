@@ -34,6 +34,8 @@ struct HistArgs {
   const unsigned* tail_pos;     // tw == 4 only: the rows' tail words by POSITION (they travel with the row ids); nullptr = gather from bins_tail
   int64_t n;
   int row_stride;               // ngroups * 32
+  const uint8_t* bins_gather;   // rows for the gathered passes (BinnedMatrix::bins_gather) and their stride
+  int gather_stride;
   int tw;                       // tail width in bytes (0, 4, 8)
   const float2* gpair;          // (g, h) by POSITION in the row-id buffer (== by row at the root)
   const unsigned* ridx;         // row ids by segment position; nullptr = identity (root)
