@@ -1,6 +1,8 @@
 """Serving input path on the device (BASELINE config 5): the CSV request body parsed by csv.cu must
 give exactly the float32 matrix the container's own route builds (encoder.csv_to_dmatrix: str.split -> np.array -> float64 ->
 DMatrix float32), for every literal form Python's float() accepts; anything outside the exact fast path falls back to it."""
+import os
+
 import numpy as np
 import pytest
 
@@ -85,16 +87,21 @@ def test_training_csv_channel_is_parsed_on_the_device_like_the_host_loader(xgb, 
     d = tmp_path / "train"
     d.mkdir()
     for i in range(3):
-        A = np.round(rng.standard_normal((700 + i, 9)) * 10 ** rng.integers(-3, 4, size=(1, 9)), 5)
+        A = np.round(rng.standard_normal((700 + i, 9)) * 10.0 ** rng.integers(-3, 4, size=(1, 9)), 5)
         A[:, 1] = np.abs(A[:, 1]) + 0.5          # weights must be non-negative
         lines = [",".join("" if (r + c) % 53 == 0 and c > 1 else repr(float(v)) for c, v in enumerate(row)) for r, row in enumerate(A)]
         (d / ("part-%d.csv" % i)).write_text("\n".join(lines) + "\n")
     uri = "%s?format=csv&label_column=0&delimiter=,&weight_column=1" % d
     dm = xgb.DMatrix(uri)
-    X, y, w = load_uri(uri)
+    X, y, w = load_uri(uri)                      # host loader (pandas' C parser: its fast strtod may be 1 ulp off in double)
     be = xgb.get_backend()
     got = be.dmatrix_get_raw(dm.handle).reshape(dm.num_row(), dm.num_col())
     assert got.shape == X.shape
-    np.testing.assert_array_equal(np.nan_to_num(got, nan=-777.0), np.nan_to_num(X, nan=-777.0))
-    np.testing.assert_array_equal(dm.get_label(), y)
-    np.testing.assert_array_equal(dm.get_weight(), w)
+    # exact reference: Python's correctly rounded float() of every field, then float32 -- the device parser must match it bit for bit
+    rows = [l.split(",") for f in sorted(os.listdir(d)) for l in open(d / f).read().strip().split("\n")]
+    ref = np.array([[np.nan if v == "" else float(v) for v in r] for r in rows], dtype=np.float64).astype(np.float32)
+    np.testing.assert_array_equal(np.nan_to_num(got, nan=-777.0), np.nan_to_num(ref[:, 2:], nan=-777.0))
+    np.testing.assert_array_equal(dm.get_label(), ref[:, 0])
+    np.testing.assert_array_equal(dm.get_weight(), ref[:, 1])
+    np.testing.assert_allclose(np.nan_to_num(got, nan=-777.0), np.nan_to_num(X, nan=-777.0), rtol=2e-7, atol=0)
+    np.testing.assert_allclose(dm.get_label(), y, rtol=2e-7)
