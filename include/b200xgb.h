@@ -123,6 +123,8 @@ XGB_DLL int XGB200DMatrixCreateFromCSV(const char* text, bst_ulong len, char del
  * info, the other columns the feature matrix.  Same status convention as XGB200DMatrixCreateFromCSV. */
 XGB_DLL int XGB200DMatrixCreateFromCSVEx(const char* text, bst_ulong len, char delimiter, int label_column, int weight_column,
                              int* status, DMatrixHandle* out);
+/* 1 when the per-level histogram all-reduce runs as the NVLink peer-memory kernel (nvlink.cu), 0 when it goes through NCCL */
+XGB_DLL int XGB200CommPeerReduceActive(void);
 /* the float32 feature matrix as the engine holds it (row-major n x F, NaN = missing), for bit-exact checks of the input paths */
 XGB_DLL int XGB200DMatrixGetRaw(DMatrixHandle handle, float* out_row_major);
 /* binned feature blocks back on the host in plain row-major n x F order (for bit-exact checks of the binning kernel) */

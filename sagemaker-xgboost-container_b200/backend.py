@@ -272,6 +272,9 @@ class CudaBackend:
     def comm_finalize(self):
         self._check(self.lib.XGCommunicatorFinalize())
 
+    def comm_peer_reduce_active(self):
+        return bool(self.lib.XGB200CommPeerReduceActive())
+
     def comm_rank(self):
         return int(self.lib.XGCommunicatorGetRank())
 

@@ -295,6 +295,7 @@ struct GrowerImpl {
   int64_t n = 0; int ngroups = 0, tw = 0, max_depth = 0, max_nodes = 0, cap_nodes = 0, max_level_nodes = 0, region = 0;
   size_t slot_stride = 0;                  // GH64 entries per histogram slot
   int64_t gp_stride = 0;                   // rows reserved per class in gpair
+  int64_t global_n = 0;                    // rows of the whole job (sum over ranks)
   DevBuf<long long> root_h_cache; uint64_t root_h_uid = 0, root_h_version = 0; bool root_h_valid = false;
   GrowState gs{}; TreeArrays ta{};
   DevBuf<unsigned char> state_block;       // all GrowState arrays
@@ -312,6 +313,12 @@ struct GrowerImpl {
     if (n == n_ && ngroups == ngroups_ && tw == tw_ && max_depth == max_depth_ && gpair.n >= (size_t)stride_ * K + 512) return;
     B200_CHECK(max_depth_ >= 1 && max_depth_ <= kMaxDepth, "max_depth must be in [1, 16] for the B200 depth-wise hist builder");
     n = n_; ngroups = ngroups_; tw = tw_; max_depth = max_depth_; gp_stride = stride_; root_h_valid = false;
+    if (peer_reduce_active()) {                     // peers still map the buffers that are about to be freed: unmap everywhere first
+      peer_reduce_close();
+      DevBuf<unsigned> bar; bar.alloc(1); bar.zero(engine_stream());
+      Comm::get().allreduce_max_u32(bar.p, 1, engine_stream());
+      Comm::get().sync_stream(engine_stream());
+    }
     for (auto& tg : graphs) tg.destroy();
     max_nodes = (1 << (max_depth + 1)) - 1;
     cap_nodes = (max_nodes + 15) & ~15;
@@ -358,13 +365,24 @@ struct GrowerImpl {
     ta.split_cond = fp; ta.base_weight = fp + N; ta.loss_chg = fp + 2 * N; ta.sum_hess = fp + 3 * N;
     ta.default_left = (unsigned char*)(fp + 4 * N);
     hist_configure();
+    // multi-rank: map the peers' histogram pools / grow-state blocks over NVLink (collective; every rank gets here in its first update)
+    global_n = n;
+    if (Comm::get().distributed()) {
+      peer_reduce_setup({{hist_pool.p, hist_pool.n * sizeof(GH64)}, {state_block.p, state_block.n}}, engine_stream());
+      double v = (double)n;
+      CUDA_OK(cudaMemcpyAsync(dsum.p, &v, sizeof v, cudaMemcpyHostToDevice, engine_stream()));
+      Comm::get().allreduce_sum_f64(dsum.p, 1, engine_stream());
+      CUDA_OK(cudaMemcpyAsync(&v, dsum.p, sizeof v, cudaMemcpyDeviceToHost, engine_stream()));
+      Comm::get().sync_stream(engine_stream());
+      global_n = (int64_t)v;
+    }
   }
 };
 
-// ranks must agree on the fixed-point grid; shards of one job may straddle the small-matrix threshold, so distributed
-// training always uses the large-matrix grid
-static int job_grad_bits(int64_t n) { return Comm::get().distributed() ? kGradBits : grad_bits_for(n); }
-static int job_window_rows(int64_t n) { return Comm::get().distributed() ? kWindowRows : window_rows_for(n); }
+// ranks must agree on the fixed-point grid: it follows the GLOBAL row count of the job (GrowerImpl::global_n, all-reduced
+// once), so that N ranks and one GPU train bit-identical models on the same data
+static int job_grad_bits(int64_t global_n) { return grad_bits_for(global_n); }
+static int job_window_rows(int64_t global_n) { return window_rows_for(global_n); }
 
 static TrainParamDev to_dev(const TrainParam& p) {
   TrainParamDev d; d.eta = p.eta; d.lambda = p.lambda; d.alpha = p.alpha; d.gamma = p.gamma; d.min_child_weight = p.min_child_weight;
@@ -624,7 +642,7 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
   ga.row_offset = (int64_t)Comm::get().rank() << 40;
   launch_gradient(ga, s);
   Comm::get().allreduce_max_u32(g.gs.absmax, 2, s);
-  launch_scales(g.gs, job_grad_bits(dtrain->n), s);
+  launch_scales(g.gs, job_grad_bits(g.global_n), s);
 
   for (int k = 0; k < K; ++k) grow_one_tree(dtrain, cache, k, round * K + k);
 }
@@ -651,7 +669,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   ha.gpair = g.gpair.p + (size_t)k * g.gp_stride; ha.ridx = nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups;
-  ha.accumulate_sum = 1; ha.g_only = root_mode == 2 ? 1 : 0; ha.window_rows = job_window_rows(dtrain->n);
+  ha.accumulate_sum = 1; ha.g_only = root_mode == 2 ? 1 : 0; ha.window_rows = job_window_rows(g.global_n);
   ha.rows_counter = profile_ ? prof_rows_.p : nullptr;
   prof_begin(0);
   launch_hist_build(ha, num_sms, s);
@@ -671,10 +689,14 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
     g.capturing->segs.push_back(exec); g.capturing->colls.push_back(f);
     CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   };
-  {
-    GH64* pool = g.hist_pool.p; GH64* nsum = g.gs.node_sum; const size_t cnt = g.slot_stride * 2;
-    collective([pool, nsum, cnt, s]() { Comm::get().allreduce_sum_i64(pool, cnt, s); Comm::get().allreduce_sum_i64(nsum, 2, s); });
-  }
+  // the per-level histogram all-reduce: one NVLink peer-memory kernel inside the graph when the peers are mapped, else NCCL
+  auto allreduce_hist = [&](GH64* p, size_t cnt) {
+    if (!comm.distributed()) return;
+    if (peer_allreduce_i64(reinterpret_cast<long long*>(p), cnt, s)) return;
+    collective([p, cnt, s]() { Comm::get().allreduce_sum_i64(p, cnt, s); });
+  };
+  allreduce_hist(g.hist_pool.p, g.slot_stride * 2);
+  allreduce_hist(g.gs.node_sum, 2);
   EvalArgs ea{}; ea.hist_pool = g.hist_pool.p; ea.gs = g.gs; ea.cut_ptrs = dtrain->d_cut_ptrs.p; ea.feat_mask = mask; ea.p = pd; ea.F = bm.F;
   ea.ngroups = bm.ngroups; ea.tw = bm.tw; ea.ntail = bm.ntail; ea.has_missing = bm.has_missing; ea.level = 0; ea.max_level_nodes = g.max_level_nodes;
   launch_eval(ea, 1, s);
@@ -703,10 +725,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
     prof_begin(L + 1);
     launch_hist_build(ha, num_sms, s);
     prof_end();
-    {
-      GH64* lvl = g.hist_pool.p + (size_t)next_base * g.slot_stride; const size_t cnt = (size_t)next_half * g.slot_stride * 2;
-      collective([lvl, cnt, s]() { Comm::get().allreduce_sum_i64(lvl, cnt, s); });
-    }
+    allreduce_hist(g.hist_pool.p + (size_t)next_base * g.slot_stride, (size_t)next_half * g.slot_stride * 2);
     launch_subtract(g.gs, g.hist_pool.p, g.slot_stride, next_half, s);
     ea.level = L + 1;
     launch_eval(ea, 1 << (L + 1), s);
@@ -958,14 +977,14 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   for (int64_t i = 0; i < rows; ++i) { mg = std::max(mg, std::fabs(gpair_host[2 * i])); mh = std::max(mh, gpair_host[2 * i + 1]); }
   unsigned am[2]; memcpy(&am[0], &mg, 4); memcpy(&am[1], &mh, 4);
   CUDA_OK(cudaMemcpyAsync(g.gs.absmax, am, 8, cudaMemcpyHostToDevice, s));
-  launch_scales(g.gs, job_grad_bits(dm->n), s);
+  launch_scales(g.gs, job_grad_bits(g.global_n), s);
   const BinnedMatrix bm = dm->binned_view();
   HistArgs ha{}; ha.bins = bm.bins; ha.bins_tail = bm.bins_tail; ha.n = bm.n; ha.row_stride = bm.ngroups * kSlots; ha.tw = bm.tw; ha.gpair = g.gpair.p;
   ha.bins_gather = bm.bins_gather; ha.gather_stride = bm.gather_stride;
   ha.ridx = row_ids ? g.ridx0.p : nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups; ha.accumulate_sum = 1;
-  ha.force_gather = mode == 1 ? 1 : 0; ha.g_only = mode == 2 ? 1 : 0; ha.window_rows = job_window_rows(dm->n);
+  ha.force_gather = mode == 1 ? 1 : 0; ha.g_only = mode == 2 ? 1 : 0; ha.window_rows = job_window_rows(g.global_n);
   g.root_h_valid = false;                       // the debug entry point overwrites gpair and the root slot
   cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
   float total = 0.f;

@@ -244,6 +244,7 @@ int XGCommunicatorInit(const char* config) {
 int XGCommunicatorFinalize(void) { API_BEGIN(); Comm::get().finalize(); API_END(); }
 int XGCommunicatorGetRank(void) { return Comm::get().rank(); }
 int XGCommunicatorGetWorldSize(void) { return Comm::get().world(); }
+int XGB200CommPeerReduceActive(void) { return peer_reduce_active() ? 1 : 0; }
 int XGCommunicatorGetUniqueId(const char** out_hex) {
   API_BEGIN(); engine_stream(); g_ret_str = hex_encode(Comm::create_unique_id()); *out_hex = g_ret_str.c_str(); API_END();
 }

@@ -55,6 +55,7 @@ void Comm::init(const std::string& unique_id, int rank, int world) {
   comm_ = c;
 }
 void Comm::finalize() {
+  peer_reduce_close();
   if (comm_) { api().CommDestroy(static_cast<ncclComm_t>(comm_)); comm_ = nullptr; }
   rank_ = 0; world_ = 1;
 }

@@ -7,6 +7,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace b200 {
@@ -35,5 +36,13 @@ class Comm {
   int rank_ = 0, world_ = 1;
   void* comm_ = nullptr;
 };
+
+// nvlink.cu: single-kernel int64 sum all-reduce over NVLink peer memory (CUDA IPC mappings of the registered buffers).
+// setup is collective; peer_allreduce_i64 returns false when the pointer is not inside a registered buffer or peers could
+// not be mapped (different hosts, no peer access, B200XGB_NO_PEER_REDUCE): the caller then uses NCCL.
+bool peer_reduce_setup(const std::vector<std::pair<void*, size_t>>& buffers, cudaStream_t s);
+bool peer_reduce_active();
+bool peer_allreduce_i64(long long* ptr, size_t count, cudaStream_t s);
+void peer_reduce_close();
 
 }  // namespace b200

@@ -25,6 +25,8 @@ def main():
     bst = xgb.train(dict(objective=objective, max_depth=5, eta=0.3, max_bin=256), d, num_boost_round=rounds, evals=[(d, "train")],
                     evals_result=res, verbose_eval=False)
     if rank == 0:
+        with open(out + ".path", "w") as f:
+            f.write("nvlink-peer-kernel" if xgb.get_backend().comm_peer_reduce_active() else "nccl")
         bst.save_model(out)
         with open(out + ".metric", "w") as f:
             f.write(repr(list(res["train"].values())[0][-1]))

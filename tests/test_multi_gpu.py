@@ -22,15 +22,20 @@ def _ngpu():
         return 0
 
 
+@pytest.mark.parametrize("collective_path", ["nvlink-peer-kernel", "nccl"])
 @pytest.mark.parametrize("objective", ["reg:squarederror", "binary:logistic"])
-def test_two_rank_training_equals_single_gpu(xgb, tmp_path, objective):
+def test_two_rank_training_equals_single_gpu(xgb, tmp_path, objective, collective_path):
+    """Both histogram all-reduce paths (the NVLink peer-memory kernel inside the tree graph, and NCCL between graph segments)."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
+    env = dict(os.environ)
+    if collective_path == "nccl":
+        env["B200XGB_NO_PEER_REDUCE"] = "1"
     n, F, rounds = 40000, 20, 6
     out = str(tmp_path / "model.ubj")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
            "29611", os.path.join(ROOT, "tests", "helpers", "train_shard_worker.py"), out, str(n), str(F), str(rounds), objective]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     kind = "bin" if objective.startswith("binary") else "reg"
     X, y = synth(n, F, 7, kind)
@@ -43,5 +48,6 @@ def test_two_rank_training_equals_single_gpu(xgb, tmp_path, objective):
     m1, m2 = be.booster_export_model(single.handle), be.booster_export_model(multi.handle)
     assert_same_structure(m2, m1)
     np.testing.assert_array_equal(m2["split_cond"], m1["split_cond"])          # bit-identical leaves: exact integer histograms
+    assert open(out + ".path").read() == collective_path
     metric = float(open(out + ".metric").read())
     assert abs(metric - list(res["train"].values())[0][-1]) < 1e-9
