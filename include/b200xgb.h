@@ -43,6 +43,14 @@ XGB_DLL int XGBuildInfo(const char** out);
 
 /* ---- DMatrix: data_utils.py:309-313,361,384,453 ; encoder.py:52,76,87,98 ; serve_utils.py:137,205 ---------- */
 /* dense row-major float matrix, `missing` marks absent values (NaN is always missing) */
+/* upstream's Python package passes ndarray inputs as `__array_interface__` JSON ({"data":[ptr,ro],"shape":[n,m],"typestr":"<f4"}),
+ * config {"missing": NaN, "nthread": 0}; data_utils.py:384 (Parquet -> numpy), encoder.py:52 (CSV payload) reach it */
+XGB_DLL int XGDMatrixCreateFromDense(const char* data, const char* config, DMatrixHandle* out);
+/* labels / weights / base_margin from an array interface (DMatrix(label=...), data_utils.py:384) */
+XGB_DLL int XGDMatrixSetInfoFromInterface(DMatrixHandle handle, const char* field, const char* data);
+/* {"uri": "<path>?format=csv&label_column=0[&weight_column=1][&delimiter=,]" | "<path>?format=libsvm"}: data_utils.py:309-313,361;
+ * a directory means every regular file in it (data_utils.py:520-545); CSV text is parsed on the device */
+XGB_DLL int XGDMatrixCreateFromURI(const char* config, DMatrixHandle* out);
 XGB_DLL int XGDMatrixCreateFromMat(const float* data, bst_ulong nrow, bst_ulong ncol, float missing, DMatrixHandle* out);
 /* CSR; num_col = 0 means "infer from the indices" (libsvm loader: indices kept as-is, data_utils.py:348-365) */
 XGB_DLL int XGDMatrixCreateFromCSREx(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr,
@@ -102,6 +110,8 @@ XGB_DLL int XGBoosterGetStrFeatureInfo(BoosterHandle handle, const char* field, 
 /* config JSON: {"nccl_unique_id": "<hex, 128 bytes>", "rank": r, "world_size": w}; the id comes from
  * XGCommunicatorGetUniqueId on rank 0 and is shipped by the Python-side bootstrap (tracker / torch.distributed). */
 XGB_DLL int XGCommunicatorInit(const char* config);
+/* broadcast of a host buffer from `root` (distributed.py:119-136 via xgboost.collective.broadcast) */
+XGB_DLL int XGCommunicatorBroadcast(void* send_receive_buffer, size_t size, int root);
 XGB_DLL int XGCommunicatorFinalize(void);
 XGB_DLL int XGCommunicatorGetRank(void);
 XGB_DLL int XGCommunicatorGetWorldSize(void);

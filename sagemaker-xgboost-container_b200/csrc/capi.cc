@@ -4,8 +4,13 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <dirent.h>
 #include <fstream>
+#include <map>
 #include <memory>
+#include <sstream>
+#include <sys/stat.h>
 #include <string>
 #include <vector>
 #include "booster.h"
@@ -79,6 +84,135 @@ int XGDMatrixCreateFromCudaArrayInterface(const char* data, const char* config, 
   *out = guard.release();
   API_END();
 }
+// ---- host array interface (numpy `__array_interface__` as JSON): what upstream's Python package passes for ndarray inputs
+namespace {
+struct HostArray { const void* ptr; int64_t n, m; std::string typestr; };
+HostArray parse_array_interface(const char* json) {
+  JPtr a = parse_json(json);
+  HostArray h{};
+  const JValue& shape = a->at("shape");
+  if (shape.length() < 1 || shape.length() > 2) throw Error("array interface: expecting a 1- or 2-dimensional array");
+  h.n = (int64_t)shape.num_at(0); h.m = shape.length() == 2 ? (int64_t)shape.num_at(1) : 1;
+  if (a->has("strides") && a->at("strides").type != JValue::kNull) throw Error("array interface: only C-contiguous arrays are supported");
+  h.typestr = a->at("typestr").s;
+  h.ptr = reinterpret_cast<const void*>((uintptr_t)a->at("data").arr[0]->as_int());
+  return h;
+}
+std::vector<float> to_float32(const HostArray& h) {
+  const size_t cnt = (size_t)h.n * h.m;
+  std::vector<float> v(cnt);
+  const std::string& t = h.typestr;
+#define CONV(T) { const T* p = static_cast<const T*>(h.ptr); for (size_t i = 0; i < cnt; ++i) v[i] = (float)p[i]; }
+  if (t == "<f4") memcpy(v.data(), h.ptr, cnt * 4);
+  else if (t == "<f8") CONV(double) else if (t == "<i4") CONV(int32_t) else if (t == "<i8") CONV(int64_t) else if (t == "<u4") CONV(uint32_t)
+  else if (t == "<u8") CONV(uint64_t) else if (t == "<i2") CONV(int16_t) else if (t == "<u2") CONV(uint16_t) else if (t == "|i1") CONV(int8_t)
+  else if (t == "|u1" || t == "|b1") CONV(uint8_t)
+  else throw Error("array interface: unsupported typestr " + t);
+#undef CONV
+  return v;
+}
+}  // namespace
+
+int XGDMatrixCreateFromDense(const char* data, const char* config, DMatrixHandle* out) {
+  API_BEGIN();
+  HostArray h = parse_array_interface(data);
+  JPtr cfg = parse_json(config ? config : "{}");
+  float missing = cfg->has("missing") ? (float)cfg->at("missing").as_double() : std::nanf("");
+  auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
+  if (h.typestr == "<f4") box->dm = DMatrix::from_dense(static_cast<const float*>(h.ptr), h.n, (int)h.m, missing);
+  else { std::vector<float> v = to_float32(h); box->dm = DMatrix::from_dense(v.data(), h.n, (int)h.m, missing); }
+  *out = guard.release();
+  API_END();
+}
+int XGDMatrixSetInfoFromInterface(DMatrixHandle handle, const char* field, const char* data) {
+  API_BEGIN();
+  HostArray h = parse_array_interface(data);
+  std::vector<float> v = to_float32(h);
+  DM(handle)->set_float_info(field, v.data(), v.size());
+  API_END();
+}
+
+// ---- URI loader in C (data_utils.py:309-313,361 hand "<path>?format=csv&label_column=0[&weight_column=1]" / "?format=libsvm"
+// to xgb.DMatrix): every regular file of the directory; CSV text goes to the device parser, libsvm is tokenised here.
+namespace {
+std::vector<std::string> list_files(const std::string& path) {
+  struct stat st;
+  if (stat(path.c_str(), &st) != 0) throw Error("Opening " + path + " failed: No such file or directory");
+  std::vector<std::string> files;
+  if (S_ISDIR(st.st_mode)) {
+    DIR* d = opendir(path.c_str());
+    if (!d) throw Error("Opening " + path + " failed");
+    while (dirent* e = readdir(d)) { std::string f = path + "/" + e->d_name; struct stat fs; if (stat(f.c_str(), &fs) == 0 && S_ISREG(fs.st_mode)) files.push_back(f); }
+    closedir(d);
+    std::sort(files.begin(), files.end());
+    if (files.empty()) throw Error("No files found in " + path);
+  } else files.push_back(path);
+  return files;
+}
+std::string read_stripped(const std::string& f) {
+  std::ifstream in(f, std::ios::binary);
+  std::stringstream ss; ss << in.rdbuf();
+  std::string t = ss.str();
+  size_t a = 0, b = t.size();
+  while (a < b && (t[a] == '\n' || t[a] == '\r' || t[a] == ' ' || t[a] == '\t')) ++a;
+  while (b > a && (t[b - 1] == '\n' || t[b - 1] == '\r' || t[b - 1] == ' ' || t[b - 1] == '\t')) --b;
+  t = t.substr(a, b - a);
+  t.erase(std::remove(t.begin(), t.end(), '\r'), t.end());
+  return t;
+}
+}  // namespace
+
+int XGDMatrixCreateFromURI(const char* config, DMatrixHandle* out) {
+  API_BEGIN();
+  JPtr cfg = parse_json(config);
+  const std::string uri = cfg->at("uri").s;
+  const size_t qm = uri.find('?');
+  const std::string path = uri.substr(0, qm);
+  std::map<std::string, std::string> q;
+  if (qm != std::string::npos) {
+    std::stringstream ss(uri.substr(qm + 1)); std::string kv;
+    while (std::getline(ss, kv, '&')) { size_t eq = kv.find('='); if (eq != std::string::npos) q[kv.substr(0, eq)] = kv.substr(eq + 1); }
+  }
+  std::string fmt = q.count("format") ? q["format"] : (path.size() > 4 && path.substr(path.size() - 4) == ".csv" ? "csv" : "libsvm");
+  std::vector<std::string> files = list_files(path);
+  auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
+  if (fmt == "csv") {
+    const std::string d = q.count("delimiter") ? q["delimiter"] : ",";
+    if (d.size() != 1) throw Error("CSV delimiter must be a single character");
+    std::string text;
+    for (auto& f : files) { std::string t = read_stripped(f); if (t.empty()) continue; if (!text.empty()) text.push_back('\n'); text += t; }
+    if (text.empty()) throw Error("CSV input is empty");
+    int st = 0;
+    box->dm = DMatrix::from_csv_text_labeled(text.data(), (int64_t)text.size(), d[0], q.count("label_column") ? std::stoi(q["label_column"]) : -1,
+                                             q.count("weight_column") ? std::stoi(q["weight_column"]) : -1, &st);
+    if (st == 1) throw Error("CSV rows have different numbers of columns");
+    if (st != 0) throw Error("CSV contains a field the device parser cannot decide exactly (blank line, > 19 digits or malformed number)");
+  } else if (fmt == "libsvm") {
+    std::vector<size_t> indptr{0}; std::vector<unsigned> indices; std::vector<float> vals, labels;
+    for (auto& f : files) {
+      std::ifstream in(f); std::string line;
+      while (std::getline(in, line)) {
+        size_t hash = line.find('#'); if (hash != std::string::npos) line.resize(hash);
+        std::stringstream ls(line); std::string tok;
+        if (!(ls >> tok)) continue;
+        labels.push_back(std::stof(tok.substr(0, tok.find(':'))));
+        while (ls >> tok) {
+          size_t c = tok.find(':');
+          if (c == std::string::npos) throw Error("Invalid libsvm token " + tok + " in " + f);
+          if (tok.compare(0, 4, "qid:") == 0) continue;
+          indices.push_back((unsigned)std::stoul(tok.substr(0, c))); vals.push_back(std::stof(tok.substr(c + 1)));
+        }
+        indptr.push_back(indices.size());
+      }
+    }
+    if (labels.empty()) throw Error("libsvm input is empty");
+    box->dm = DMatrix::from_csr(indptr.data(), indices.data(), vals.data(), indptr.size(), indices.size(), 0);
+    box->dm->set_float_info("label", labels.data(), labels.size());
+  } else throw Error("Unknown data format in URI: " + fmt);
+  *out = guard.release();
+  API_END();
+}
+
 int XGDMatrixFree(DMatrixHandle handle) { API_BEGIN(); delete static_cast<DMatrixBox*>(handle); API_END(); }
 int XGDMatrixNumRow(DMatrixHandle handle, bst_ulong* out) { API_BEGIN(); *out = (bst_ulong)DM(handle)->n; API_END(); }
 int XGDMatrixNumCol(DMatrixHandle handle, bst_ulong* out) { API_BEGIN(); *out = (bst_ulong)DM(handle)->F; API_END(); }
@@ -239,6 +373,20 @@ int XGCommunicatorInit(const char* config) {
   std::string id = cfg->has("nccl_unique_id") ? hex_decode(cfg->at("nccl_unique_id").s) : std::string();
   engine_stream();            // binds this process to its GPU (LOCAL_RANK) before NCCL initialises
   Comm::get().init(id, rank, world);
+  API_END();
+}
+// host buffer broadcast (distributed.py:119-136 RabitHelper.synchronize reaches it through xgboost.collective.broadcast)
+int XGCommunicatorBroadcast(void* send_receive_buffer, size_t size, int root) {
+  API_BEGIN();
+  Comm& comm = Comm::get();
+  if (comm.distributed() && size > 0) {
+    cudaStream_t s = engine_stream();
+    DevBuf<unsigned char> d; d.alloc(size);
+    if (comm.rank() == root) CUDA_OK(cudaMemcpyAsync(d.p, send_receive_buffer, size, cudaMemcpyHostToDevice, s));
+    comm.broadcast_bytes(d.p, size, root, s);
+    CUDA_OK(cudaMemcpyAsync(send_receive_buffer, d.p, size, cudaMemcpyDeviceToHost, s));
+    comm.sync_stream(s);
+  }
   API_END();
 }
 int XGCommunicatorFinalize(void) { API_BEGIN(); Comm::get().finalize(); API_END(); }

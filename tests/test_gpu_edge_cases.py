@@ -63,3 +63,43 @@ def test_empty_prediction_batch_and_feature_count(xgb):
     bst = xgb.train({"objective": "reg:squarederror", "max_depth": 2}, xgb.DMatrix(X, label=X[:, 0]), num_boost_round=2, verbose_eval=False)
     assert bst.predict(xgb.DMatrix(np.zeros((0, 4), np.float32))).shape == (0,)
     assert bst.num_features() == 4
+
+
+def test_c_abi_array_interface_and_uri_constructors(xgb, tmp_path):
+    """SURVEY.md 8(b) minimum export set: XGDMatrixCreateFromDense / SetInfoFromInterface / CreateFromURI straight through ctypes,
+    the way upstream's Python package (INTEGRATION.md option B) would call them."""
+    import ctypes as C
+    import json
+    be = xgb.get_backend()
+    lib = be.lib
+    rng = np.random.default_rng(5)
+    X64 = np.ascontiguousarray(rng.standard_normal((300, 6)))               # float64 ndarray, like data_utils.py:384 after Parquet
+    y = np.ascontiguousarray(rng.random(300).astype(np.float32))
+
+    def aif(a):
+        return json.dumps({"data": [a.ctypes.data, True], "shape": list(a.shape), "typestr": a.dtype.str, "version": 3}).encode()
+    h = C.c_void_p()
+    assert lib.XGDMatrixCreateFromDense(aif(X64), json.dumps({"missing": float("nan"), "nthread": 0}).encode(), C.byref(h)) == 0, lib.XGBGetLastError()
+    assert lib.XGDMatrixSetInfoFromInterface(h, b"label", aif(y)) == 0
+    np.testing.assert_array_equal(be.dmatrix_get_raw(h).reshape(300, 6), X64.astype(np.float32))
+    np.testing.assert_array_equal(be.dmatrix_get_float_info(h, "label"), y)
+    be.dmatrix_free(h)
+    # URI: a directory with two CSV files (label first) and a libsvm file
+    d = tmp_path / "csv"
+    d.mkdir()
+    A = np.round(rng.standard_normal((50, 4)), 4)
+    (d / "a.csv").write_text("\n".join(",".join(repr(float(v)) for v in r) for r in A[:30]) + "\n")
+    (d / "b.csv").write_text("\n".join(",".join(repr(float(v)) for v in r) for r in A[30:]) + "\n")
+    h2 = C.c_void_p()
+    cfg = json.dumps({"uri": "%s?format=csv&label_column=0&delimiter=," % d, "silent": 1}).encode()
+    assert lib.XGDMatrixCreateFromURI(cfg, C.byref(h2)) == 0, lib.XGBGetLastError()
+    np.testing.assert_array_equal(be.dmatrix_get_raw(h2).reshape(50, 3), A[:, 1:].astype(np.float32))
+    np.testing.assert_array_equal(be.dmatrix_get_float_info(h2, "label"), A[:, 0].astype(np.float32))
+    be.dmatrix_free(h2)
+    f = tmp_path / "d.libsvm"
+    f.write_text("1 1:0.5 3:2\n0 2:1.5\n")
+    h3 = C.c_void_p()
+    assert lib.XGDMatrixCreateFromURI(json.dumps({"uri": "%s?format=libsvm" % f}).encode(), C.byref(h3)) == 0, lib.XGBGetLastError()
+    got = be.dmatrix_get_raw(h3).reshape(2, 4)
+    assert got[0, 1] == 0.5 and got[0, 3] == 2.0 and got[1, 2] == 1.5 and np.isnan(got[0, 0])
+    be.dmatrix_free(h3)
