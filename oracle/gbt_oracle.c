@@ -518,6 +518,25 @@ static int new_node(OrcModel* m, int64_t base, int parent) {
 /* Grow one tree on gradient column k.  [UPSTREAM src/tree/updater_quantile_hist.cc, src/tree/driver.h,
  * src/tree/hist/histogram.h (subtraction trick, build the child with the smaller hessian sum),
  * src/common/partition_builder.h (stable partition, bin <= split_bin -> left)] */
+/* child[f] = parent[f] && fewer than keep = max(1, floor(frac * |parent|)) parent features have a smaller hash (ties: lower index) */
+static void subset_mask(const uint8_t* parent, int F, float frac, uint32_t seed, uint64_t stream, uint8_t* child) {
+  if (frac >= 1.0f) { memcpy(child, parent, (size_t)F); return; }
+  int cnt = 0; for (int f = 0; f < F; ++f) cnt += parent[f] ? 1 : 0;
+  int keep = (int)floorf(frac * (float)cnt); if (keep < 1) keep = 1;
+  for (int f = 0; f < F; ++f) {
+    child[f] = 0;
+    if (!parent[f]) continue;
+    float u = rng_uniform(seed, stream, (uint64_t)f);
+    int rank = 0;
+    for (int g = 0; g < F; ++g) {
+      if (!parent[g]) continue;
+      float v = rng_uniform(seed, stream, (uint64_t)g);
+      if (v < u || (v == u && g < f)) ++rank;
+    }
+    child[f] = rank < keep;
+  }
+}
+
 /* Stable partition of the row segment [begin, begin + count) by the split (feature f, bin sb, default direction dl):
  * lefts first, rights after, both in their original order.  [UPSTREAM src/common/partition_builder.h]  Parallel over
  * row blocks (count, prefix, scatter), so that the CPU baseline scales with the host's cores like upstream's does. */
@@ -578,22 +597,24 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
   const int64_t base = m->n_nodes;
   const float* gp = t->gpair + 2 * k; const int64_t gs = 2 * K;
 
-  /* column sampling (own counter-based RNG; upstream uses std::shuffle on a mt19937, not restatable) */
-  uint8_t* tree_mask = NULL;
-  if (p->colsample_bytree < 1.0f) {
-    tree_mask = (uint8_t*)calloc((size_t)F, 1);
-    int keep = (int)fmaxf(1.0f, floorf(p->colsample_bytree * F + 0.5f));
-    /* choose the `keep` features with the smallest hash */
-    for (int f = 0; f < F; ++f) {
-      float u = rng_uniform(p->seed, 0x1000 + (uint64_t)tree_index, (uint64_t)f);
-      int rank = 0;
-      for (int g = 0; g < F; ++g) {
-        float v = rng_uniform(p->seed, 0x1000 + (uint64_t)tree_index, (uint64_t)g);
-        if (v < u || (v == u && g < f)) ++rank;
-      }
-      tree_mask[f] = rank < keep;
-    }
+  /* column sampling [UPSTREAM src/common/random.h ColumnSampler: bytree, bylevel inside it, bynode inside that; a subset keeps
+   * max(1, floor(frac * |parent|)) features].  Upstream shuffles with a mt19937 (not restatable): oracle and product keep the
+   * features of the parent set with the smallest counter-based hash instead (subset_mask). */
+  const int sampling = p->colsample_bytree < 1.0f || p->colsample_bylevel < 1.0f || p->colsample_bynode < 1.0f;
+  uint8_t* tree_mask = NULL; uint8_t* level_masks = NULL; uint8_t* node_mask = NULL;
+  const int maxd = p->max_depth > 0 ? p->max_depth : 1;
+  if (sampling) {
+    uint8_t* all = (uint8_t*)malloc((size_t)F); memset(all, 1, (size_t)F);
+    tree_mask = (uint8_t*)malloc((size_t)F);
+    subset_mask(all, F, p->colsample_bytree, p->seed, 0x1000ull + (uint64_t)tree_index, tree_mask);
+    level_masks = (uint8_t*)malloc((size_t)F * (size_t)maxd);
+    for (int d = 0; d < maxd; ++d)
+      subset_mask(tree_mask, F, p->colsample_bylevel, p->seed, 0x300000ull + 64ull * (uint64_t)tree_index + (uint64_t)d, level_masks + (size_t)d * F);
+    node_mask = (uint8_t*)malloc((size_t)F);
+    free(all);
   }
+#define NODE_MASK(depth, nid) (!sampling ? NULL : (subset_mask(level_masks + (size_t)((depth) < maxd ? (depth) : maxd - 1) * F, F, p->colsample_bynode, p->seed, \
+                               0x80000000ull + ((uint64_t)tree_index << 20) + (uint64_t)(nid), node_mask), node_mask))
 
   for (int64_t r = 0; r < n; ++r) t->ridx[r] = (uint32_t)r;
   Cand* cur = (Cand*)calloc(1, sizeof(Cand)); int ncur = 0;
@@ -608,7 +629,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
     else { for (int64_t r = 0; r < n; ++r) { G += gp[r * gs]; H += gp[r * gs + 1]; } }
     c.G = G; c.H = H; c.root_gain = calc_gain(p, G, H); c.weight = calc_weight(p, G, H);
     m->base_weight[base] = c.weight; m->sum_hess[base] = (float)H; m->split_cond[base] = p->eta * c.weight;
-    orc_eval_split(p, c.hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, tree_mask, G, H, c.root_gain, &c.split);
+    orc_eval_split(p, c.hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(0, 0), G, H, c.root_gain, &c.split);
     cur[0] = c; ncur = 1;
   }
   int num_leaves = 1;
@@ -659,7 +680,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
         for (int s = 0; s < 2; ++s) {
           Cand* ch = two[s];
           ch->root_gain = calc_gain(p, ch->G, ch->H); ch->weight = calc_weight(p, ch->G, ch->H);
-          orc_eval_split(p, ch->hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, tree_mask, ch->G, ch->H, ch->root_gain, &ch->split);
+          orc_eval_split(p, ch->hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(ch->depth, ch->nid), ch->G, ch->H, ch->root_gain, &ch->split);
           if (ch->split.loss_chg > K_RT_EPS) next[nnext++] = *ch; else { free(ch->hist); ch->hist = NULL; }
         }
       }
@@ -668,7 +689,8 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
     free(cur); cur = next; ncur = nnext;
   }
   free(cur);
-  free(tree_mask);
+  free(tree_mask); free(level_masks); free(node_mask);
+#undef NODE_MASK
   /* finalize tree + prediction cache: traverse by bins (exact for training rows) */
   m->tree_offset[m->n_trees + 1] = m->n_nodes; m->tree_info[m->n_trees] = k; m->n_trees++;
 #pragma omp parallel for schedule(static)

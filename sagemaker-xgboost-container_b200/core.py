@@ -252,10 +252,6 @@ def _check_unapplied(k, v):
         if str(v).strip("()[] ,0") != "":
             warnings.warn("%s is accepted for hyperparameter compatibility but NOT applied by the B200 hist builder" % k)
         return _DROP
-    if k in ("colsample_bylevel", "colsample_bynode"):
-        if _as_float(v, 1.0) < 1.0:
-            warnings.warn("%s=%s is NOT applied by the B200 hist builder (only colsample_bytree is); training proceeds with %s=1" % (k, v, k))
-        return _DROP
     if k == "max_bin" and _as_float(v, 256) > 256:
         warnings.warn("max_bin=%s exceeds the 256 bins per feature of the uint8 bin codes; using max_bin=256" % v)
         return 256

@@ -279,7 +279,7 @@ struct PinnedPool {
   void reset() { cur = 0; off = 0; }
 };
 
-struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds; int world, root_mode; int64_t n; };
+struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds, bynode; unsigned seed; int world, root_mode; int64_t n; };
 // The per-tree launch sequence as CUDA graphs.  On one GPU it is a single graph; with NCCL it is cut into SEGMENTS at every
 // collective (root + one per level): the segments are replayed as graphs and the all-reduces are issued between them as
 // ordinary stream operations, so no NCCL call is ever captured (a capture with lazily connecting NCCL channels hung an
@@ -302,7 +302,7 @@ struct GrowerImpl {
   DevBuf<unsigned char> tree_block;        // header + TreeArrays, copied to the host in one piece
   size_t tree_block_bytes = 0;
   DevBuf<GH64> hist_pool; DevBuf<unsigned> ridx0, ridx1, scratch;
-  DevBuf<float2> gpair, gp0, gp1; DevBuf<unsigned> tl0, tl1; DevBuf<int> err; DevBuf<unsigned char> feat_mask;
+  DevBuf<float2> gpair, gp0, gp1; DevBuf<unsigned> tl0, tl1; DevBuf<int> err, tree_index_dev; DevBuf<unsigned char> feat_mask;
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
   DevBuf<DevNode> packed; std::vector<TreeGraph> graphs; std::vector<char> eager_done;
@@ -397,14 +397,29 @@ static inline float rng_uniform(uint32_t seed, uint64_t stream, uint64_t idx) {
   uint64_t h = splitmix64(splitmix64(((uint64_t)seed << 32) ^ stream) ^ idx);
   return (float)(h >> 40) * (1.0f / 16777216.0f);
 }
-std::string colsample_mask(unsigned seed, int tree_index, int F, float frac) {
-  std::string m((size_t)F, (char)1);
-  if (frac >= 1.0f) return m;
-  int keep = (int)std::max(1.0f, std::floor(frac * F + 0.5f));
+// Column sampling (upstream src/common/random.h ColumnSampler: bytree, then bylevel inside it, then bynode inside that; a
+// subset keeps max(1, floor(frac * |parent|)) features).  Upstream shuffles with a mt19937; product and oracle share a
+// counter-based rule instead: feature f of the parent set is kept iff fewer than `keep` parent features have a smaller
+// hash u(stream, f) (ties: lower index first).  Streams: tree 0x1000 + t, level 0x300000 + 64 t + depth, node (eval kernel)
+// 0x80000000 + 2^20 t + nid.
+std::string subset_mask(const std::string& parent, float frac, unsigned seed, uint64_t stream) {
+  if (frac >= 1.0f) return parent;
+  const int F = (int)parent.size();
+  int cnt = 0; for (int f = 0; f < F; ++f) cnt += parent[f] ? 1 : 0;
+  const int keep = std::max(1, (int)std::floor(frac * (float)cnt));
   std::vector<float> u(F);
-  for (int f = 0; f < F; ++f) u[f] = rng_uniform(seed, 0x1000 + (uint64_t)tree_index, (uint64_t)f);
-  for (int f = 0; f < F; ++f) { int rank = 0; for (int g = 0; g < F; ++g) if (u[g] < u[f] || (u[g] == u[f] && g < f)) ++rank; m[f] = rank < keep ? 1 : 0; }
+  for (int f = 0; f < F; ++f) u[f] = rng_uniform(seed, stream, (uint64_t)f);
+  std::string m((size_t)F, (char)0);
+  for (int f = 0; f < F; ++f) {
+    if (!parent[f]) continue;
+    int rank = 0;
+    for (int g = 0; g < F; ++g) if (parent[g] && (u[g] < u[f] || (u[g] == u[f] && g < f))) ++rank;
+    m[f] = rank < keep ? 1 : 0;
+  }
   return m;
+}
+std::string colsample_mask(unsigned seed, int tree_index, int F, float frac) {
+  return subset_mask(std::string((size_t)F, (char)1), frac, seed, 0x1000 + (uint64_t)tree_index);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -699,6 +714,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   allreduce_hist(g.gs.node_sum, 2);
   EvalArgs ea{}; ea.hist_pool = g.hist_pool.p; ea.gs = g.gs; ea.cut_ptrs = dtrain->d_cut_ptrs.p; ea.feat_mask = mask; ea.p = pd; ea.F = bm.F;
   ea.ngroups = bm.ngroups; ea.tw = bm.tw; ea.ntail = bm.ntail; ea.has_missing = bm.has_missing; ea.level = 0; ea.max_level_nodes = g.max_level_nodes;
+  ea.colsample_bynode = mask ? param_.colsample_bynode : 1.0f; ea.seed = param_.seed; ea.tree_index = g.tree_index_dev.p;
   launch_eval(ea, 1, s);
 
   for (int L = 0; L < D; ++L) {
@@ -728,6 +744,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
     allreduce_hist(g.hist_pool.p + (size_t)next_base * g.slot_stride, (size_t)next_half * g.slot_stride * 2);
     launch_subtract(g.gs, g.hist_pool.p, g.slot_stride, next_half, s);
     ea.level = L + 1;
+    ea.feat_mask = mask ? mask + (size_t)(L + 1) * bm.F : nullptr;
     launch_eval(ea, 1 << (L + 1), s);
   }
 
@@ -744,10 +761,14 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
   cudaStream_t s = engine_stream();
   GrowerImpl& g = *grower_;
   const unsigned char* mask = nullptr;
-  if (param_.colsample_bytree < 1.0f) {
-    std::string m = colsample_mask(param_.seed, tree_index, dtrain->F, param_.colsample_bytree);
-    g.feat_mask.ensure(m.size());
-    CUDA_OK(cudaMemcpyAsync(g.feat_mask.p, m.data(), m.size(), cudaMemcpyHostToDevice, s));
+  const bool sampling = param_.colsample_bytree < 1.0f || param_.colsample_bylevel < 1.0f || param_.colsample_bynode < 1.0f;
+  if (sampling) {                               // one mask per level [max_depth][F]: bytree -> bylevel; bynode is applied inside eval_kernel
+    const std::string tm = colsample_mask(param_.seed, tree_index, dtrain->F, param_.colsample_bytree);
+    std::string all;
+    for (int d = 0; d < param_.max_depth; ++d) all += subset_mask(tm, param_.colsample_bylevel, param_.seed, 0x300000ull + 64ull * (uint64_t)tree_index + (uint64_t)d);
+    g.feat_mask.ensure(all.size()); g.tree_index_dev.ensure(1);
+    CUDA_OK(cudaMemcpyAsync(g.feat_mask.p, all.data(), all.size(), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(g.tree_index_dev.p, &tree_index, sizeof(int), cudaMemcpyHostToDevice, s));
     Comm::get().sync_stream(s);
     mask = g.feat_mask.p;
   }
@@ -780,6 +801,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     key.bins = dtrain->bins.p; key.bins_col = dtrain->bins_col.p; key.cuts = dtrain->d_cut_vals.p;     // re-binning invalidates the capture
     key.max_leaves = param_.max_leaves; key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
     key.mcw = param_.min_child_weight; key.mds = param_.max_delta_step; key.world = Comm::get().world(); key.n = dtrain->n;
+    key.bynode = param_.colsample_bynode; key.seed = param_.seed;
     if (tg.segs.empty() || memcmp(&tg.key, &key, sizeof key) != 0) {
       tg.destroy();
       const long long launches_before = g_kernel_launches;

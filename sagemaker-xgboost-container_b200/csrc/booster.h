@@ -159,5 +159,6 @@ class Booster {
 };
 
 std::string colsample_mask(unsigned seed, int tree_index, int F, float frac);   // bytes, 1 = feature usable
+std::string subset_mask(const std::string& parent, float frac, unsigned seed, uint64_t stream);
 
 }  // namespace b200

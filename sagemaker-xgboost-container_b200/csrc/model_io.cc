@@ -164,7 +164,7 @@ JPtr Booster::config_to_json() {
   JPtr gtp = JValue::Object(); gtp->set("process_type", S("default")); gtp->set("tree_method", S("hist")); gtp->set("updater", S("grow_b200_hist")); gb->set("gbtree_train_param", gtp);
   JPtr ttp = JValue::Object();
   auto f = [&](const char* k, float v) { ttp->set(k, S(float_repr(v))); }; auto i = [&](const char* k, int v) { ttp->set(k, S(std::to_string(v))); };
-  f("alpha", param_.alpha); f("colsample_bylevel", 1.0f); f("colsample_bynode", 1.0f);   /* not applied by this builder: never echo a requested value */ f("colsample_bytree", param_.colsample_bytree);
+  f("alpha", param_.alpha); f("colsample_bylevel", param_.colsample_bylevel); f("colsample_bynode", param_.colsample_bynode); f("colsample_bytree", param_.colsample_bytree);
   f("eta", param_.eta); f("gamma", param_.gamma); ttp->set("grow_policy", S("depthwise")); f("lambda", param_.lambda); i("max_bin", param_.max_bin);
   f("max_delta_step", param_.max_delta_step); i("max_depth", param_.max_depth); i("max_leaves", param_.max_leaves); f("min_child_weight", param_.min_child_weight);
   f("subsample", param_.subsample);

@@ -35,6 +35,16 @@ __device__ __forceinline__ float calc_split_gain(const TrainParamDev& p, double 
   return calc_gain_given_weight(p, GL, HL, wl) + calc_gain_given_weight(p, GR, HR, wr);
 }
 
+// counter-based RNG shared with the host and the oracle (splitmix64 on (seed, stream, index)); booster.cu subset_mask
+__device__ __forceinline__ unsigned long long splitmix64_tree(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL; return x ^ (x >> 31);
+}
+__device__ __forceinline__ float rng_uniform_tree(unsigned seed, unsigned long long stream, unsigned long long idx) {
+  unsigned long long h = splitmix64_tree(splitmix64_tree(((unsigned long long)seed << 32) ^ stream) ^ idx);
+  return (float)(h >> 40) * (1.0f / 16777216.0f);
+}
+
 // Total order of candidates == upstream SplitEntry::NeedReplace: larger loss_chg, then lower feature,
 // then earlier position in scan order (forward bins ascending, then backward bins descending).
 __device__ __forceinline__ unsigned long long cand_key(float loss, int f, int ord) {
@@ -88,7 +98,25 @@ __global__ void __launch_bounds__(32 * kEvalSegs) eval_kernel(EvalArgs a) {
   const int stride = is_tail ? a.tw : kSlots;      // accumulators per bin row
   const int slot = threadIdx.x & 31, seg = threadIdx.x >> 5;
   const int f = group * kSlots + slot;
-  const bool active = slot < stride && f < a.F && (a.feat_mask == nullptr || a.feat_mask[f] != 0);
+  bool active = slot < stride && f < a.F && (a.feat_mask == nullptr || a.feat_mask[f] != 0);
+  if (a.feat_mask != nullptr && a.colsample_bynode < 1.0f) {
+    // colsample_bynode: keep the max(1, floor(frac * |level set|)) features of the level's set with the smallest hash of this node
+    __shared__ int s_rank[32], s_cnt;
+    if (threadIdx.x < 32) s_rank[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const unsigned long long stream = 0x80000000ull + ((unsigned long long)(unsigned)*a.tree_index << 20) + (unsigned long long)nid;
+    const float uf = rng_uniform_tree(a.seed, stream, (unsigned long long)f);
+    int rank = 0, cnt = 0;
+    for (int g = seg; g < a.F; g += kEvalSegs) {
+      if (a.feat_mask[g]) { ++cnt; const float ug = rng_uniform_tree(a.seed, stream, (unsigned long long)g); rank += (ug < uf || (ug == uf && g < f)) ? 1 : 0; }
+    }
+    if (rank) atomicAdd(&s_rank[slot], rank);
+    if (slot == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    const int keep = max(1, (int)floorf(a.colsample_bynode * (float)s_cnt));
+    active = active && s_rank[slot] < keep;
+  }
   const int nbf = active ? a.cut_ptrs[f + 1] - a.cut_ptrs[f] : 0;
   const double isg = (double)a.gs.scales[2], ish = (double)a.gs.scales[3];
   const GH64 tot = a.gs.node_sum[nid];

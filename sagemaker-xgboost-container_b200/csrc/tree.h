@@ -14,6 +14,7 @@ struct TrainParamDev {
 struct EvalArgs {
   const GH64* hist_pool; GrowState gs; const int* cut_ptrs; const unsigned char* feat_mask;
   TrainParamDev p; int F, ngroups, tw, ntail, has_missing, level, max_level_nodes;
+  float colsample_bynode; unsigned seed; const int* tree_index;     // per-node feature subset inside feat_mask (the level's set); tree index in device memory (graph replay)
 };
 
 struct ApplyArgs {

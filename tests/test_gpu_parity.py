@@ -165,6 +165,27 @@ def test_training_matches_oracle(xgb, oracle, objective, kind, K, hp, n, F, roun
     np.testing.assert_allclose(margin, oracle.predict_margin(mr, X), rtol=0, atol=MARGIN_TOL)
 
 
+@pytest.mark.parametrize("hp", [dict(colsample_bytree=0.5), dict(colsample_bylevel=0.5), dict(colsample_bynode=0.3),
+                                dict(colsample_bytree=0.8, colsample_bylevel=0.7, colsample_bynode=0.6, subsample=0.8)])
+def test_column_and_row_sampling_match_the_oracle(xgb, oracle, hp):
+    """colsample_bytree / bylevel / bynode (nested like upstream's ColumnSampler, counter-based RNG shared with the oracle) and
+    subsample: same trees as the oracle, and the sampled models really differ from the unsampled one."""
+    X, y = synth(20000, 40, 35, "reg")
+    params = dict(objective="reg:squarederror", max_depth=5, eta=0.3, max_bin=256, seed=11, **hp)
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=6, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, 6).model()
+    assert first_structural_difference(m, mr) is None
+    assert_same_structure(m, mr)
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    plain = oracle.train(dict(objective="reg:squarederror", max_depth=5, eta=0.3, max_bin=256, seed=11), X, y, 6).model()
+    assert not np.array_equal(plain["split_index"], mr["split_index"])
+    cfg = __import__("json").loads(bst.save_config())["learner"]["gradient_booster"]["tree_train_param"]
+    for k, v in hp.items():
+        assert abs(float(cfg[k]) - v) < 1e-6                      # applied values are echoed by save_config
+
+
 def test_logitraw_with_minority_positive_class(xgb, oracle):
     """binary:logitraw with mean(y) < 0.5: the estimated base score must give a finite base margin (the stump
     weight), trees must split, and the model must match the oracle."""
