@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--max-depth", type=int, default=6)
     ap.add_argument("--max-bin", type=int, default=256)
     ap.add_argument("--seed", type=int, default=43)
-    ap.add_argument("--cpu-sample-rows", type=int, default=4_000_000, help="rows of the cpu_baseline leg of the default arm")
+    ap.add_argument("--cpu-sample-rows", type=int, default=10_000_000, help="rows of the cpu_baseline leg of the default arm")
     ap.add_argument("--reference-rows", type=int, default=0, help="rows of the --impl reference arm (first blocks of the same generator); 0 = all rows: "
                     "the full 50M x 100 job takes ~3.7 s per round on 128 host threads, ~3.5 min for 5 + 20 rounds incl. generation, cuts and binning")
     ap.add_argument("--job-rounds", type=int, default=200)
