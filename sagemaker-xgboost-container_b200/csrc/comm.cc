@@ -81,7 +81,7 @@ void Comm::sync_stream(cudaStream_t s) {
   const auto t0 = std::chrono::steady_clock::now();
   for (unsigned spin = 0;; ++spin) {
     cudaError_t q = cudaStreamQuery(s);
-    if (q == cudaSuccess) return;
+    if (q == cudaSuccess) { peer_reduce_check(); return; }
     if (q != cudaErrorNotReady) CUDA_OK(q);
     if ((spin & 63) == 63) {
       ncclResult_t ar = ncclSuccess;

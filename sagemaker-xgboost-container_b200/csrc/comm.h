@@ -44,5 +44,6 @@ bool peer_reduce_setup(const std::vector<std::pair<void*, size_t>>& buffers, cud
 bool peer_reduce_active();
 bool peer_allreduce_i64(long long* ptr, size_t count, cudaStream_t s);
 void peer_reduce_close();
+void peer_reduce_check();           // throws when a peer barrier timed out (called after stream waits)
 
 }  // namespace b200

@@ -33,7 +33,9 @@ struct PeerFlags {                 // one page per rank, written by its peers
   unsigned done[kPeerMax];         // done[src]:  src has stored all its sums of call `epoch`
   unsigned epoch;                  // calls completed so far + 1 == stamp of the call in flight
   unsigned arrived;                // CTAs of this rank that finished their slice in the call in flight
+  unsigned timed_out;              // set when a barrier wait exceeded kPeerSpinCycles (a peer died or never launched): the host turns it into an error
 };
+constexpr long long kPeerSpinCycles = 60ll * 2000000000ll;      // ~60 s at 2 GHz: far beyond any skew between healthy ranks
 
 struct PeerArgs {
   long long* bufs[kPeerMax];       // the same buffer on every rank (own + mapped peers), base pointers
@@ -49,6 +51,14 @@ __device__ __forceinline__ longlong2 ld_volatile_v2(const long long* p) {
   longlong2 v; asm volatile("ld.volatile.global.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory"); return v;
 }
 
+// bounded spin on a flag written by a peer: a rank that never arrives must not wedge this GPU for ever
+__device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned e, unsigned* timed_out) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < e) {
+    if (clock64() - t0 > kPeerSpinCycles) { *timed_out = 1u; break; }
+  }
+}
+
 __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a) {
   PeerFlags* mine = a.flags[a.rank];
   __shared__ unsigned s_epoch;
@@ -57,7 +67,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a
   const unsigned e = s_epoch;
   // ---- ready barrier: my inputs were produced by earlier kernels of this stream, hence complete; tell everyone, wait for everyone
   if (blockIdx.x == 0 && threadIdx.x < a.world) st_release_sys(&a.flags[threadIdx.x]->ready[a.rank], e);
-  if (threadIdx.x < a.world) { while (ld_acquire_sys(&mine->ready[threadIdx.x]) < e) { } }
+  if (threadIdx.x < a.world) wait_flag(&mine->ready[threadIdx.x], e, &mine->timed_out);
   __syncthreads();
   // ---- my slice: [lo, hi) in units of (g,h) pairs
   const size_t pairs = a.count / 2;
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(PeerArgs a
   __syncthreads();
   if (s_last && threadIdx.x < a.world) st_release_sys(&a.flags[threadIdx.x]->done[a.rank], e);
   if (blockIdx.x == 0) {
-    if (threadIdx.x < a.world) { while (ld_acquire_sys(&mine->done[threadIdx.x]) < e) { } }
+    if (threadIdx.x < a.world) wait_flag(&mine->done[threadIdx.x], e, &mine->timed_out);
     __syncthreads();
     // every rank has stored its sums and (to get here) read its inputs: the buffer may be reused; open the next call
     if (threadIdx.x == 0) st_release_sys(&mine->epoch, e + 1u);
@@ -166,6 +176,14 @@ bool peer_reduce_setup(const std::vector<std::pair<void*, size_t>>& buffers, cud
 }
 
 bool peer_reduce_active() { return g_peer.active; }
+
+// after a stream wait: did a peer barrier give up?  (cheap: 4 bytes, only while the peer path is active)
+void peer_reduce_check() {
+  if (!g_peer.active || !g_peer.my_flags) return;
+  unsigned v = 0;
+  if (cudaMemcpy(&v, &g_peer.my_flags->timed_out, 4, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
+  if (v) { g_peer.active = false; throw Error("NVLink peer all-reduce timed out waiting for rank(s) that never reached the collective"); }
+}
 
 // in-place sum over ranks of `count` int64 at `ptr` (inside a registered buffer); false = not registered / inactive (caller uses NCCL)
 bool peer_allreduce_i64(long long* ptr, size_t count, cudaStream_t s) {

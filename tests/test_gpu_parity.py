@@ -205,6 +205,30 @@ def test_logitraw_with_minority_positive_class(xgb, oracle):
     np.testing.assert_allclose(margin.reshape(len(y), -1), oracle.predict_margin(mr, X), rtol=0, atol=MARGIN_TOL)
 
 
+@pytest.mark.parametrize("objective,kind,K,n,F,rounds", [
+    ("reg:squarederror", "reg", 1, 2_000_000, 100, 3),       # BASELINE config 3 family (3 groups + tail, 18-bit grid, several overflow windows per CTA)
+    ("binary:logistic", "bin", 1, 1_500_000, 28, 3),         # config 2 family
+    ("multi:softprob", "multi", 10, 600_000, 50, 2),         # config 4 family: 10 classes
+])
+def test_full_model_parity_at_baseline_shape_families(xgb, oracle, objective, kind, K, n, F, rounds):
+    """Whole-model parity on the BASELINE.json shapes at the largest size the oracle finishes in about a minute: max_depth 6,
+    256 bins, structure identical, leaves within 1e-5, pred_leaf bit-exact."""
+    X, y = synth(n, F, 77, kind, K=max(K, 1))
+    params = dict(objective=objective, tree_method="hist", max_depth=6, max_bin=256, eta=0.3)
+    if K > 1:
+        params["num_class"] = K
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=rounds, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, rounds).model()
+    assert len(m["tree_info"]) == rounds * max(K, 1)
+    assert first_structural_difference(m, mr) is None
+    assert_same_structure(m, mr)
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    sub = np.arange(0, n, 97)
+    np.testing.assert_array_equal(bst.predict(xgb.DMatrix(X[sub]), pred_leaf=True).astype(np.int32), oracle.predict_leaf(mr, X[sub]))
+
+
 def test_training_with_missing_values(xgb, oracle):
     X, y = synth(15000, 12, 41, "reg", quantised=False, missing_frac=0.15)
     params = dict(objective="reg:squarederror", max_depth=5, eta=0.3, max_bin=64)
