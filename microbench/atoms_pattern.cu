@@ -6,24 +6,28 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o atoms_pattern atoms_pattern.cu
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("CUDA error %s at %d\n",cudaGetErrorString(e),__LINE__); return 1;}}while(0)
 
-template <int PAT, int NA>
+template <int PAT, int NA, int HOFF = 32768>
 __global__ void __launch_bounds__(1024) kern(int iters, const uint4* __restrict__ src, unsigned long long* sink, long long* cyc) {
-  extern __shared__ __align__(16) int smem[];      // G[256][32] then H[256][32]
-  for (int i = threadIdx.x; i < 2 * 8192; i += blockDim.x) smem[i] = 0;
+  extern __shared__ __align__(16) int smem[];      // G[256][32] then H[256][32] (x3 groups for PAT 3)
+  constexpr int NGRP = PAT == 3 ? 3 : 1;
+  for (int i = threadIdx.x; i < NGRP * 2 * 8192 + 64; i += blockDim.x) smem[i] = 0;
   __syncthreads();
   const unsigned base = (unsigned)__cvta_generic_to_shared(smem);
   const int lane = threadIdx.x & 31;
   unsigned A[16], S[4];
-  const int rot = lane >> 1, half = lane & 1, qw = rot >> 2, qb = rot & 3;
-  for (int jb = 0; jb < 4; ++jb) S[jb] = PAT == 2 ? (0x4440u | ((jb + qb) & 3)) : (0x4440u | jb);
+  int rot = lane >> 1, half = lane & 1; unsigned gbase = 0;
+  if (PAT == 3) { const int q = lane / 6, c = lane % 6; rot = q < 5 ? 3 * q + (c >> 1) : 15; half = c & 1; gbase = q < 5 ? (unsigned)(c >> 1) * 65536u : 0u; }
+  const int qw = rot >> 2, qb = rot & 3;
+  for (int jb = 0; jb < 4; ++jb) S[jb] = PAT >= 2 ? (0x4440u | ((jb + qb) & 3)) : (0x4440u | jb);
   for (int jw = 0; jw < 4; ++jw) for (int jb = 0; jb < 4; ++jb) {
     const int step = 4 * jw + jb;
     if (PAT == 0) A[step] = base + 4u * lane;
     else if (PAT == 1) A[step] = base + 4u * ((lane + step) & 31);
-    else A[step] = base + 64u * half + 16u * ((jw + qw) & 3) + 4u * ((jb + qb) & 3);
+    else A[step] = base + gbase + 64u * half + 16u * ((jw + qw) & 3) + 4u * ((jb + qb) & 3);
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(A[i]));
@@ -44,26 +48,26 @@ __global__ void __launch_bounds__(1024) kern(int iters, const uint4* __restrict_
         const unsigned bin = __byte_perm(ww[jw], 0u, S[jb]);
         const unsigned addr = (bin << 7) + A[4 * jw + jb];
         asm volatile("red.shared.add.s32 [%0], %1;" :: "r"(addr), "r"(g) : "memory");
-        if (NA == 2) asm volatile("red.shared.add.u32 [%0+32768], %1;" :: "r"(addr), "r"(h) : "memory");
+        if (NA == 2) asm volatile("red.shared.add.u32 [%0+%2], %1;" :: "r"(addr), "r"(h), "n"(HOFF) : "memory");
       }
     w = nw;
   }
   long long t1 = clock64();
   __syncthreads();
   unsigned long long acc = 0;
-  for (int i = threadIdx.x; i < 2 * 8192; i += blockDim.x) acc += (unsigned)smem[i];
+  for (int i = threadIdx.x; i < NGRP * 2 * 8192; i += blockDim.x) acc += (unsigned)smem[i];
   if (acc == 0xdeadbeefULL) sink[0] = acc;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-template <int PAT, int NA> int run(const char* name, int threads, const uint4* src) {
+template <int PAT, int NA, int HOFF = 32768> int run(const char* name, int threads, const uint4* src) {
   int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
-  const int iters = 4000; size_t smem = 2 * 8192 * 4;
-  CK(cudaFuncSetAttribute(kern<PAT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int iters = 4000; size_t smem = (PAT == 3 ? 3 : 1) * 2 * 8192 * 4 + 256;
+  CK(cudaFuncSetAttribute(kern<PAT, NA, HOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned long long* sink; long long* cyc; CK(cudaMalloc(&sink, 8)); CK(cudaMalloc(&cyc, 8 * nsm));
-  kern<PAT, NA><<<nsm, threads, smem>>>(iters / 4, src, sink, cyc); CK(cudaDeviceSynchronize());
+  kern<PAT, NA, HOFF><<<nsm, threads, smem>>>(iters / 4, src, sink, cyc); CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  cudaEventRecord(e0); kern<PAT, NA><<<nsm, threads, smem>>>(iters, src, sink, cyc); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+  cudaEventRecord(e0); kern<PAT, NA, HOFF><<<nsm, threads, smem>>>(iters, src, sink, cyc); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   long long hc[256]; CK(cudaMemcpy(hc, cyc, 8 * nsm, cudaMemcpyDeviceToHost));
   double avg = 0; for (int i = 0; i < nsm; i++) avg += hc[i]; avg /= nsm;
@@ -79,6 +83,16 @@ int main() {
     uint32_t* h = (uint32_t*)malloc(n * 16); uint32_t s = 12345u;
     for (size_t i = 0; i < n * 4; ++i) { s = s * 1664525u + 1013904223u; h[i] = s ^ (s >> 13); }
     CK(cudaMemcpy(src, h, n * 16, cudaMemcpyHostToDevice)); free(h);
+  }
+  if (getenv("ATOMS_PAIR_ONLY")) {          // pair variants only (short list for an ncu capture)
+    run<2, 2>("P2 hist.cu lane table    2xATOMS", 768, src);
+    run<2, 2, 32768 + 64>("P2 + H plane shifted 16 banks   ", 768, src);
+    run<2, 2, 32768 + 4>("P2 + H plane shifted 1 bank     ", 768, src);
+    run<3, 2>("P3 gather NG=3 mapping   2xATOMS", 768, src);
+    run<3, 2, 32768 + 64>("P3 + H plane shifted 16 banks   ", 768, src);
+    run<3, 1>("P3 gather NG=3 mapping   1xATOMS", 768, src);
+    run<0, 2, 32768 + 64>("P0 + H plane shifted 16 banks   ", 768, src);
+    return 0;
   }
   for (int thr : {256, 768, 1024}) {
     run<0, 1>("P0 fixed lane==bank      1xATOMS", thr, src);

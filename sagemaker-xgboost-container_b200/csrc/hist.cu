@@ -181,6 +181,28 @@ __device__ __forceinline__ void rotate_words(const LaneConst& lc, const uint4& w
   ww[0] = w0; ww[1] = w1; ww[2] = w2; ww[3] = w3;
 }
 
+// The gather kernel is register-bound, not issue-bound: it rotates the BYTES of the data too (one funnel shift per word) and
+// uses immediate PRMT selectors, so the four selector registers of LaneConst are never live there
+__device__ __forceinline__ void rotate_words_bytes(int qw, int qb8, const uint4& w, unsigned (&ww)[4]) {
+  unsigned w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
+  if (qw & 1) { unsigned x = w0; w0 = w1; w1 = w2; w2 = w3; w3 = x; }
+  if (qw & 2) { unsigned x = w0; w0 = w2; w2 = x; x = w1; w1 = w3; w3 = x; }
+  ww[0] = __funnelshift_r(w0, w0, qb8); ww[1] = __funnelshift_r(w1, w1, qb8); ww[2] = __funnelshift_r(w2, w2, qb8); ww[3] = __funnelshift_r(w3, w3, qb8);
+}
+template <int GOFF>
+__device__ __forceinline__ void accumulate16_pairs_prerotated(const unsigned (&A)[16], const unsigned (&ww)[4], int gq, unsigned hq) {
+#pragma unroll
+  for (int jw = 0; jw < 4; ++jw) {
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb) {
+      const unsigned bin = (ww[jw] >> (8 * jb)) & 0xffu;            // byte jb of the byte-rotated word == byte (jb + qb) & 3 of the original
+      const unsigned addr = (bin << 7) + A[4 * jw + jb];
+      red_shared_s32_off<GOFF>(addr, gq);
+      red_shared_u32_off<GOFF + 32768>(addr, hq);
+    }
+  }
+}
+
 // 16 conflict-free atomic (pairs) of one lane's 16 bin bytes (already word-rotated) into the planes at byte offset GOFF
 template <bool GONLY, int GOFF>
 __device__ __forceinline__ void accumulate16(const LaneConst& lc, const unsigned (&ww)[4], int gq, unsigned hq) {
@@ -213,6 +235,28 @@ __device__ __forceinline__ void tail_accumulate(const TailConst& tc, int lane, u
       if (!GONLY) red_shared_u32(addr + tc.hplane_bytes, hq);
     }
   }
+}
+
+// Same with the tail geometry known at compile time (gather kernel: everything but the lane's base address folds into immediates)
+template <int TW, int TREP>
+__device__ __forceinline__ void tail_accumulate_ct(unsigned base_rep, int lane, unsigned w0, unsigned w1, int gq, unsigned hq) {
+  constexpr unsigned kBinStride = (unsigned)(TW * TREP) * 4u, kHPlane = 256u * kBinStride;
+#pragma unroll
+  for (int j = 0; j < TW; ++j) {
+    const unsigned slot = (unsigned)(j + lane) & (unsigned)(TW - 1);
+    const unsigned bin = __byte_perm(w0, w1, slot) & 0xffu;
+    const unsigned addr = base_rep + bin * kBinStride + slot * 4u;
+    red_shared_s32(addr, gq);
+    red_shared_u32(addr + kHPlane, hq);
+  }
+}
+
+// warp-reduce one window's worth of per-lane (g, h) sums (32-bit is enough per window) into the node's int64 totals
+__device__ __forceinline__ void flush_node_sum(GH64* dst, int g, unsigned h, int lane) {
+  long long G = g, H = h;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { G += __shfl_xor_sync(0xffffffffu, G, o); H += __shfl_xor_sync(0xffffffffu, H, o); }
+  if (lane == 0 && (G != 0 || H != 0)) { red_global_s64(&dst->g, G); red_global_s64(&dst->h, H); }
 }
 
 // Spill / flush pass over the CTA's accumulators.  Between windows only accumulators that could overflow in the next
@@ -429,7 +473,8 @@ hist_root_kernel(const __grid_constant__ CUtensorMap tm, HistArgs a, RootCfg c) 
 // ---------------------------------------------------------------------------------------------
 // Deeper levels (and the fallback for the root): rows gathered by row id, register-staged.
 // ---------------------------------------------------------------------------------------------
-struct Stage { unsigned id; float2 gh; unsigned t0, t1; };
+template <int TW> struct Stage { unsigned id; float2 gh; unsigned t0; };
+template <> struct Stage<8> { unsigned id; float2 gh; unsigned t0, t1; };
 
 // tail planes [bin][trep][tw] of the gather kernel: 32 KB (G + H, trep * tw = 16) fit next to three groups, 64 KB otherwise
 __host__ __device__ constexpr int gather_tail_replicas(int ng) { return ng >= 3 ? 4 : 8; }
@@ -440,8 +485,9 @@ __host__ __device__ constexpr int gather_tail_bytes(int ng) { return ng >= 3 ? 3
 // cost ~2.6 bursts), i.e. 16 / 8 / 5 rows per instruction for NG = 1 / 2 / 3 (NG = 3 leaves lanes 30, 31 idle).  Lane (row q,
 // chunk c) owns group c >> 1, half c & 1 and the slot rotation NG * q + (c >> 1): the <= 16 lanes that share a half have
 // distinct rotations, so every ATOMS instruction is still bank-conflict free.
-template <int NG, bool TAIL, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_gather_kernel(HistArgs a) {
+template <int NG, int TW, int NTHREADS>       // TW: tail width this instantiation handles (0 = none, 4, 8)
+__global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TW ? 1 : 3) : 1) hist_gather_kernel(HistArgs a) {
+  constexpr bool TAIL = TW != 0;
   constexpr int NWARPS = NTHREADS / 32;
   constexpr int LPR = 2 * NG, RPI = 32 / LPR, U = 2 * NG;                  // lanes per row, rows per instruction, units per super-tile
   constexpr int SUP = RPI * U;                                             // positions per super-tile: 32, 32, 30
@@ -474,17 +520,17 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q = lane / LPR, c = lane - q * LPR;                            // row inside a unit, 16 B chunk inside the row
   const bool lane_on = q < RPI && (c >> 1) < ng_here;                       // idle lanes add zeros to a slot rotation nobody else uses
-  const LaneConst lc = make_lane_const_rot(q < RPI ? NG * q + (c >> 1) : 15, c & 1, smem_g + (unsigned)((q < RPI ? (c >> 1) : 0) * 2 * kPlaneBytes));
+  const int rot = q < RPI ? NG * q + (c >> 1) : 15;
+  const LaneConst lc = make_lane_const_rot(rot, c & 1, smem_g + (unsigned)((q < RPI ? (c >> 1) : 0) * 2 * kPlaneBytes));
+  const int rot_qw = rot >> 2, rot_qb8 = (rot & 3) * 8;
   const uint8_t* gbins = (aligned ? a.bins_gather : a.bins) + (int64_t)g0 * kSlots + c * 16;
-  TailConst tc;
-  constexpr int TREP = gather_tail_replicas(NG);          // replicas of the tail planes that fit next to the main planes
-  tc.tw = TAIL ? a.tw : 4;
-  const int trep = min(TREP, gather_tail_bytes(NG) / (2 * 256 * 4 * tc.tw));
-  tc.base_g = smem_g + (unsigned)(NG * 2 * kPlaneBytes); tc.hplane_bytes = 256u * (unsigned)(tc.tw * trep) * 4u;
-  tc.bin_stride = (unsigned)(tc.tw * trep) * 4u; tc.rep_off = (unsigned)((lane / tc.tw) % trep) * (unsigned)tc.tw * 4u;
+  // tail planes [bin][trep][tw] behind the main planes; as many replicas as fit next to them
+  constexpr int TWC = TAIL ? TW : 4;
+  constexpr int trep = gather_tail_replicas(NG) < gather_tail_bytes(NG) / (2 * 256 * 4 * TWC) ? gather_tail_replicas(NG) : gather_tail_bytes(NG) / (2 * 256 * 4 * TWC);
+  const unsigned tail_base_rep = smem_g + (unsigned)(NG * 2 * kPlaneBytes) + (unsigned)((lane / TWC) % trep) * (unsigned)TWC * 4u;
 
   {
-    const int words4 = (NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * tc.tw * trep * 4 : 0)) / 16;
+    const int words4 = (NG * 2 * kPlaneBytes + (TAIL ? 2 * 256 * TWC * trep * 4 : 0)) / 16;
     for (int i = threadIdx.x; i < words4; i += NTHREADS) reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
   }
   __syncthreads();
@@ -493,7 +539,7 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
   { int lo = 0, hi = nb; while (lo < hi) { int mid = (lo + hi) >> 1; if (a.build_prefix[mid + 1] > r0) hi = mid; else lo = mid + 1; } b = lo; }
 
   const size_t slot_entries = (size_t)a.ngroups * kGroupEntries + (size_t)256 * a.tw;
-  const Stage none{0xffffffffu, make_float2(0.f, 0.f), 0u, 0u};
+  typedef Stage<TW> StageT;
   while (r0 < r1) {
     const unsigned nbeg = a.build_prefix[b], nend_node = a.build_prefix[b + 1];
     const unsigned nend = nend_node < r1 ? nend_node : r1;
@@ -502,7 +548,7 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
     GH64* out_slot = a.hist_pool + (size_t)a.hist_slot[nid] * slot_entries;
     GH64* out_main = out_slot + (size_t)g0 * kGroupEntries;
     GH64* out_tail = out_slot + (size_t)a.ngroups * kGroupEntries;
-    long long accG = 0, accH = 0;
+    int accG = 0; unsigned accH = 0;          // this lane's (g, h) since the last overflow check: <= iters_per_window rows, far from 32 bits
     const unsigned pa = seg + (r0 - nbeg), pb = seg + (nend - nbeg);
     const unsigned nsuper = (pb - pa + SUP - 1) / SUP;
     const unsigned iters = (nsuper + NWARPS - 1) / NWARPS;          // same for every warp: barriers stay aligned
@@ -512,15 +558,16 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
     //   bin chunks (one LDG.128 per lane and unit) one super-tile ahead, ROLLING: the register of unit k is refilled with
     //   unit k of the next super-tile right after it has been consumed (U loads in flight per lane at all times);
     //   conflict-free ATOMS pairs now.
-    auto load_ids = [&](unsigned st) -> Stage {
-      Stage s_ = none;
+    auto load_ids = [&](unsigned st) -> StageT {
+      StageT s_; s_.id = 0xffffffffu; s_.gh = make_float2(0.f, 0.f); s_.t0 = 0u;
+      if constexpr (TW == 8) s_.t1 = 0u;
       unsigned p = pa + st * SUP + lane;
       if (lane < SUP && st < nsuper && p < pb) {
         s_.id = a.ridx ? __ldg(a.ridx + p) : p; s_.gh = ldg_nc_f2(a.gpair + p);
         if (TAIL && has_tail) {
-          if (a.tail_pos) s_.t0 = ldg_nc_u32(a.tail_pos + p);                       // tail bytes travel with the row ids (tw == 4)
-          else if (tc.tw == 4) s_.t0 = ldg_nc_u32(a.bins_tail + (int64_t)s_.id * 4);
-          else { const uint2 v = ldg_nc_v2(a.bins_tail + (int64_t)s_.id * 8); s_.t0 = v.x; s_.t1 = v.y; }
+          if constexpr (TW == 8) { const uint2 v = ldg_nc_v2(a.bins_tail + (int64_t)s_.id * 8); s_.t0 = v.x; s_.t1 = v.y; }
+          else if (a.tail_pos) s_.t0 = ldg_nc_u32(a.tail_pos + p);                  // tail bytes travel with the row ids (tw == 4)
+          else s_.t0 = ldg_nc_u32(a.bins_tail + (int64_t)s_.id * 4);
         }
       }
       return s_;
@@ -529,14 +576,14 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
       const unsigned rid = __shfl_sync(0xffffffffu, ids, q < RPI ? k * RPI + q : 0);
       return (lane_on && rid != 0xffffffffu) ? ldg_nc_v4(gbins + (int64_t)rid * row_stride) : make_uint4(0, 0, 0, 0);
     };
-    Stage cur = load_ids(warp);
-    Stage nxt = load_ids(warp + NWARPS);
+    StageT cur = load_ids(warp);
+    StageT nxt = load_ids(warp + NWARPS);
     uint4 w[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) w[k] = load_unit(cur.id, k);
     for (unsigned it = 0; it < iters; ++it) {
       const unsigned s = warp + it * NWARPS;
-      Stage nn = load_ids(s + 2 * NWARPS);
+      StageT nn = load_ids(s + 2 * NWARPS);
       const bool active = s < nsuper;
       const int gq_l = __float2int_rn(cur.gh.x * sg);
       const unsigned hq_l = (unsigned)__float2int_rn(cur.gh.y * sh);
@@ -548,29 +595,26 @@ __global__ void __launch_bounds__(NTHREADS, NG == 1 ? (TAIL ? 1 : 3) : 1) hist_g
           unsigned hq = __shfl_sync(0xffffffffu, hq_l, q < RPI ? k * RPI + q : 0);
           if (!lane_on) { gq = 0; hq = 0; }
           unsigned ww[4];
-          rotate_words(lc, w[k], ww);
-          accumulate16<false, 0>(lc, ww, gq, hq);
+          rotate_words_bytes(rot_qw, rot_qb8, w[k], ww);
+          accumulate16_pairs_prerotated<0>(lc.A, ww, gq, hq);
         }
         w[k] = load_unit(nxt.id, k);
       }
-      if (TAIL) { if (active && has_tail) tail_accumulate<false>(tc, lane, cur.t0, cur.t1, gq_l, hq_l); }
+      if constexpr (TAIL) { if (active && has_tail) { unsigned t1 = 0; if constexpr (TW == 8) t1 = cur.t1; tail_accumulate_ct<TWC, trep>(tail_base_rep, lane, cur.t0, t1, gq_l, hq_l); } }
       cur = nxt; nxt = nn;
       if ((it + 1) % iters_per_window == 0 && it + 1 < iters) {       // overflow check: at most kWindowRows rows since the last one
+        if (a.accumulate_sum && blockIdx.y == 0) { flush_node_sum(a.node_sum + nid, accG, accH, lane); accG = 0; accH = 0; }
         __syncthreads();
         spill_main<2>(smem, ng_here, out_main, false, threadIdx.x, NTHREADS);
-        if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, trep, out_tail, false, threadIdx.x, NTHREADS);
+        if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, TWC, trep, out_tail, false, threadIdx.x, NTHREADS);
         __syncthreads();
       }
     }
     __syncthreads();
     spill_main<2>(smem, ng_here, out_main, true, threadIdx.x, NTHREADS);
-    if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, tc.tw, trep, out_tail, true, threadIdx.x, NTHREADS);
+    if (has_tail) spill_tail<2>(smem + NG * 2 * kGroupEntries, TWC, trep, out_tail, true, threadIdx.x, NTHREADS);
     __syncthreads();
-    if (a.accumulate_sum && blockIdx.y == 0) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { accG += __shfl_xor_sync(0xffffffffu, accG, o); accH += __shfl_xor_sync(0xffffffffu, accH, o); }
-      if (lane == 0 && (accG != 0 || accH != 0)) { red_global_s64(&a.node_sum[nid].g, accG); red_global_s64(&a.node_sum[nid].h, accH); }
-    }
+    if (a.accumulate_sum && blockIdx.y == 0) flush_node_sum(a.node_sum + nid, accG, accH, lane);
     r0 = nend; ++b;
   }
 }
@@ -646,25 +690,27 @@ static bool get_tensor_map(const uint8_t* bins, int64_t n, int row_stride, int b
   return true;
 }
 
-template <int NG, bool TAIL, int NT> static void set_gather_attr() {
-  CUDA_OK(cudaFuncSetAttribute(hist_gather_kernel<NG, TAIL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * 2 * kPlaneBytes + (TAIL ? gather_tail_bytes(NG) : 0)));
+template <int NG, int TW, int NT> static void set_gather_attr() {
+  CUDA_OK(cudaFuncSetAttribute(hist_gather_kernel<NG, TW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NG * 2 * kPlaneBytes + (TW ? gather_tail_bytes(NG) : 0)));
 }
 
 void hist_configure() {
   static bool configured = false;
   if (configured) return;
-  set_gather_attr<1, false, 256>(); set_gather_attr<1, true, 256>();
-  set_gather_attr<2, false, 768>(); set_gather_attr<2, true, 768>();
-  set_gather_attr<3, false, 768>(); set_gather_attr<3, true, 768>();
+  set_gather_attr<1, 0, 256>(); set_gather_attr<1, 4, 256>(); set_gather_attr<1, 8, 256>();
+  set_gather_attr<2, 0, 768>(); set_gather_attr<2, 4, 768>(); set_gather_attr<2, 8, 768>();
+  set_gather_attr<3, 0, 768>(); set_gather_attr<3, 4, 768>(); set_gather_attr<3, 8, 768>();
   CUDA_OK(cudaFuncSetAttribute(hist_root_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   CUDA_OK(cudaFuncSetAttribute(hist_root_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   configured = true;
 }
 
-template <int NG, bool TAIL, int NT>
+template <int NG, int NT>
 static void launch_gather(const HistArgs& a, int gx, int nchunks, cudaStream_t stream) {
-  const int smem = NG * 2 * kPlaneBytes + (TAIL ? gather_tail_bytes(NG) : 0);
-  hist_gather_kernel<NG, TAIL, NT><<<dim3(gx, nchunks), NT, smem, stream>>>(a);
+  const int smem = NG * 2 * kPlaneBytes + (a.tw ? gather_tail_bytes(NG) : 0);
+  if (a.tw == 0) hist_gather_kernel<NG, 0, NT><<<dim3(gx, nchunks), NT, smem, stream>>>(a);
+  else if (a.tw == 4) hist_gather_kernel<NG, 4, NT><<<dim3(gx, nchunks), NT, smem, stream>>>(a);
+  else hist_gather_kernel<NG, 8, NT><<<dim3(gx, nchunks), NT, smem, stream>>>(a);
 }
 
 void launch_hist_build(const HistArgs& a_in, int num_sms, cudaStream_t stream) {
@@ -692,11 +738,10 @@ void launch_hist_build(const HistArgs& a_in, int num_sms, cudaStream_t stream) {
   if (ng == 1) {
     const int per_sm = tail ? 1 : 3;          // 64 KB of planes (+ 64 KB of replicated tail planes) per CTA
     const int gx = (num_sms * per_sm + nchunks - 1) / nchunks;
-    if (tail) launch_gather<1, true, 256>(a, gx, nchunks, stream); else launch_gather<1, false, 256>(a, gx, nchunks, stream);
+    launch_gather<1, 256>(a, gx, nchunks, stream);
   } else {
     const int gx = (num_sms + nchunks - 1) / nchunks;
-    if (ng == 2) { if (tail) launch_gather<2, true, 768>(a, gx, nchunks, stream); else launch_gather<2, false, 768>(a, gx, nchunks, stream); }
-    else { if (tail) launch_gather<3, true, 768>(a, gx, nchunks, stream); else launch_gather<3, false, 768>(a, gx, nchunks, stream); }
+    if (ng == 2) launch_gather<2, 768>(a, gx, nchunks, stream); else launch_gather<3, 768>(a, gx, nchunks, stream);
   }
   g_last_kernel = "hist_gather_kernel";
   ++g_kernel_launches;
