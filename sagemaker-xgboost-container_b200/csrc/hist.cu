@@ -264,7 +264,11 @@ __device__ __forceinline__ void flush_node_sum(GH64* dst, int g, unsigned h, int
 template <int PL>      // planes per group in shared memory: 1 = G only, 2 = G then H
 __device__ __forceinline__ void spill_main(int* smem, int ng_here, GH64* out, bool last, int tid, int nthr) {
   const int vecs = ng_here * PL * (kGroupEntries / 4);
-  for (int v = tid; v < vecs; v += nthr) {
+  // every CTA flushes the same histogram: each one starts at a different place so that the REDs of a wave of CTAs spread over
+  // the L2 slices instead of queueing on the same lines
+  const int start = (int)(((long long)blockIdx.x * vecs) / gridDim.x);
+  for (int i = tid; i < vecs; i += nthr) {
+    int v = i + start; if (v >= vecs) v -= vecs;
     int4 x = reinterpret_cast<int4*>(smem)[v];
     if ((x.x | x.y | x.z | x.w) == 0) continue;
     const int plane = v >> 11;                                // 2048 int4 per plane
