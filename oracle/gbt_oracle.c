@@ -34,7 +34,8 @@
 #define K_RT_EPS 1e-6f
 
 enum { OBJ_SQUAREDERROR = 0, OBJ_BINARY_LOGISTIC = 1, OBJ_REG_LOGISTIC = 2, OBJ_LOGITRAW = 3,
-       OBJ_SOFTPROB = 4, OBJ_SOFTMAX = 5 };
+       OBJ_SOFTPROB = 4, OBJ_SOFTMAX = 5,
+       OBJ_SQUAREDLOGERROR = 6, OBJ_PSEUDOHUBER = 7, OBJ_POISSON = 8, OBJ_GAMMA = 9, OBJ_TWEEDIE = 10, OBJ_HINGE = 11 };
 
 typedef struct {
   int32_t objective;
@@ -47,6 +48,7 @@ typedef struct {
   uint32_t seed;
   float eta, lambda, alpha, gamma, min_child_weight, max_delta_step, scale_pos_weight;
   float subsample, colsample_bytree, colsample_bylevel, colsample_bynode;
+  float huber_slope, tweedie_variance_power, poisson_max_delta_step;    /* objective parameters (upstream defaults 1, 1.5, 0.7) */
 } OrcParams;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -172,7 +174,11 @@ static inline float orc_sigmoid(float x) {
 }
 
 /* margins: n x K row-major; gpair out: n x K x 2 (g,h) row-major.  Returns 0, or a negative code
- * for a label error (-1 logistic label range, -2 multiclass label range). */
+ * for a label error (-1 logistic label range, -2 multiclass label range, -3 squaredlogerror label <= -1, -4 poisson label < 0,
+ * -5 gamma label <= 0, -6 tweedie label < 0).
+ * Formulas [UPSTREAM-RECALL v3.0.5]: regression_loss.h (LinearSquareLoss, LogisticRegression, SquaredLogError, PseudoHuberError via
+ * regression_obj.cu), regression_obj.cu (PoissonRegression: hess = exp(p + max_delta_step); GammaRegression; TweedieRegression),
+ * hinge.cu (y' = 2y - 1; p*y' < 1 ? (-y', 1) : (0, FLT_MIN)).  scale_pos_weight belongs to the RegLossObj family only. */
 int orc_gradient(const OrcParams* p, const float* margins, const float* labels, const float* weights,
                  int64_t n, float* gpair) {
   const int K = p->num_class > 1 ? p->num_class : 1;
@@ -203,10 +209,33 @@ int orc_gradient(const OrcParams* p, const float* margins, const float* labels, 
   for (int64_t r = 0; r < n; ++r) {
     float y = labels[r];
     float w = weights ? weights[r] : 1.0f;
-    if (y == 1.0f) w *= p->scale_pos_weight;
+    const int reg_loss = p->objective <= OBJ_LOGITRAW || p->objective == OBJ_SQUAREDLOGERROR || p->objective == OBJ_PSEUDOHUBER;
+    if (reg_loss && y == 1.0f) w *= p->scale_pos_weight;
     float pr = margins[r], g, h;
     if (p->objective == OBJ_SQUAREDERROR) { g = pr - y; h = 1.0f; }
-    else {
+    else if (p->objective == OBJ_SQUAREDLOGERROR) {
+      if (!(y > -1.0f)) err = -3;
+      pr = fmaxf(pr, -1.0f + 1e-6f);
+      g = (log1pf(pr) - log1pf(y)) / (pr + 1.0f);
+      h = fmaxf((-log1pf(pr) + log1pf(y) + 1.0f) / ((pr + 1.0f) * (pr + 1.0f)), 1e-6f);
+    } else if (p->objective == OBJ_PSEUDOHUBER) {
+      const float z = pr - y, s2 = p->huber_slope * p->huber_slope, scale_sqrt = sqrtf(1.0f + z * z / s2);
+      g = z / scale_sqrt; h = s2 / ((s2 + z * z) * scale_sqrt);
+    } else if (p->objective == OBJ_POISSON) {
+      if (y < 0.0f) err = -4;
+      g = expf(pr) - y; h = expf(pr + p->poisson_max_delta_step);
+    } else if (p->objective == OBJ_GAMMA) {
+      if (!(y > 0.0f)) err = -5;
+      const float ep = expf(pr);
+      g = 1.0f - y / ep; h = y / ep;
+    } else if (p->objective == OBJ_TWEEDIE) {
+      if (y < 0.0f) err = -6;
+      const float rho = p->tweedie_variance_power, e1 = expf((1.0f - rho) * pr), e2 = expf((2.0f - rho) * pr);
+      g = -y * e1 + e2; h = -y * (1.0f - rho) * e1 + (2.0f - rho) * e2;
+    } else if (p->objective == OBJ_HINGE) {
+      const float yy = y * 2.0f - 1.0f;
+      if (pr * yy < 1.0f) { g = -yy; h = 1.0f; } else { g = 0.0f; h = 1.17549435e-38f; }
+    } else {
       if (y < 0.0f || y > 1.0f) err = -1;
       pr = orc_sigmoid(pr);
       g = pr - y;
@@ -223,6 +252,8 @@ int orc_gradient(const OrcParams* p, const float* margins, const float* labels, 
  * Returns the base_score in OUTPUT space (what the model file stores). */
 float orc_base_score(const OrcParams* p, const float* labels, const float* weights, int64_t n) {
   if (p->objective == OBJ_SOFTPROB || p->objective == OBJ_SOFTMAX) return 0.5f;
+  /* only the RegLossObj family fits an intercept in 3.0.x [UPSTREAM-RECALL]; the log-link objectives and hinge keep 0.5 */
+  if (p->objective == OBJ_POISSON || p->objective == OBJ_GAMMA || p->objective == OBJ_TWEEDIE || p->objective == OBJ_HINGE) return 0.5f;
   if (n == 0) return 0.5f;
   float* zero = (float*)calloc((size_t)n, sizeof(float));
   float* gp = (float*)malloc(sizeof(float) * 2 * (size_t)n);
@@ -240,6 +271,7 @@ float orc_base_score(const OrcParams* p, const float* labels, const float* weigh
 float orc_prob_to_margin(const OrcParams* p, float base_score) {
   if (p->objective == OBJ_BINARY_LOGISTIC || p->objective == OBJ_REG_LOGISTIC || p->objective == OBJ_LOGITRAW)
     return -logf(1.0f / base_score - 1.0f);
+  if (p->objective == OBJ_POISSON || p->objective == OBJ_GAMMA || p->objective == OBJ_TWEEDIE) return logf(base_score);
   return base_score;
 }
 

@@ -17,6 +17,7 @@ _SRC = os.path.join(_HERE, "gbt_oracle.c")
 OBJECTIVES = {
     "reg:squarederror": 0, "reg:linear": 0, "binary:logistic": 1, "reg:logistic": 2,
     "binary:logitraw": 3, "multi:softprob": 4, "multi:softmax": 5,
+    "reg:squaredlogerror": 6, "reg:pseudohubererror": 7, "count:poisson": 8, "reg:gamma": 9, "reg:tweedie": 10, "binary:hinge": 11,
 }
 
 
@@ -36,6 +37,7 @@ class OrcParams(C.Structure):
         ("min_child_weight", C.c_float), ("max_delta_step", C.c_float), ("scale_pos_weight", C.c_float),
         ("subsample", C.c_float), ("colsample_bytree", C.c_float), ("colsample_bylevel", C.c_float),
         ("colsample_bynode", C.c_float),
+        ("huber_slope", C.c_float), ("tweedie_variance_power", C.c_float), ("poisson_max_delta_step", C.c_float),
     ]
 
 
@@ -96,7 +98,7 @@ def make_params(params):
         raise ValueError("oracle: unsupported objective %r" % obj)
     p = OrcParams()
     p.objective = OBJECTIVES[obj]
-    p.num_class = int(g("num_class", 1)) if p.objective >= 4 else 1
+    p.num_class = int(g("num_class", 1)) if p.objective in (4, 5) else 1
     p.max_depth = int(g("max_depth", 6))
     p.max_leaves = int(g("max_leaves", 0))
     p.max_bin = int(g("max_bin", 256))
@@ -114,6 +116,14 @@ def make_params(params):
     p.colsample_bytree = float(g("colsample_bytree", 1.0))
     p.colsample_bylevel = float(g("colsample_bylevel", 1.0))
     p.colsample_bynode = float(g("colsample_bynode", 1.0))
+    p.huber_slope = float(g("huber_slope", 1.0))
+    p.tweedie_variance_power = float(g("tweedie_variance_power", 1.5))
+    if obj == "count:poisson":          # upstream learner.cc: max_delta_step defaults to 0.7 for count:poisson (objective AND tree)
+        if g("max_delta_step") is None:
+            p.max_delta_step = 0.7
+        p.poisson_max_delta_step = p.max_delta_step
+    else:
+        p.poisson_max_delta_step = 0.7
     return p
 
 
@@ -320,6 +330,10 @@ def transform(model, margins):
     m = np.asarray(margins, np.float32)
     if obj in ("binary:logistic", "reg:logistic"):
         return (1.0 / (1.0 + np.exp(-m, dtype=np.float32))).astype(np.float32)
+    if obj in ("count:poisson", "reg:gamma", "reg:tweedie"):
+        return np.exp(m, dtype=np.float32)
+    if obj == "binary:hinge":
+        return (m > 0).astype(np.float32)
     if obj == "multi:softprob":
         e = np.exp(m - m.max(axis=1, keepdims=True), dtype=np.float32)
         return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)

@@ -433,7 +433,9 @@ Booster::~Booster() {
 
 static const std::map<std::string, int>& objective_table() {
   static const std::map<std::string, int> t = {{"reg:squarederror", kSquaredError}, {"reg:linear", kSquaredError}, {"binary:logistic", kBinaryLogistic},
-    {"reg:logistic", kRegLogistic}, {"binary:logitraw", kLogitRaw}, {"multi:softprob", kSoftprob}, {"multi:softmax", kSoftmax}};
+    {"reg:logistic", kRegLogistic}, {"binary:logitraw", kLogitRaw}, {"multi:softprob", kSoftprob}, {"multi:softmax", kSoftmax},
+    {"reg:squaredlogerror", kSquaredLogError}, {"reg:pseudohubererror", kPseudoHuber}, {"count:poisson", kPoisson}, {"reg:gamma", kGamma},
+    {"reg:tweedie", kTweedie}, {"binary:hinge", kHinge}};
   return t;
 }
 
@@ -453,7 +455,7 @@ void Booster::configure() {
   auto ito = raw_params_.find("objective");
   if (ito != raw_params_.end()) objective_name_ = ito->second;
   auto ot = objective_table().find(objective_name_);
-  B200_CHECK(ot != objective_table().end(), "Unknown objective function: `" + objective_name_ + "` (supported on the B200 hist path: reg:squarederror, reg:linear, reg:logistic, binary:logistic, binary:logitraw, multi:softprob, multi:softmax)");
+  B200_CHECK(ot != objective_table().end(), "Unknown objective function: `" + objective_name_ + "` (supported on the B200 hist path: reg:squarederror, reg:linear, reg:logistic, reg:squaredlogerror, reg:pseudohubererror, reg:gamma, reg:tweedie, count:poisson, binary:logistic, binary:logitraw, binary:hinge, multi:softprob, multi:softmax)");
   p.objective = ot->second;
   if (objective_name_ == "reg:linear") objective_name_ = "reg:squarederror";
   p.num_class = (p.objective == kSoftprob || p.objective == kSoftmax) ? geti("num_class", 0) : 1;
@@ -465,6 +467,16 @@ void Booster::configure() {
   p.subsample = getf("subsample", nullptr, 1.0f); p.colsample_bytree = getf("colsample_bytree", nullptr, 1.0f);
   p.colsample_bylevel = getf("colsample_bylevel", nullptr, 1.0f); p.colsample_bynode = getf("colsample_bynode", nullptr, 1.0f);
   p.seed = (unsigned)geti("seed", 0);
+  p.huber_slope = getf("huber_slope", nullptr, 1.0f); p.tweedie_variance_power = getf("tweedie_variance_power", nullptr, 1.5f);
+  B200_CHECK(p.huber_slope != 0.0f, "Check failed: slope != 0.0 (huber_slope)");
+  B200_CHECK(p.tweedie_variance_power >= 1.0f && p.tweedie_variance_power < 2.0f, "tweedie_variance_power must be in interval [1, 2)");
+  // count:poisson: max_delta_step defaults to 0.7 for the objective's hessian AND the tree's leaf clipping (upstream learner.cc sets
+  // the shared parameter when the user did not)
+  if (p.objective == kPoisson) {
+    if (raw_params_.find("max_delta_step") == raw_params_.end()) p.max_delta_step = 0.7f;
+    p.poisson_max_delta_step = p.max_delta_step;
+    B200_CHECK(p.poisson_max_delta_step >= 0.0f, "max_delta_step must be non-negative for count:poisson");
+  }
   B200_CHECK(p.lambda >= 0.0f, "Parameter reg_lambda should be greater equal to 0");
   B200_CHECK(p.subsample > 0.0f && p.subsample <= 1.0f, "Parameter subsample should be in (0, 1]");
   auto tm = raw_params_.find("tree_method");
@@ -491,9 +503,13 @@ void Booster::configure() {
 }
 
 float Booster::base_margin() const {
-  if (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic || param_.objective == kLogitRaw)
-    return -std::log(1.0f / base_score_ - 1.0f);
+  if (objective_is_logistic(param_.objective)) return -std::log(1.0f / base_score_ - 1.0f);
+  if (objective_is_log_link(param_.objective)) return std::log(base_score_);          // ProbToMargin of the log-link objectives
   return base_score_;
+}
+
+static float objective_aux(const TrainParam& p) {
+  switch (p.objective) { case kPseudoHuber: return p.huber_slope; case kTweedie: return p.tweedie_variance_power; case kPoisson: return p.poisson_max_delta_step; default: return 0.0f; }
 }
 
 // One Newton stump at margin 0, then PredTransform (upstream src/objective/init_estimation.cc, src/tree/fit_stump.cc)
@@ -501,11 +517,14 @@ void Booster::estimate_base_score(DMatrix* dtrain) {
   if (base_score_set_ || base_score_estimated_ || !trees_.empty()) { base_score_estimated_ = true; return; }
   base_score_estimated_ = true;
   if (param_.objective == kSoftprob || param_.objective == kSoftmax) { base_score_ = 0.5f; return; }
+  // 3.0.x fits the intercept for the RegLossObj family only; the log-link objectives and binary:hinge keep the 0.5 default
+  // [UPSTREAM-RECALL: src/objective/init_estimation.cc; later releases changed the GLM objectives]
+  if (objective_is_log_link(param_.objective) || param_.objective == kHinge) { base_score_ = 0.5f; return; }
   cudaStream_t s = engine_stream();
   GrowerImpl& g = *grower_;
   GradArgs ga{}; ga.margin = nullptr; ga.label = dtrain->d_labels.p; ga.weight = dtrain->weights.empty() ? nullptr : dtrain->d_weights.p;
   ga.gpair = g.gpair.p; ga.gp_stride = g.gp_stride; ga.absmax = nullptr; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = 1; ga.objective = param_.objective;
-  ga.scale_pos_weight = param_.scale_pos_weight; ga.subsample = 1.0f; ga.seed = 0; ga.iter = 0;
+  ga.scale_pos_weight = param_.scale_pos_weight; ga.subsample = 1.0f; ga.seed = 0; ga.iter = 0; ga.aux = objective_aux(param_);
   CUDA_OK(cudaMemsetAsync(g.dsum.p, 0, 4 * sizeof(double), s));
   launch_gradient(ga, s);
   launch_sum_gpair(g.gpair.p, dtrain->n, g.dsum.p, s);
@@ -642,6 +661,10 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
       for (float v : y) B200_CHECK(v >= 0.0f && v <= 1.0f, "Check failed: label must be in [0,1] for logistic regression");
     if (param_.objective == kSoftprob || param_.objective == kSoftmax)
       for (float v : y) B200_CHECK(v >= 0.0f && (int)v < K, "SoftmaxMultiClassObj: label must be in [0, num_class).");
+    if (param_.objective == kSquaredLogError) for (float v : y) B200_CHECK(v > -1.0f, "Check failed: label must be greater than -1 for rmsle so that log(label + 1) can be valid.");
+    if (param_.objective == kPoisson) for (float v : y) B200_CHECK(v >= 0.0f, "PoissonRegression: label must be nonnegative");
+    if (param_.objective == kGamma) for (float v : y) B200_CHECK(v > 0.0f, "GammaRegression: label must be positive.");
+    if (param_.objective == kTweedie) for (float v : y) B200_CHECK(v >= 0.0f, "TweedieRegression: label must be nonnegative");
     labels_checked_ = true;
   }
   estimate_base_score(dtrain);
@@ -654,7 +677,7 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
   GradArgs ga{}; ga.margin = cache.margin.p; ga.label = dtrain->d_labels.p; ga.weight = dtrain->weights.empty() ? nullptr : dtrain->d_weights.p;
   ga.gpair = g.gpair.p; ga.gp_stride = g.gp_stride; ga.absmax = g.gs.absmax; ga.err = g.err.p; ga.n = dtrain->n; ga.row_offset = 0; ga.K = K; ga.objective = param_.objective;
   ga.scale_pos_weight = param_.scale_pos_weight; ga.subsample = param_.subsample; ga.seed = param_.seed; ga.iter = (unsigned long long)round;
-  ga.row_offset = (int64_t)Comm::get().rank() << 40;
+  ga.row_offset = (int64_t)Comm::get().rank() << 40; ga.aux = objective_aux(param_);
   launch_gradient(ga, s);
   Comm::get().allreduce_max_u32(g.gs.absmax, 2, s);
   launch_scales(g.gs, job_grad_bits(g.global_n), s);
@@ -859,15 +882,25 @@ int Booster::boosted_rounds() { configure(); return (int)trees_.size() / std::ma
 // ---------------------------------------------------------------------------------------------
 // evaluation  (upstream src/learner.cc EvalOneIter: "[iter]\t<name>-<metric>:<value>")
 // ---------------------------------------------------------------------------------------------
-static std::string default_metric(int objective) {
-  switch (objective) { case kSquaredError: case kRegLogistic: return "rmse"; case kBinaryLogistic: case kLogitRaw: return "logloss"; default: return "mlogloss"; }
+static std::string default_metric(const TrainParam& p) {
+  switch (p.objective) {
+    case kSquaredError: case kRegLogistic: return "rmse";
+    case kBinaryLogistic: case kLogitRaw: return "logloss";
+    case kSquaredLogError: return "rmsle";
+    case kPseudoHuber: return "mphe";
+    case kPoisson: return "poisson-nloglik";
+    case kGamma: return "gamma-nloglik";
+    case kTweedie: { char buf[64]; snprintf(buf, sizeof buf, "tweedie-nloglik@%g", (double)p.tweedie_variance_power); return buf; }
+    case kHinge: return "error";
+    default: return "mlogloss";
+  }
 }
 
 std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, const std::vector<std::string>& names) {
   configure();
   cudaStream_t s = engine_stream();
   std::vector<std::string> metrics = eval_metrics_;
-  if (metrics.empty()) metrics.push_back(default_metric(param_.objective));
+  if (metrics.empty()) metrics.push_back(default_metric(param_));
   if (!grower_) grower_ = new GrowerImpl();
   grower_->dsum.ensure(4);
   std::string out = "[" + std::to_string(iter) + "]";
@@ -880,7 +913,9 @@ std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, c
       MetricArgs ma{}; ma.margin = c.margin.p; ma.label = dm->d_labels.p; ma.weight = dm->weights.empty() ? nullptr : dm->d_weights.p;
       ma.out = grower_->dsum.p; ma.n = dm->n; ma.K = param_.num_class; ma.threshold = 0.5f;
       ma.is_logistic = (param_.objective == kBinaryLogistic || param_.objective == kRegLogistic) ? 1 : 0;
+      ma.transform = objective_transform(param_.objective); ma.aux = 0.0f;
       std::string base = mname;
+      if (mname.rfind("tweedie-nloglik@", 0) == 0) { base = "tweedie-nloglik"; ma.aux = std::stof(mname.substr(16)); B200_CHECK(ma.aux >= 1.0f && ma.aux < 2.0f, "tweedie variance power must be in interval [1, 2)"); }
       if (mname.rfind("error@", 0) == 0) { base = "error"; ma.threshold = std::stof(mname.substr(6)); }
       if (base == "auc") {
         // validated on hardware against sklearn.metrics.roc_auc_score (tests/test_gpu_parity.py::test_auc_matches_sklearn)
@@ -905,7 +940,12 @@ std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, c
       if (base == "rmse") ma.metric = kMetricRmse; else if (base == "mse") ma.metric = kMetricRmse; else if (base == "mae") ma.metric = kMetricMae;
       else if (base == "logloss") ma.metric = kMetricLogloss; else if (base == "error") ma.metric = kMetricError;
       else if (base == "merror") ma.metric = kMetricMerror; else if (base == "mlogloss") ma.metric = kMetricMlogloss;
-      else throw Error("Unknown metric function " + mname + " (B200 hist path implements rmse, mae, logloss, error, error@t, merror, mlogloss)");
+      else if (base == "rmsle") ma.metric = kMetricRmsle; else if (base == "mape") ma.metric = kMetricMape;
+      else if (base == "mphe") { ma.metric = kMetricMphe; ma.aux = param_.huber_slope; }
+      else if (base == "poisson-nloglik") ma.metric = kMetricPoissonNll; else if (base == "gamma-nloglik") ma.metric = kMetricGammaNll;
+      else if (base == "gamma-deviance") ma.metric = kMetricGammaDeviance;
+      else if (base == "tweedie-nloglik") { ma.metric = kMetricTweedieNll; if (ma.aux == 0.0f) throw Error("tweedie-nloglik needs its variance power: tweedie-nloglik@rho"); }
+      else throw Error("Unknown metric function " + mname + " (B200 hist path implements rmse, mse, rmsle, mae, mape, mphe, logloss, error, error@t, merror, mlogloss, auc, poisson-nloglik, gamma-nloglik, gamma-deviance, tweedie-nloglik@rho)");
       if (param_.objective == kLogitRaw && (ma.metric == kMetricLogloss || ma.metric == kMetricError)) ma.is_logistic = 1;
       if ((ma.metric == kMetricMerror || ma.metric == kMetricMlogloss)) B200_CHECK(param_.num_class > 1, "Check failed: preds.size() == info.labels_.size() : label and prediction size not match, hint: use merror or mlogloss for multi-class classification");
       CUDA_OK(cudaMemsetAsync(grower_->dsum.p, 0, 2 * sizeof(double), s));
@@ -915,7 +955,8 @@ std::string Booster::eval_one_iter(int iter, const std::vector<DMatrix*>& dms, c
       CUDA_OK(cudaMemcpyAsync(h, grower_->dsum.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
       Comm::get().sync_stream(s);
       double v = h[1] == 0.0 ? h[0] : h[0] / h[1];
-      if (mname == "rmse") v = std::sqrt(v);
+      if (mname == "rmse" || mname == "rmsle") v = std::sqrt(v);
+      if (mname == "gamma-deviance") v *= 2.0;
       char buf[64]; snprintf(buf, sizeof buf, "%.17g", v);
       out += "\t" + names[i] + "-" + mname + ":" + buf;
     }

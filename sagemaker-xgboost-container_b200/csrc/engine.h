@@ -82,7 +82,18 @@ inline size_t hist_slot_entries(int ngroups, int tw) { return (size_t)ngroups * 
 // training parameters (names follow the container's hyperparameter schema,
 // reference: src/sagemaker_xgboost_container/algorithm_mode/hyperparameter_validation.py:141-346)
 // ---------------------------------------------------------------------------------------------
-enum Objective : int { kSquaredError = 0, kBinaryLogistic = 1, kRegLogistic = 2, kLogitRaw = 3, kSoftprob = 4, kSoftmax = 5 };
+enum Objective : int { kSquaredError = 0, kBinaryLogistic = 1, kRegLogistic = 2, kLogitRaw = 3, kSoftprob = 4, kSoftmax = 5,
+                       kSquaredLogError = 6, kPseudoHuber = 7, kPoisson = 8, kGamma = 9, kTweedie = 10, kHinge = 11 };
+// prediction transform of an objective (upstream ObjFunction::PredTransform / ProbToMargin): 0 identity, 1 sigmoid / logit,
+// 2 exp / log (count:poisson, reg:gamma, reg:tweedie), 3 step at 0 (binary:hinge; its margin is the raw score)
+enum Transform : int { kTransformNone = 0, kTransformSigmoid = 1, kTransformExp = 2, kTransformHinge = 3 };
+inline bool objective_is_logistic(int o) { return o == kBinaryLogistic || o == kRegLogistic || o == kLogitRaw; }
+inline bool objective_is_log_link(int o) { return o == kPoisson || o == kGamma || o == kTweedie; }
+inline int objective_transform(int o) {
+  if (o == kBinaryLogistic || o == kRegLogistic) return kTransformSigmoid;
+  if (objective_is_log_link(o)) return kTransformExp;
+  return o == kHinge ? kTransformHinge : kTransformNone;
+}
 
 struct TrainParam {
   int objective = kSquaredError;
@@ -91,6 +102,7 @@ struct TrainParam {
   float eta = 0.3f, lambda = 1.0f, alpha = 0.0f, gamma = 0.0f, min_child_weight = 1.0f, max_delta_step = 0.0f;
   float scale_pos_weight = 1.0f, subsample = 1.0f, colsample_bytree = 1.0f, colsample_bylevel = 1.0f, colsample_bynode = 1.0f;
   unsigned seed = 0;
+  float huber_slope = 1.0f, tweedie_variance_power = 1.5f, poisson_max_delta_step = 0.7f;   // objective parameters (upstream defaults)
 };
 
 // ---------------------------------------------------------------------------------------------

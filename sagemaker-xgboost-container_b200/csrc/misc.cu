@@ -54,12 +54,44 @@ __global__ void __launch_bounds__(256) gradient_kernel(GradArgs a) {
         mg = fmaxf(mg, fabsf(g)); mh = fmaxf(mh, h);
       }
     } else {
-      if (y == 1.0f) w *= a.scale_pos_weight;
+      const bool reg_loss = a.objective <= kLogitRaw || a.objective == kSquaredLogError || a.objective == kPseudoHuber;     // RegLossObj family
+      if (reg_loss && y == 1.0f) w *= a.scale_pos_weight;
       float p = a.margin ? a.margin[r] : 0.f, g, h;
-      if (a.objective == kSquaredError) { g = p - y; h = 1.0f; }
-      else {
-        if (y < 0.0f || y > 1.0f) *a.err = 1;
-        p = sigmoidf_xgb(p); g = p - y; h = fmaxf(p * (1.0f - p), 1e-16f);
+      // upstream src/objective/regression_loss.h (RegLossObj family), regression_obj.cu (Poisson / Gamma / Tweedie), hinge.cu
+      switch (a.objective) {
+        case kSquaredError: g = p - y; h = 1.0f; break;
+        case kSquaredLogError: {
+          if (!(y > -1.0f)) *a.err = 3;
+          p = fmaxf(p, -1.0f + 1e-6f);
+          g = (log1pf(p) - log1pf(y)) / (p + 1.0f);
+          h = fmaxf((-log1pf(p) + log1pf(y) + 1.0f) / ((p + 1.0f) * (p + 1.0f)), 1e-6f);
+          break; }
+        case kPseudoHuber: {
+          const float z = p - y, s2 = a.aux * a.aux, scale_sqrt = sqrtf(1.0f + z * z / s2);
+          g = z / scale_sqrt; h = s2 / ((s2 + z * z) * scale_sqrt);
+          break; }
+        case kPoisson: {
+          if (y < 0.0f) *a.err = 4;
+          g = expf(p) - y; h = expf(p + a.aux);
+          break; }
+        case kGamma: {
+          if (!(y > 0.0f)) *a.err = 5;
+          const float ep = expf(p);
+          g = 1.0f - y / ep; h = y / ep;
+          break; }
+        case kTweedie: {
+          if (y < 0.0f) *a.err = 6;
+          const float rho = a.aux, e1 = expf((1.0f - rho) * p), e2 = expf((2.0f - rho) * p);
+          g = -y * e1 + e2; h = -y * (1.0f - rho) * e1 + (2.0f - rho) * e2;
+          break; }
+        case kHinge: {
+          const float yy = y * 2.0f - 1.0f;
+          if (p * yy < 1.0f) { g = -yy; h = 1.0f; } else { g = 0.0f; h = 1.17549435e-38f; }      // upstream: numeric_limits<float>::min()
+          break; }
+        default: {
+          if (y < 0.0f || y > 1.0f) *a.err = 1;
+          p = sigmoidf_xgb(p); g = p - y; h = fmaxf(p * (1.0f - p), 1e-16f);
+          break; }
       }
       g *= w; h *= w;
       if (dropped) { g = 0.f; h = 0.f; }
@@ -273,6 +305,8 @@ __global__ void __launch_bounds__(256) transform_kernel(float* m, int64_t n, int
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   if (objective == kBinaryLogistic || objective == kRegLogistic) m[r] = sigmoidf_xgb(m[r]);
+  else if (objective == kPoisson || objective == kGamma || objective == kTweedie) m[r] = expf(m[r]);
+  else if (objective == kHinge) m[r] = m[r] > 0.0f ? 1.0f : 0.0f;
   else if (objective == kSoftprob || objective == kSoftmax) {
     float* p = m + r * K;
     float wmax = p[0]; int arg = 0;
@@ -315,8 +349,17 @@ __global__ void __launch_bounds__(256) metric_kernel(MetricArgs a) {
       }
     } else {
       float p = a.margin[r];
-      if (a.is_logistic) p = sigmoidf_xgb(p);
-      switch (a.metric) {
+      if (a.is_logistic || a.transform == kTransformSigmoid) p = sigmoidf_xgb(p);
+      else if (a.transform == kTransformExp) p = expf(p);
+      else if (a.transform == kTransformHinge) p = p > 0.0f ? 1.0f : 0.0f;
+      switch (a.metric) {          // upstream src/metric/elementwise_metric.cu
+        case kMetricRmsle: { float d = log1pf(y) - log1pf(p); loss = d * d; break; }
+        case kMetricMape: loss = fabsf((y - p) / y); break;
+        case kMetricMphe: { const float z = (y - p) / a.aux; loss = a.aux * a.aux * (sqrtf(1.0f + z * z) - 1.0f); break; }
+        case kMetricPoissonNll: { const float py = fmaxf(p, 1e-16f); loss = lgammaf(y + 1.0f) + py - logf(py) * y; break; }
+        case kMetricGammaNll: { const float py = fmaxf(p, 1e-6f); loss = y / py + logf(py); break; }       // psi = 1: -((y * theta - b) / a + c), theta = -1 / py, b = -log(-theta)
+        case kMetricGammaDeviance: { const float py = p + 1e-6f, yy = y + 1e-6f; loss = logf(py / yy) + yy / py - 1.0f; break; }      // x 2 on the host
+        case kMetricTweedieNll: { const float rho = a.aux, lp = logf(p); loss = -y * expf((1.0f - rho) * lp) / (1.0f - rho) + expf((2.0f - rho) * lp) / (2.0f - rho); break; }
         case kMetricRmse: { float d = p - y; loss = d * d; break; }
         case kMetricMae: loss = fabsf(p - y); break;
         case kMetricLogloss: {

@@ -10,11 +10,13 @@ struct GradArgs {
   float2* gpair;            // [K][gp_stride]
   int64_t gp_stride;        // rows reserved per class (>= n, multiple of 64: keeps class blocks 16 B aligned for the TMA bulk copies)
   unsigned* absmax;         // max|g|, max h as float bits (atomicMax), may be nullptr
-  int* err;                 // 1 = logistic label range, 2 = multiclass label range
+  int* err;                 // 1 = logistic label range, 2 = multiclass label range, 3 = squaredlogerror label <= -1, 4 = poisson label < 0,
+                            // 5 = gamma label <= 0, 6 = tweedie label < 0
   int64_t n, row_offset;    // row_offset: global index of local row 0 (multi-GPU subsampling stream)
   int K, objective;
   float scale_pos_weight, subsample;
   unsigned seed; unsigned long long iter;
+  float aux;                // objective parameter: huber_slope / tweedie_variance_power / the Poisson max_delta_step
 };
 
 struct DevNode { float cond; int left; int right; unsigned fidx_dl; };   // 16 B, leaf: left == -1, cond = leaf value
@@ -31,11 +33,14 @@ struct PredictArgs {
 };
 
 enum Metric : int { kMetricRmse = 0, kMetricMae = 1, kMetricLogloss = 2, kMetricError = 3, kMetricMerror = 4, kMetricMlogloss = 5,
-                    kMetricAuc = 6, kMetricMse = 7 };
+                    kMetricAuc = 6, kMetricMse = 7, kMetricRmsle = 8, kMetricMape = 9, kMetricMphe = 10, kMetricPoissonNll = 11,
+                    kMetricGammaNll = 12, kMetricGammaDeviance = 13, kMetricTweedieNll = 14 };
 
 struct MetricArgs {
   const float* margin; const float* label; const float* weight; double* out;
   int64_t n; int K, metric, is_logistic; float threshold;
+  int transform;            // engine.h Transform applied to the margin first (is_logistic == 1 is kTransformSigmoid)
+  float aux;                // huber slope (mphe) / variance power (tweedie-nloglik)
 };
 
 void launch_gradient(const GradArgs& a, cudaStream_t s);

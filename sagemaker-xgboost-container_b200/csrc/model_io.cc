@@ -21,6 +21,18 @@ static std::string float_repr(float v) {       // shortest round-trip, xgboost s
 }
 static JPtr S(const std::string& s) { return JValue::Str(s); }
 
+// per-objective parameter block of the model / config documents (upstream ObjFunction::SaveConfig)
+static void objective_params_to_json(JValue& obj, const TrainParam& p) {
+  JPtr rp = JValue::Object();
+  switch (p.objective) {
+    case kPoisson: rp->set("max_delta_step", S(float_repr(p.poisson_max_delta_step))); obj.set("poisson_regression_param", rp); break;
+    case kTweedie: rp->set("tweedie_variance_power", S(float_repr(p.tweedie_variance_power))); obj.set("tweedie_regression_param", rp); break;
+    case kPseudoHuber: rp->set("huber_slope", S(float_repr(p.huber_slope))); obj.set("pseudo_huber_param", rp); break;
+    case kGamma: case kHinge: break;
+    default: rp->set("scale_pos_weight", S(float_repr(p.scale_pos_weight))); obj.set("reg_loss_param", rp); break;
+  }
+}
+
 JPtr Booster::model_to_json() {
   configure(); sync_model();
   const int K = param_.num_class;
@@ -70,7 +82,7 @@ JPtr Booster::model_to_json() {
   learner->set("learner_model_param", lmp);
   JPtr obj = JValue::Object(); obj->set("name", S(objective_name_));
   if (param_.objective == kSoftprob || param_.objective == kSoftmax) { JPtr sp = JValue::Object(); sp->set("num_class", S(std::to_string(K))); obj->set("softmax_multiclass_param", sp); }
-  else { JPtr rp = JValue::Object(); rp->set("scale_pos_weight", S(float_repr(param_.scale_pos_weight))); obj->set("reg_loss_param", rp); }
+  else objective_params_to_json(*obj, param_);
   learner->set("objective", obj);
   doc->set("learner", learner);
   JPtr ver = JValue::Array(); ver->arr = {JValue::Int(3), JValue::Int(0), JValue::Int(5)};
@@ -100,6 +112,9 @@ void Booster::model_from_json(const JValue& doc) {
   objective_name_ = obj.at("name").s;
   raw_params_["objective"] = objective_name_;
   if (auto rp = obj.get("reg_loss_param")) if (auto sp = rp->get("scale_pos_weight")) raw_params_["scale_pos_weight"] = std::to_string(sp->as_double());
+  if (auto pp = obj.get("poisson_regression_param")) if (auto v = pp->get("max_delta_step")) raw_params_["max_delta_step"] = std::to_string(v->as_double());
+  if (auto tp = obj.get("tweedie_regression_param")) if (auto v = tp->get("tweedie_variance_power")) raw_params_["tweedie_variance_power"] = std::to_string(v->as_double());
+  if (auto hp = obj.get("pseudo_huber_param")) if (auto v = hp->get("huber_slope")) raw_params_["huber_slope"] = std::to_string(v->as_double());
   const JValue& lmp = learner.at("learner_model_param");
   num_feature_ = (int)lmp.at("num_feature").as_int();
   int nc = lmp.has("num_class") ? (int)lmp.at("num_class").as_int() : 0;
@@ -178,7 +193,7 @@ JPtr Booster::config_to_json() {
   JPtr metrics = JValue::Array(); for (auto& m : eval_metrics_) { JPtr mo = JValue::Object(); mo->set("name", S(m)); metrics->arr.push_back(mo); } learner->set("metrics", metrics);
   JPtr obj = JValue::Object(); obj->set("name", S(objective_name_));
   if (param_.objective == kSoftprob || param_.objective == kSoftmax) { JPtr sp = JValue::Object(); sp->set("num_class", S(std::to_string(param_.num_class))); obj->set("softmax_multiclass_param", sp); }
-  else { JPtr rp = JValue::Object(); rp->set("scale_pos_weight", S(float_repr(param_.scale_pos_weight))); obj->set("reg_loss_param", rp); }
+  else objective_params_to_json(*obj, param_);
   learner->set("objective", obj);
   doc->set("learner", learner);
   JPtr ver = JValue::Array(); ver->arr = {JValue::Int(3), JValue::Int(0), JValue::Int(5)}; doc->set("version", ver);
@@ -193,6 +208,9 @@ void Booster::config_from_json(const JValue& doc) {
     raw_params_["objective"] = o->at("name").s;
     if (auto rp = o->get("reg_loss_param")) if (auto sp = rp->get("scale_pos_weight")) raw_params_["scale_pos_weight"] = sp->s;
     if (auto sp = o->get("softmax_multiclass_param")) raw_params_["num_class"] = sp->at("num_class").s;
+    if (auto pp = o->get("poisson_regression_param")) if (auto v = pp->get("max_delta_step")) raw_params_["max_delta_step"] = v->s;
+    if (auto tp = o->get("tweedie_regression_param")) if (auto v = tp->get("tweedie_variance_power")) raw_params_["tweedie_variance_power"] = v->s;
+    if (auto hp = o->get("pseudo_huber_param")) if (auto v = hp->get("huber_slope")) raw_params_["huber_slope"] = v->s;
   }
   if (auto m = learner.get("metrics")) { eval_metrics_.clear(); for (auto& x : m->arr) eval_metrics_.push_back(x->at("name").s); }
   configured_ = false;

@@ -311,6 +311,89 @@ def test_eval_metrics_match_numpy(xgb):
     assert abs(res["train"]["rmse"][-1] - np.sqrt(np.mean((p - y) ** 2))) < 1e-6
 
 
+MORE_OBJECTIVES = [
+    ("reg:squaredlogerror", "pos", {}, "rmsle"),
+    ("reg:pseudohubererror", "reg", dict(huber_slope=0.7), "mphe"),
+    ("count:poisson", "count", {}, "poisson-nloglik"),
+    ("count:poisson", "count", dict(max_delta_step=0.3), "poisson-nloglik"),
+    ("reg:gamma", "pos", {}, "gamma-nloglik"),
+    ("reg:tweedie", "count", dict(tweedie_variance_power=1.3), "tweedie-nloglik@1.3"),
+    ("binary:hinge", "bin", {}, "error"),
+]
+
+
+def _numpy_metric(name, y, p, slope=1.0):
+    y = y.astype(np.float64); p = p.astype(np.float64)
+    if name == "rmsle":
+        return np.sqrt(np.mean((np.log1p(y) - np.log1p(p)) ** 2))
+    if name == "mape":
+        return np.mean(np.abs((y - p) / y))
+    if name == "mphe":
+        return np.mean(slope ** 2 * (np.sqrt(1 + ((y - p) / slope) ** 2) - 1))
+    if name == "poisson-nloglik":
+        from scipy.special import gammaln
+        p = np.maximum(p, 1e-16)
+        return np.mean(gammaln(y + 1) + p - np.log(p) * y)
+    if name == "gamma-nloglik":
+        p = np.maximum(p, 1e-6)
+        return np.mean(y / p + np.log(p))
+    if name == "gamma-deviance":
+        return 2 * np.mean(np.log((p + 1e-6) / (y + 1e-6)) + (y + 1e-6) / (p + 1e-6) - 1)
+    if name.startswith("tweedie-nloglik@"):
+        rho = float(name.split("@")[1])
+        return np.mean(-y * np.exp((1 - rho) * np.log(p)) / (1 - rho) + np.exp((2 - rho) * np.log(p)) / (2 - rho))
+    if name == "error":
+        return np.mean((p > 0.5) != (y > 0.5))
+    raise ValueError(name)
+
+
+@pytest.mark.parametrize("objective,kind,hp,default_metric", MORE_OBJECTIVES)
+def test_remaining_elementwise_objectives_match_oracle(xgb, oracle, objective, kind, hp, default_metric):
+    """The other element-wise objectives the container's hyperparameter validation accepts (hyperparameter_validation.py:283-309):
+    gradients, base score, prediction transform, default metric name and value."""
+    n, F, rounds = 8000, 12, 6
+    X, y = synth(n, F, 57, kind)
+    params = dict(objective=objective, tree_method="hist", max_depth=4, eta=0.3, **hp)
+    d = xgb.DMatrix(X, label=y)
+    res = {}
+    bst = xgb.train(params, d, num_boost_round=rounds, evals=[(d, "train")], evals_result=res, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, rounds).model()
+    assert abs(m["base_score"] - mr["base_score"]) <= 1e-6 * max(1.0, abs(mr["base_score"]))
+    assert first_structural_difference(m, mr) is None
+    assert_same_structure(m, mr)
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    margin = bst.predict(d, output_margin=True)
+    np.testing.assert_allclose(margin, oracle.predict_margin(mr, X).ravel(), rtol=0, atol=MARGIN_TOL)
+    pred = bst.predict(d)
+    np.testing.assert_allclose(pred, oracle.transform(mr, oracle.predict_margin(mr, X)).ravel(), rtol=2e-6, atol=1e-6)
+    assert list(res["train"].keys()) == [default_metric]                       # the objective's default metric, upstream's spelling
+    ref = _numpy_metric(default_metric, y, pred, slope=hp.get("huber_slope", 1.0))
+    assert abs(res["train"][default_metric][-1] - ref) <= 2e-5 * max(1.0, abs(ref))
+    # the objective's parameters survive save_config / load_config and a model round trip
+    cfg = bst.save_config()
+    b2 = xgb.Booster(model_file=bytes(bst.save_raw("ubj")))
+    b2.load_config(cfg)
+    np.testing.assert_array_equal(b2.predict(d), pred)
+
+
+def test_extra_metrics_and_label_checks_of_the_new_objectives(xgb):
+    X, y = synth(4000, 6, 58, "pos")
+    d = xgb.DMatrix(X, label=y)
+    res = {}
+    bst = xgb.train(dict(objective="reg:gamma", max_depth=3, eval_metric=["gamma-deviance", "mape", "rmsle", "mphe", "gamma-nloglik"]), d, num_boost_round=4,
+                    evals=[(d, "train")], evals_result=res, verbose_eval=False)
+    p = bst.predict(d)
+    for name in ("gamma-deviance", "mape", "rmsle", "mphe", "gamma-nloglik"):
+        ref = _numpy_metric(name, y, p)
+        assert abs(res["train"][name][-1] - ref) <= 2e-5 * max(1.0, abs(ref)), name
+    for objective, bad, msg in (("count:poisson", -1.0, "label must be nonnegative"), ("reg:gamma", 0.0, "label must be positive"),
+                                ("reg:tweedie", -0.5, "label must be nonnegative"), ("reg:squaredlogerror", -1.0, "label must be greater than -1")):
+        yb = y.copy(); yb[3] = bad
+        with pytest.raises(xgb.XGBoostError, match=msg):
+            xgb.train(dict(objective=objective), xgb.DMatrix(X, label=yb), num_boost_round=1, verbose_eval=False)
+
+
 @pytest.mark.parametrize("weighted", [False, True])
 def test_auc_matches_sklearn(xgb, weighted):
     """Native `auc` (the one HPO metric the container does not compute itself, train_utils.py:45-76) against

@@ -17,6 +17,10 @@ def synth(n, F, seed, kind="reg", K=1, quantised=True, missing_frac=0.0):
     elif kind == "multi":
         beta = (rng.standard_normal((F, K)) / np.sqrt(F)).astype(np.float32)
         y = np.argmax(X @ beta + rng.standard_normal((n, K)).astype(np.float32), axis=1).astype(np.float32)
+    elif kind in ("pos", "count"):        # positive targets (gamma / tweedie / squaredlogerror) and Poisson counts
+        beta = (rng.standard_normal(F) / np.sqrt(F)).astype(np.float32)
+        mu = np.exp(0.5 * (X @ beta) + 0.1 * rng.standard_normal(n).astype(np.float32))
+        y = rng.poisson(mu).astype(np.float32) if kind == "count" else mu.astype(np.float32)
     else:
         raise ValueError(kind)
     if missing_frac > 0:
