@@ -828,3 +828,54 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* Prediction contributions, brute force.  [UPSTREAM src/predictor/cpu_treeshap.cc computes the same quantity with the      */
+/* polynomial-time Tree SHAP recursion]  Definition: the value of a feature subset S for one tree is the expectation of the */
+/* tree's output when only the features in S are known -- at a split on a known feature follow the row, otherwise average  */
+/* both children weighted by their cover (sum_hess).  phi_j is the Shapley value of feature j for that game, phi[F] = v({}) */
+/* (+ base margin).  Enumerates all 2^F subsets: test sizes only (F <= 12).  Independent of the recursion it checks.       */
+/* ------------------------------------------------------------------------------------------ */
+static double shap_expect(const int32_t* left, const int32_t* right, const int32_t* split_index, const uint8_t* default_left,
+                          const float* split_cond, const float* sum_hess, int64_t base, int node, const float* x, unsigned known) {
+  const int64_t i = base + node;
+  if (left[i] < 0) return (double)split_cond[i];
+  const int f = split_index[i];
+  if (known & (1u << f)) {
+    const float v = x[f];
+    const int go_left = (v != v) ? default_left[i] != 0 : v < split_cond[i];
+    return shap_expect(left, right, split_index, default_left, split_cond, sum_hess, base, go_left ? left[i] : right[i], x, known);
+  }
+  const double hl = sum_hess[base + left[i]], hr = sum_hess[base + right[i]];
+  return (hl * shap_expect(left, right, split_index, default_left, split_cond, sum_hess, base, left[i], x, known) +
+          hr * shap_expect(left, right, split_index, default_left, split_cond, sum_hess, base, right[i], x, known)) / (double)sum_hess[i];
+}
+
+void orc_shap_bruteforce(const float* X, int64_t n, int32_t F, int32_t K, int32_t tree_begin, int32_t tree_end, const int64_t* tree_offset,
+                         const int32_t* tree_info, const int32_t* left, const int32_t* right, const int32_t* split_index,
+                         const uint8_t* default_left, const float* split_cond, const float* sum_hess, float base_margin, double* out) {
+  const unsigned nsub = 1u << F;
+  double* fact = (double*)malloc(sizeof(double) * (F + 1));
+  fact[0] = 1.0; for (int i = 1; i <= F; ++i) fact[i] = fact[i - 1] * i;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t r = 0; r < n; ++r) {
+    double* v = (double*)malloc(sizeof(double) * nsub);
+    const float* x = X + r * F;
+    double* phi_row = out + r * K * (F + 1);
+    for (int k = 0; k < K; ++k) { for (int j = 0; j <= F; ++j) phi_row[k * (F + 1) + j] = 0.0; phi_row[k * (F + 1) + F] = base_margin; }
+    for (int t = tree_begin; t < tree_end; ++t) {
+      double* phi = phi_row + tree_info[t] * (F + 1);
+      for (unsigned S = 0; S < nsub; ++S) v[S] = shap_expect(left, right, split_index, default_left, split_cond, sum_hess, tree_offset[t], 0, x, S);
+      phi[F] += v[0];
+      for (int j = 0; j < F; ++j)
+        for (unsigned S = 0; S < nsub; ++S) {
+          if (S & (1u << j)) continue;
+          const int s = __builtin_popcount(S);
+          phi[j] += fact[s] * fact[F - s - 1] / fact[F] * (v[S | (1u << j)] - v[S]);
+        }
+    }
+    free(v);
+  }
+  free(fact);
+}

@@ -324,6 +324,24 @@ def predict_leaf(model, X, tree_begin=0, tree_end=None):
     return out
 
 
+def shap_bruteforce(model, X, tree_begin=0, tree_end=None):
+    """Exact Shapley values of the cover-weighted conditional-expectation game, by subset enumeration (F <= 12): the quantity
+    Tree SHAP / Booster.predict(pred_contribs=True) computes.  Returns float64 (n, K, F + 1); last column = bias."""
+    X = np.ascontiguousarray(X, np.float32)
+    n, F = X.shape
+    assert F <= 12, "brute force enumerates 2^F subsets"
+    K = int(model.get("num_class", 1))
+    nt = len(model["tree_info"])
+    tree_end = nt if tree_end is None else tree_end
+    out = np.zeros((n, K, F + 1), np.float64)
+    L = lib()
+    L.orc_shap_bruteforce.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_float, C.c_void_p]
+    L.orc_shap_bruteforce(_p(X), n, F, K, tree_begin, tree_end, _p(model["tree_offset"]), _p(model["tree_info"]), _p(model["left"]),
+                          _p(model["right"]), _p(model["split_index"]), _p(model["default_left"]), _p(model["split_cond"]),
+                          _p(model["sum_hess"]), C.c_float(base_margin_of(model)), _p(out))
+    return out
+
+
 def transform(model, margins):
     """PredTransform of the objective (identity / sigmoid / softmax)."""
     obj = model.get("objective", "reg:squarederror")

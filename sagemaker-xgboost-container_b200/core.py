@@ -486,11 +486,13 @@ class Booster:
             raise TypeError("Expecting data to be a DMatrix object, got: %s" % type(data))
         if validate_features:
             self._validate_features(data)
-        if pred_contribs or approx_contribs or pred_interactions:
-            raise XGBoostError("pred_contribs / pred_interactions are not implemented on the B200 path")
+        if approx_contribs or pred_interactions:
+            raise XGBoostError("approx_contribs / pred_interactions are not implemented on the B200 path (pred_contribs is)")
         ptype = 1 if output_margin else 0
         if pred_leaf:
             ptype = 6
+        if pred_contribs:
+            ptype = 2           # exact path-dependent Tree SHAP on the device, shape (n, F + 1) or (n, K, F + 1); last column = bias
         cfg = {"type": ptype, "training": bool(training), "iteration_begin": int(iteration_range[0]),
                "iteration_end": int(iteration_range[1]), "strict_shape": bool(strict_shape)}
         return get_backend().booster_predict(self.handle, data.handle, cfg)

@@ -979,7 +979,8 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
   B200_CHECK(iter_begin >= 0 && iter_begin <= iter_end && iter_end <= rounds, "Invalid iteration range: [" + std::to_string(iter_begin) + ", " + std::to_string(iter_end) + ") for a model with " + std::to_string(rounds) + " rounds");
   if (num_feature_ > 0 && !trees_.empty())
     B200_CHECK(dm->F <= num_feature_ || true, "feature count mismatch");
-  B200_CHECK(type == 0 || type == 1 || type == 6, "predict type " + std::to_string(type) + " (contributions / interactions) is not implemented on the B200 path");
+  B200_CHECK(type == 0 || type == 1 || type == 2 || type == 6, "predict type " + std::to_string(type) + " (approximate contributions / interactions) is not implemented on the B200 path");
+  if (type == 2) { predict_contribs(dm, iter_begin * K, iter_end * K, out, shape); return; }
   upload_model();
   const int tb = iter_begin * K, te = iter_end * K;
   const int64_t n = dm->n;
@@ -1066,6 +1067,57 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   CUDA_OK(cudaMemcpyAsync(scales_out, g.gs.scales, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
   Comm::get().sync_stream(s);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+}
+
+// pred_contribs: path-dependent Tree SHAP on the device (shap.cu); output [n][F + 1], or [n][K][F + 1] for multi-class models
+void Booster::predict_contribs(DMatrix* dm, int tb, int te, std::vector<float>* out, std::vector<uint64_t>* shape) {
+  cudaStream_t s = engine_stream();
+  sync_model();
+  const int K = param_.num_class;
+  const int64_t n = dm->n;
+  const int F = std::max(dm->F, num_feature_);
+  B200_CHECK(dm->F == F, "pred_contribs: the data has " + std::to_string(dm->F) + " columns, the model uses " + std::to_string(F));
+  std::vector<ShapNode> nodes; std::vector<int64_t> offs; std::vector<int> info;
+  int max_depth = 0;
+  for (int t = tb; t < te; ++t) {
+    const HostTree& h = trees_[t];
+    const int nn = h.num_nodes();
+    const size_t base = nodes.size();
+    offs.push_back((int64_t)base); info.push_back(tree_info_[t]);
+    nodes.resize(base + nn);
+    std::vector<int> depth(nn, 0);
+    for (int i = 0; i < nn; ++i) {
+      ShapNode& d = nodes[base + i];
+      d.cond = h.split_cond[i]; d.left = h.left[i]; d.right = h.right[i]; d.fidx_dl = (unsigned)h.split_index[i] | ((unsigned)h.default_left[i] << 31);
+      d.sum_hess = h.sum_hess[i]; d.mean = 0.0f;
+      if (h.left[i] >= 0) { B200_CHECK(h.left[i] > i && h.right[i] > i, "pred_contribs: children must follow their parent in the node array"); depth[h.left[i]] = depth[h.right[i]] = depth[i] + 1; }
+      max_depth = std::max(max_depth, depth[i]);
+    }
+    // cover-weighted mean value per node, children before parents (upstream FillNodeMeanValues, float arithmetic)
+    for (int i = nn - 1; i >= 0; --i) {
+      ShapNode& d = nodes[base + i];
+      if (d.left < 0) d.mean = d.cond;
+      else { float r = nodes[base + d.left].mean * nodes[base + d.left].sum_hess; r += nodes[base + d.right].mean * nodes[base + d.right].sum_hess; d.mean = r / d.sum_hess; }
+    }
+  }
+  DevBuf<ShapNode> d_sn; DevBuf<int64_t> d_off; DevBuf<int> d_info; DevBuf<float> d_out;
+  d_sn.alloc(std::max<size_t>(nodes.size(), 1)); d_off.alloc(std::max<size_t>(offs.size(), 1)); d_info.alloc(std::max<size_t>(info.size(), 1));
+  const size_t total = (size_t)n * K * (F + 1);
+  d_out.alloc(std::max<size_t>(total, 1));
+  if (!nodes.empty()) {
+    CUDA_OK(cudaMemcpyAsync(d_sn.p, nodes.data(), sizeof(ShapNode) * nodes.size(), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(d_off.p, offs.data(), sizeof(int64_t) * offs.size(), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(d_info.p, info.data(), sizeof(int) * info.size(), cudaMemcpyHostToDevice, s));
+  }
+  CUDA_OK(cudaMemsetAsync(d_out.p, 0, sizeof(float) * std::max<size_t>(total, 1), s));
+  ShapArgs sa{}; sa.X = dm->X.p; sa.n = n; sa.F = F; sa.nodes = d_sn.p; sa.tree_offset = d_off.p; sa.tree_info = d_info.p; sa.tree_begin = tb; sa.tree_end = te; sa.K = K;
+  sa.out = d_out.p; sa.base_margin = base_margin();
+  if (!dm->base_margin.empty()) { B200_CHECK(dm->base_margin.size() == (size_t)n * K, "base_margin size does not match rows x groups"); sa.base_margin_rows = dm->d_base_margin.p; }
+  launch_shap(sa, max_depth, s);
+  out->resize(total);
+  if (total) CUDA_OK(cudaMemcpyAsync(out->data(), d_out.p, sizeof(float) * total, cudaMemcpyDeviceToHost, s));
+  Comm::get().sync_stream(s);
+  if (K > 1) shape->assign({(uint64_t)n, (uint64_t)K, (uint64_t)(F + 1)}); else shape->assign({(uint64_t)n, (uint64_t)(F + 1)});
 }
 
 // device time of the predictor kernel alone (margins of all trees into the scratch buffer), for the roofline line of bench.py

@@ -84,6 +84,7 @@ class Booster {
   // inference; returns host buffer + shape
   void predict(DMatrix* dm, int type, bool training, int iter_begin, int iter_end, bool strict_shape,
                std::vector<float>* out, std::vector<uint64_t>* shape);
+  void predict_contribs(DMatrix* dm, int tree_begin, int tree_end, std::vector<float>* out, std::vector<uint64_t>* shape);
   // model IO
   std::string save_model_buffer(const std::string& format);      // "ubj" | "json"
   void load_model_buffer(const char* buf, size_t len);

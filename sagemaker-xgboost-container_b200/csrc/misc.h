@@ -43,6 +43,18 @@ struct MetricArgs {
   float aux;                // huber slope (mphe) / variance power (tweedie-nloglik)
 };
 
+// prediction contributions (shap.cu): the model subset [tree_begin, tree_end) repacked with cover and mean value per node
+struct ShapNode { float cond; int left; int right; unsigned fidx_dl; float sum_hess; float mean; };   // leaf: left == -1, cond = leaf value
+struct ShapArgs {
+  const float* X; int64_t n; int F;
+  const ShapNode* nodes; const int64_t* tree_offset; const int* tree_info;     // offsets / classes indexed from tree_begin
+  int tree_begin, tree_end, K;
+  float* out;                      // [n][K][F + 1], zero-initialised by the caller
+  const float* base_margin_rows;   // [n][K] user base margins, or nullptr -> base_margin
+  float base_margin;
+};
+void launch_shap(const ShapArgs& a, int max_depth, cudaStream_t s);
+
 void launch_gradient(const GradArgs& a, cudaStream_t s);
 void launch_sum_gpair(const float2* gp, int64_t n, double* out, cudaStream_t s);
 void launch_bin(const float* X, int64_t n, int F, int ngroups, int tw, const int* cut_ptrs, const float* cut_vals, uint8_t* bins, uint8_t* bins_tail, cudaStream_t s);

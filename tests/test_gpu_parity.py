@@ -394,6 +394,41 @@ def test_extra_metrics_and_label_checks_of_the_new_objectives(xgb):
             xgb.train(dict(objective=objective), xgb.DMatrix(X, label=yb), num_boost_round=1, verbose_eval=False)
 
 
+@pytest.mark.parametrize("objective,kind,K,missing", [("reg:squarederror", "reg", 1, 0.0), ("binary:logistic", "bin", 1, 0.15), ("multi:softprob", "multi", 3, 0.0)])
+def test_pred_contribs_are_the_exact_shapley_values(xgb, oracle, objective, kind, K, missing):
+    """Booster.predict(pred_contribs=True) (test_abalone.py:65): the device Tree SHAP against brute-force Shapley values of the
+    cover-weighted game (oracle.shap_bruteforce enumerates all 2^F feature subsets), incl. missing values, several classes and
+    iteration_range; the contributions of a row add up to its margin."""
+    n, F, rounds = 400, 8, 6
+    X, y = synth(n, F, 63, kind, K=max(K, 1), missing_frac=missing)
+    params = dict(objective=objective, max_depth=4, eta=0.4)
+    if K > 1:
+        params["num_class"] = K
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=rounds, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    m["objective"] = objective                      # the oracle derives the base margin (logit of base_score, ...) from it
+    phi = bst.predict(d, pred_contribs=True)
+    assert phi.shape == ((n, F + 1) if K == 1 else (n, K, F + 1))
+    ref = oracle.shap_bruteforce(m, X)
+    np.testing.assert_allclose(phi.reshape(n, max(K, 1), F + 1), ref, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(phi.reshape(n, max(K, 1), F + 1).sum(-1), bst.predict(d, output_margin=True).reshape(n, -1), rtol=0, atol=2e-5)
+    part = bst.predict(d, pred_contribs=True, iteration_range=(1, 4))
+    np.testing.assert_allclose(part.reshape(n, max(K, 1), F + 1), oracle.shap_bruteforce(m, X, tree_begin=1 * max(K, 1), tree_end=4 * max(K, 1)), rtol=0, atol=2e-5)
+
+
+def test_pred_contribs_add_up_to_the_margin_on_a_wide_deep_model(xgb):
+    n, F = 3000, 60
+    X, y = synth(n, F, 64, "reg", missing_frac=0.05)
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(dict(max_depth=9, eta=0.2, min_child_weight=1), d, num_boost_round=8, verbose_eval=False)
+    phi = bst.predict(d, pred_contribs=True)
+    assert phi.shape == (n, F + 1)
+    np.testing.assert_allclose(phi.sum(1), bst.predict(d, output_margin=True), rtol=0, atol=1e-4)
+    with pytest.raises(xgb.XGBoostError, match="not implemented"):
+        bst.predict(d, pred_interactions=True)
+
+
 @pytest.mark.parametrize("weighted", [False, True])
 def test_auc_matches_sklearn(xgb, weighted):
     """Native `auc` (the one HPO metric the container does not compute itself, train_utils.py:45-76) against
