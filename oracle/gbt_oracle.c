@@ -665,10 +665,23 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
     cur[0] = c; ncur = 1;
   }
   int num_leaves = 1;
+  /* One Driver::Pop batch: depthwise = every open candidate of the current depth in increasing nid; lossguide = the single best
+   * open candidate (max loss_chg, ties to the smaller nid), and an invalid top entry ends the tree (upstream Driver::Pop returns
+   * an empty batch).  [UPSTREAM src/tree/driver.h, src/tree/hist/expand_entry.h] */
+  const int lossguide = p->grow_policy == 1;
   while (ncur > 0) {
-    /* candidates of one depth, increasing nid (depthwise Driver::Pop) */
-    Cand* next = (Cand*)calloc((size_t)ncur * 2, sizeof(Cand)); int nnext = 0;
-    for (int ci = 0; ci < ncur; ++ci) {
+    Cand* next = (Cand*)calloc((size_t)ncur * 2 + 2, sizeof(Cand)); int nnext = 0;
+    int stop = 0;
+    int first = 0, last = ncur;
+    if (lossguide) {
+      int bi = 0;
+      for (int ci = 1; ci < ncur; ++ci)
+        if (cur[ci].split.loss_chg > cur[bi].split.loss_chg || (cur[ci].split.loss_chg == cur[bi].split.loss_chg && cur[ci].nid < cur[bi].nid)) bi = ci;
+      for (int ci = 0; ci < ncur; ++ci) if (ci != bi) next[nnext++] = cur[ci];     /* everything else stays open */
+      Cand tmp = cur[bi]; cur[bi] = cur[0]; cur[0] = tmp;
+      first = 0; last = 1;
+    }
+    for (int ci = first; ci < last; ++ci) {
       Cand* c = &cur[ci];
       int valid = 1;
       if (!(c->split.loss_chg > K_RT_EPS)) valid = 0;
@@ -676,7 +689,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
       else if (c->split.loss_chg < p->gamma) valid = 0;
       else if (p->max_depth > 0 && c->depth == p->max_depth) valid = 0;
       else if (p->max_leaves > 0 && num_leaves == p->max_leaves) valid = 0;
-      if (!valid) { free(c->hist); c->hist = NULL; continue; }
+      if (!valid) { free(c->hist); c->hist = NULL; if (lossguide) stop = 1; continue; }
       num_leaves++;
       /* ApplySplit / ExpandNode */
       int64_t gi = base + c->nid;
@@ -719,6 +732,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
       free(c->hist); c->hist = NULL;
     }
     free(cur); cur = next; ncur = nnext;
+    if (stop) { for (int ci = 0; ci < ncur; ++ci) free(cur[ci].hist); ncur = 0; }
   }
   free(cur);
   free(tree_mask); free(level_masks); free(node_mask);

@@ -279,7 +279,7 @@ struct PinnedPool {
   void reset() { cur = 0; off = 0; }
 };
 
-struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves; float eta, lambda, alpha, gamma, mcw, mds, bynode; unsigned seed; int world, root_mode; int64_t n; };
+struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves, lg_iters; float eta, lambda, alpha, gamma, mcw, mds, bynode; unsigned seed; int world, root_mode; int64_t n; };
 // The per-tree launch sequence as CUDA graphs.  On one GPU it is a single graph; with NCCL it is cut into SEGMENTS at every
 // collective (root + one per level): the segments are replayed as graphs and the all-reduces are issued between them as
 // ordinary stream operations, so no NCCL call is ever captured (a capture with lazily connecting NCCL channels hung an
@@ -293,6 +293,7 @@ struct TreeGraph {
 
 struct GrowerImpl {
   int64_t n = 0; int ngroups = 0, tw = 0, max_depth = 0, max_nodes = 0, cap_nodes = 0, max_level_nodes = 0, region = 0;
+  int lg_iters = 0;                        // grow_policy=lossguide: expansions per tree (0 = depthwise)
   size_t slot_stride = 0;                  // GH64 entries per histogram slot
   int64_t gp_stride = 0;                   // rows reserved per class in gpair
   int64_t global_n = 0;                    // rows of the whole job (sum over ranks)
@@ -308,11 +309,11 @@ struct GrowerImpl {
   DevBuf<DevNode> packed; std::vector<TreeGraph> graphs; std::vector<char> eager_done;
   TreeGraph* capturing = nullptr;          // set while enqueue_tree runs under stream capture: collectives cut the capture
 
-  void ensure(int64_t n_, int ngroups_, int tw_, int max_depth_, int K) {
+  void ensure(int64_t n_, int ngroups_, int tw_, int max_depth_, int K, int lg_iters_ = 0) {
     const int64_t stride_ = (n_ + 63) & ~(int64_t)63;
-    if (n == n_ && ngroups == ngroups_ && tw == tw_ && max_depth == max_depth_ && gpair.n >= (size_t)stride_ * K + 512) return;
-    B200_CHECK(max_depth_ >= 1 && max_depth_ <= kMaxDepth, "max_depth must be in [1, 16] for the B200 depth-wise hist builder");
-    n = n_; ngroups = ngroups_; tw = tw_; max_depth = max_depth_; gp_stride = stride_; root_h_valid = false;
+    if (n == n_ && ngroups == ngroups_ && tw == tw_ && max_depth == max_depth_ && lg_iters == lg_iters_ && gpair.n >= (size_t)stride_ * K + 512) return;
+    if (lg_iters_ == 0) B200_CHECK(max_depth_ >= 1 && max_depth_ <= kMaxDepth, "max_depth must be in [1, 16] for the B200 depth-wise hist builder");
+    n = n_; ngroups = ngroups_; tw = tw_; max_depth = max_depth_; lg_iters = lg_iters_; gp_stride = stride_; root_h_valid = false;
     if (peer_reduce_active()) {                     // peers still map the buffers that are about to be freed: unmap everywhere first
       peer_reduce_close();
       DevBuf<unsigned> bar; bar.alloc(1); bar.zero(engine_stream());
@@ -320,15 +321,20 @@ struct GrowerImpl {
       Comm::get().sync_stream(engine_stream());
     }
     for (auto& tg : graphs) tg.destroy();
-    max_nodes = (1 << (max_depth + 1)) - 1;
+    size_t pool_slots;
+    if (lg_iters > 0) {            // lossguide: two children per expansion; "levels" 0 / 1 hold the split node and its children
+      max_nodes = 2 * lg_iters + 1; max_level_nodes = 2; region = 0;
+      pool_slots = (size_t)lg_iters + kLgFirstFreeSlot;         // root, staging, one fresh slot per expansion
+    } else {
+      max_nodes = (1 << (max_depth + 1)) - 1; max_level_nodes = 1 << (max_depth - 1); region = max_level_nodes;
+      pool_slots = 2 * (size_t)region;
+    }
     cap_nodes = (max_nodes + 15) & ~15;
-    max_level_nodes = 1 << (max_depth - 1);
-    region = max_level_nodes;
     slot_stride = hist_slot_entries(ngroups, tw);
-    const size_t pool_bytes = 2 * (size_t)region * slot_stride * sizeof(GH64);
+    const size_t pool_bytes = pool_slots * slot_stride * sizeof(GH64);
     size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-    B200_CHECK(pool_bytes < free_b / 2 + hist_pool.n * sizeof(GH64), "histogram pool for this max_depth / feature count does not fit in device memory");
-    hist_pool.alloc(2 * (size_t)region * slot_stride);
+    B200_CHECK(pool_bytes < free_b / 2 + hist_pool.n * sizeof(GH64), "histogram pool for this max_depth / max_leaves / feature count does not fit in device memory");
+    hist_pool.alloc(pool_slots * slot_stride);
     ridx0.alloc(n); ridx1.alloc(n);
     gpair.alloc((size_t)gp_stride * K + 512); gpair.zero(engine_stream()); gp0.alloc(n); gp1.alloc(n); err.alloc(1); dsum.alloc(4);
     root_h_cache.alloc(slot_stride);
@@ -344,6 +350,7 @@ struct GrowerImpl {
     size_t o_bnid = take(4 * L), o_bsub = take(4 * L), o_bps = take(4 * L), o_bcount = take(4), o_bprefix = take(4 * (L + 1));
     size_t o_action = take(4 * L), o_tprefix = take(4 * (L + 1)), o_tleft = take(4 * (size_t)max_tiles), o_toff = take(4 * (size_t)max_tiles);
     size_t o_flags = take((size_t)n + 16), o_nleaves = take(4), o_scales = take(16), o_absmax = take(8);
+    size_t o_depth = take(4 * N), o_open = take(N), o_nslots = take(4), o_lgdone = take(4);
     state_block.alloc(off); state_block.zero(engine_stream());
     unsigned char* b = state_block.p;
     gs.seg_begin = (unsigned*)(b + o_seg_begin); gs.seg_count = (unsigned*)(b + o_seg_count); gs.hist_slot = (int*)(b + o_slot);
@@ -353,6 +360,7 @@ struct GrowerImpl {
     gs.build_nid = (int*)(b + o_bnid); gs.build_sub_nid = (int*)(b + o_bsub); gs.build_parent_slot = (int*)(b + o_bps);
     gs.build_count = (int*)(b + o_bcount); gs.build_prefix = (unsigned*)(b + o_bprefix);
     gs.part_action = (int*)(b + o_action); gs.tile_prefix = (unsigned*)(b + o_tprefix); gs.tile_left = (unsigned*)(b + o_tleft); gs.tile_off = (unsigned*)(b + o_toff);
+    gs.depth = (int*)(b + o_depth); gs.open = b + o_open; gs.n_slots = (int*)(b + o_nslots); gs.lg_done = (int*)(b + o_lgdone);
     gs.flags = b + o_flags; gs.n_leaves = (int*)(b + o_nleaves); gs.scales = (float*)(b + o_scales); gs.absmax = (unsigned*)(b + o_absmax);
     // ---- tree block: [n_nodes + pad to 64][5 int arrays][4 float arrays][u8 array]
     tree_block_bytes = 64 + 9 * 4 * N + N;
@@ -383,6 +391,13 @@ struct GrowerImpl {
 // once), so that N ranks and one GPU train bit-identical models on the same data
 static int job_grad_bits(int64_t global_n) { return grad_bits_for(global_n); }
 static int job_window_rows(int64_t global_n) { return window_rows_for(global_n); }
+
+// grow_policy=lossguide: expansions per tree = leaves - 1, bounded by max_leaves or by a full tree of max_depth
+static int lossguide_iters(const TrainParam& p) {
+  if (!p.lossguide) return 0;
+  if (p.max_leaves > 0) return std::max(1, p.max_leaves - 1);
+  return (1 << p.max_depth) - 1;
+}
 
 static TrainParamDev to_dev(const TrainParam& p) {
   TrainParamDev d; d.eta = p.eta; d.lambda = p.lambda; d.alpha = p.alpha; d.gamma = p.gamma; d.min_child_weight = p.min_child_weight;
@@ -489,14 +504,23 @@ void Booster::configure() {
   auto bo = raw_params_.find("booster");
   if (bo != raw_params_.end()) B200_CHECK(bo->second == "gbtree", "Only booster=gbtree is implemented on the B200 hist path (got " + bo->second + ")");
   auto gp = raw_params_.find("grow_policy");
-  if (gp != raw_params_.end()) B200_CHECK(gp->second == "depthwise", "grow_policy=" + gp->second + " is not implemented on the B200 hist path yet (depthwise only)");
+  if (gp != raw_params_.end()) {
+    B200_CHECK(gp->second == "depthwise" || gp->second == "lossguide", "Invalid grow_policy: " + gp->second + " (depthwise, lossguide)");
+    p.lossguide = gp->second == "lossguide" ? 1 : 0;
+  }
+  if (p.lossguide) {
+    B200_CHECK(p.max_depth >= 0 && p.max_depth <= kMaxDepth, "max_depth must be in [0, 16]");
+    B200_CHECK(p.max_leaves > 0 || p.max_depth > 0, "grow_policy=lossguide needs max_leaves > 0 or max_depth > 0");
+    B200_CHECK(p.max_leaves <= 4096, "max_leaves above 4096 is not supported by the B200 lossguide builder");
+    B200_CHECK(p.colsample_bytree >= 1.0f && p.colsample_bylevel >= 1.0f && p.colsample_bynode >= 1.0f, "column sampling (colsample_*) with grow_policy=lossguide is not implemented by the B200 hist builder");
+  }
   auto bs = raw_params_.find("base_score");
   if (bs != raw_params_.end() && !bs->second.empty()) {
     base_score_ = std::stof(bs->second); base_score_set_ = true;
     if (p.objective == kBinaryLogistic || p.objective == kRegLogistic || p.objective == kLogitRaw)
       B200_CHECK(base_score_ > 0.0f && base_score_ < 1.0f, "Check failed: base_score > 0.0f && base_score < 1.0f base_score must be in (0,1) for logistic loss");
   }
-  B200_CHECK(p.max_depth >= 1, "max_depth=" + std::to_string(p.max_depth) + " (no depth limit) needs grow_policy=lossguide, which the B200 depth-wise hist builder does not implement; use max_depth in [1, 16]");
+  if (!p.lossguide) B200_CHECK(p.max_depth >= 1, "max_depth=" + std::to_string(p.max_depth) + " (no depth limit) needs grow_policy=lossguide with max_leaves; the depth-wise builder takes max_depth in [1, 16]");
   if (p.max_bin > 256) p.max_bin = 256;            // uint8 bin codes (the Python layer warns)
   param_ = p;
   configured_ = true;
@@ -653,7 +677,7 @@ void Booster::update_one_iter(int iter, DMatrix* dtrain) {
   const int K = param_.num_class;
   if (!grower_) grower_ = new GrowerImpl();
   GrowerImpl& g = *grower_;
-  g.ensure(dtrain->n, dtrain->ngroups, dtrain->tw, param_.max_depth, K);
+  g.ensure(dtrain->n, dtrain->ngroups, dtrain->tw, param_.max_depth, K, lossguide_iters(param_));
   if (!labels_checked_) {
     // label-range errors must surface from update() (the container maps them to UserError, train.py:461-467)
     const std::vector<float>& y = dtrain->labels;
@@ -740,7 +764,37 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   ea.colsample_bynode = mask ? param_.colsample_bynode : 1.0f; ea.seed = param_.seed; ea.tree_index = g.tree_index_dev.p;
   launch_eval(ea, 1, s);
 
-  for (int L = 0; L < D; ++L) {
+  const int lg_iters = lossguide_iters(param_);
+  for (int it = 0; it < lg_iters; ++it) {                 // grow_policy=lossguide: one expansion per iteration (tree.cu apply_lossguide_kernel)
+    ApplyArgs aa{}; aa.gs = g.gs; aa.tree = g.ta; aa.cut_ptrs = dtrain->d_cut_ptrs.p; aa.cut_vals = dtrain->d_cut_vals.p; aa.min_vals = dtrain->d_min_vals.p;
+    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups + (bm.tw > 0 ? 1 : 0); aa.level = 0; aa.max_level_nodes = g.max_level_nodes;
+    launch_apply_lossguide(aa, it, s);
+    // live row segments always sit in buffer set 0; the partition writes the children into set 1 and they are copied straight back
+    const bool carry_tail = bm.tw == 4;
+    PartArgs pa{}; pa.gs = g.gs; pa.tree = g.ta; pa.bins_col = bm.bins_col; pa.n = bm.n;
+    pa.ridx_cur = it == 0 ? nullptr : g.ridx0.p; pa.ridx_next = g.ridx1.p;
+    pa.gp_cur = it == 0 ? g.gpair.p + (size_t)k * g.gp_stride : g.gp0.p; pa.gp_next = g.gp1.p;
+    pa.tl_cur = !carry_tail ? nullptr : (it == 0 ? reinterpret_cast<const unsigned*>(bm.bins_tail) : g.tl0.p); pa.tl_next = !carry_tail ? nullptr : g.tl1.p;
+    pa.has_missing = bm.has_missing; pa.level = 0; pa.max_level_nodes = g.max_level_nodes;
+    launch_partition(pa, max_tiles, 1, s);
+    launch_lg_copy_back(pa, g.ridx0.p, g.gp0.p, g.tl0.p, max_tiles, s);
+    launch_zero_build_slots(g.gs, g.hist_pool.p, g.slot_stride, 1, s);
+    ha.ridx = g.ridx0.p; ha.gpair = g.gp0.p; ha.tail_pos = carry_tail ? g.tl0.p : nullptr; ha.accumulate_sum = 0;
+    ha.rows_counter = profile_ ? prof_rows_.p + 1 : nullptr;
+    prof_begin(1);
+    launch_hist_build(ha, num_sms, s);
+    prof_end();
+    if (comm.distributed()) {                              // the collective needs a fixed address: go through the staging slot
+      launch_lg_stage(g.gs, g.hist_pool.p, g.slot_stride, 1, s);
+      allreduce_hist(g.hist_pool.p + (size_t)kLgStageSlot * g.slot_stride, g.slot_stride * 2);
+      launch_lg_stage(g.gs, g.hist_pool.p, g.slot_stride, 0, s);
+    }
+    launch_subtract(g.gs, g.hist_pool.p, g.slot_stride, 1, s);
+    ea.level = 1; ea.feat_mask = nullptr;
+    launch_eval(ea, 2, s);
+  }
+
+  for (int L = 0; L < D && lg_iters == 0; ++L) {
     const bool final_level = (L == D - 1);
     const int next_base = ((L + 1) & 1) * g.region, next_half = 1 << L;
     ApplyArgs aa{}; aa.gs = g.gs; aa.tree = g.ta; aa.cut_ptrs = dtrain->d_cut_ptrs.p; aa.cut_vals = dtrain->d_cut_vals.p; aa.min_vals = dtrain->d_min_vals.p;
@@ -822,7 +876,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     key.uid = dtrain->uid; key.binned_version = dtrain->binned_version; key.root_mode = root_mode;
     key.margin = cache.margin.p; key.mask = mask; key.packed = g.packed.p; key.max_depth = param_.max_depth;
     key.bins = dtrain->bins.p; key.bins_col = dtrain->bins_col.p; key.cuts = dtrain->d_cut_vals.p;     // re-binning invalidates the capture
-    key.max_leaves = param_.max_leaves; key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
+    key.max_leaves = param_.max_leaves; key.lg_iters = lossguide_iters(param_); key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
     key.mcw = param_.min_child_weight; key.mds = param_.max_delta_step; key.world = Comm::get().world(); key.n = dtrain->n;
     key.bynode = param_.colsample_bynode; key.seed = param_.seed;
     if (tg.segs.empty() || memcmp(&tg.key, &key, sizeof key) != 0) {
@@ -1030,7 +1084,7 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   dm->ensure_binned(param_.max_bin);
   if (!grower_) grower_ = new GrowerImpl();
   GrowerImpl& g = *grower_;
-  g.ensure(dm->n, dm->ngroups, dm->tw, param_.max_depth, param_.num_class);
+  g.ensure(dm->n, dm->ngroups, dm->tw, param_.max_depth, param_.num_class, lossguide_iters(param_));
   hist_configure();
   const int64_t rows = row_ids ? n_ids : dm->n;
   B200_CHECK(rows <= dm->n, "debug_build_root_hist: more row ids than rows");

@@ -99,6 +99,7 @@ struct TrainParam {
   int objective = kSquaredError;
   int num_class = 1;
   int max_depth = 6, max_leaves = 0, max_bin = 256;
+  int lossguide = 0;            // grow_policy: 0 depthwise, 1 lossguide
   float eta = 0.3f, lambda = 1.0f, alpha = 0.0f, gamma = 0.0f, min_child_weight = 1.0f, max_delta_step = 0.0f;
   float scale_pos_weight = 1.0f, subsample = 1.0f, colsample_bytree = 1.0f, colsample_bylevel = 1.0f, colsample_bynode = 1.0f;
   unsigned seed = 0;
@@ -140,6 +141,8 @@ struct GrowState {
   unsigned* tile_left; unsigned* tile_off;      // per tile
   unsigned char* flags;                         // per row position: goes left
   int* n_nodes; int* n_leaves;
+  // grow_policy=lossguide: depth and open-candidate flag per node, next free histogram slot, sticky end-of-tree flag
+  int* depth; unsigned char* open; int* n_slots; int* lg_done;
   float* scales;                                // [0]=sg [1]=sh [2]=1/sg [3]=1/sh
   unsigned* absmax;                             // [0]=max|g| bits [1]=max h bits
 };

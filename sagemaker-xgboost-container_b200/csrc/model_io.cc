@@ -180,7 +180,7 @@ JPtr Booster::config_to_json() {
   JPtr ttp = JValue::Object();
   auto f = [&](const char* k, float v) { ttp->set(k, S(float_repr(v))); }; auto i = [&](const char* k, int v) { ttp->set(k, S(std::to_string(v))); };
   f("alpha", param_.alpha); f("colsample_bylevel", param_.colsample_bylevel); f("colsample_bynode", param_.colsample_bynode); f("colsample_bytree", param_.colsample_bytree);
-  f("eta", param_.eta); f("gamma", param_.gamma); ttp->set("grow_policy", S("depthwise")); f("lambda", param_.lambda); i("max_bin", param_.max_bin);
+  f("eta", param_.eta); f("gamma", param_.gamma); ttp->set("grow_policy", S(param_.lossguide ? "lossguide" : "depthwise")); f("lambda", param_.lambda); i("max_bin", param_.max_bin);
   f("max_delta_step", param_.max_delta_step); i("max_depth", param_.max_depth); i("max_leaves", param_.max_leaves); f("min_child_weight", param_.min_child_weight);
   f("subsample", param_.subsample);
   gb->set("tree_train_param", ttp);

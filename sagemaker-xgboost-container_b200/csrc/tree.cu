@@ -57,6 +57,7 @@ __device__ __forceinline__ unsigned long long cand_key(float loss, int f, int or
 __global__ void init_tree_kernel(GrowState gs, TreeArrays t, unsigned n, int root_slot, int max_level_nodes) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   *gs.n_nodes = 1; *gs.n_leaves = 1;
+  *gs.n_slots = kLgFirstFreeSlot; *gs.lg_done = 0; gs.depth[0] = 0; gs.open[0] = 0;
   for (int d = 0; d < kMaxDepth + 2; ++d) gs.level_count[d] = 0;
   gs.level_count[0] = 1; gs.level_nodes[0] = 0;
   gs.seg_begin[0] = 0; gs.seg_count[0] = n; gs.hist_slot[0] = root_slot;
@@ -305,6 +306,132 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// grow_policy=lossguide: one node per iteration (upstream Driver::Pop in loss-guided mode: the open candidate with the largest
+// loss_chg, ties to the smaller node id; an INVALID top candidate ends the tree).  The per-level machinery is reused with
+// "level" 0 = the node being split and "level" 1 = its two children: this kernel (a) registers the candidates evaluated by the
+// previous iteration, (b) picks and validates the best one, (c) expands it exactly like apply_kernel does for a whole level.
+// Histogram slots: the built child gets a fresh slot, its sibling inherits the parent's (subtract_kernel works in place).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) apply_lossguide_kernel(ApplyArgs a, int iter) {
+  __shared__ unsigned long long s_key[8];
+  GrowState& gs = a.gs; TreeArrays& t = a.tree;
+  const double isg = (double)gs.scales[2], ish = (double)gs.scales[3];
+  const int src = iter == 0 ? 0 : 1;
+  const int cnt = gs.level_count[src];
+  const int* nodes = gs.level_nodes + (size_t)src * a.max_level_nodes;
+  if (iter == 0 && threadIdx.x == 0 && cnt > 0) {
+    t.base_weight[0] = gs.weight[0]; t.sum_hess[0] = (float)((double)gs.node_sum[0].h * ish); t.split_cond[0] = a.p.eta * gs.weight[0];
+  }
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {        // (a) Driver::Push: candidates with loss_chg > eps enter the queue
+    const int nid = nodes[i];
+    SplitCand best = gs.best_group[(size_t)nid * a.ngroups];
+    unsigned long long bk = cand_key(best.loss_chg, best.feature, best.ord);
+    for (int g = 1; g < a.ngroups; ++g) {
+      SplitCand c = gs.best_group[(size_t)nid * a.ngroups + g];
+      unsigned long long k = cand_key(c.loss_chg, c.feature, c.ord);
+      if (k > bk) { bk = k; best = c; }
+    }
+    gs.best[nid] = best;
+    gs.open[nid] = best.loss_chg > 1e-6f ? 1 : 0;
+  }
+  __syncthreads();
+  const int n0 = *gs.n_nodes;
+  unsigned long long key = 0ull;                               // (b) arg-max of (loss_chg, -nid) over the open candidates
+  for (int nid = threadIdx.x; nid < n0; nid += blockDim.x)
+    if (gs.open[nid]) { unsigned long long k = ((unsigned long long)__float_as_uint(gs.best[nid].loss_chg) << 32) | (unsigned long long)(0xffffffffu - (unsigned)nid); key = k > key ? k : key; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long x = __shfl_xor_sync(0xffffffffu, key, o); key = x > key ? x : key; }
+  if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 1; w < 8; ++w) key = s_key[w] > key ? s_key[w] : key;
+  bool stop = *gs.lg_done != 0 || key == 0ull;
+  int nid = 0; SplitCand best{}; GH64 tot{};
+  if (!stop) {
+    nid = (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+    best = gs.best[nid]; tot = gs.node_sum[nid];
+    bool ok = best.loss_chg > 1e-6f;                                            // ExpandEntry::IsValid
+    if (ok && (best.HL == 0 || tot.h - best.HL == 0)) ok = false;
+    if (ok && best.loss_chg < a.p.gamma) ok = false;
+    if (ok && a.p.max_depth > 0 && gs.depth[nid] == a.p.max_depth) ok = false;
+    if (ok && a.p.max_leaves > 0 && *gs.n_leaves == a.p.max_leaves) ok = false;
+    stop = !ok;
+  }
+  if (stop) {
+    *gs.lg_done = 1;
+    gs.level_count[0] = 0; gs.level_count[1] = 0; *gs.build_count = 0; gs.part_action[0] = 0; gs.tile_prefix[0] = 0; gs.tile_prefix[1] = 0;
+    return;
+  }
+  gs.open[nid] = 0;                                            // (c) expand
+  const int Lc = n0, Rc = n0 + 1, d = gs.depth[nid];
+  const long long GLq = best.GL, HLq = best.HL, GRq = tot.g - best.GL, HRq = tot.h - best.HL;
+  const double GL = (double)GLq * isg, HL = (double)HLq * ish, GR = (double)GRq * isg, HR = (double)HRq * ish;
+  const float wl = calc_weight(a.p, GL, HL), wr = calc_weight(a.p, GR, HR);
+  const int cb = a.cut_ptrs[best.feature];
+  const float thr = best.dleft ? (best.bin < 0 ? a.min_vals[best.feature] : a.cut_vals[cb + best.bin]) : a.cut_vals[cb + best.bin];
+  t.left[nid] = Lc; t.right[nid] = Rc; t.split_index[nid] = best.feature; t.split_cond[nid] = thr;
+  t.split_bin[nid] = best.bin; t.default_left[nid] = (unsigned char)best.dleft;
+  t.base_weight[nid] = gs.weight[nid]; t.loss_chg[nid] = best.loss_chg; t.sum_hess[nid] = (float)((double)tot.h * ish);
+  const int ch[2] = {Lc, Rc}; const float cw[2] = {wl, wr}; const double chh[2] = {HL, HR};
+  for (int s = 0; s < 2; ++s) {
+    const int c = ch[s];
+    t.left[c] = -1; t.right[c] = -1; t.parent[c] = nid; t.split_index[c] = 0; t.split_bin[c] = -1; t.default_left[c] = 0;
+    t.split_cond[c] = a.p.eta * cw[s]; t.base_weight[c] = a.p.eta * cw[s]; t.loss_chg[c] = 0.f; t.sum_hess[c] = (float)chh[s];
+    gs.depth[c] = d + 1; gs.open[c] = 0;
+  }
+  gs.node_sum[Lc].g = GLq; gs.node_sum[Lc].h = HLq; gs.node_sum[Rc].g = GRq; gs.node_sum[Rc].h = HRq;
+  gs.seg_begin[Lc] = 0; gs.seg_count[Lc] = 0; gs.seg_begin[Rc] = 0; gs.seg_count[Rc] = 0;      // set by part_scan
+  *gs.n_nodes = n0 + 2;
+  const int leaves = *gs.n_leaves + 1;
+  *gs.n_leaves = leaves;
+  // ExpandEntry::ChildIsValid: children that could never split are not evaluated (no partition, no histogram)
+  const bool children_evaluated = !(a.p.max_depth > 0 && d + 1 >= a.p.max_depth) && !(a.p.max_leaves > 0 && leaves >= a.p.max_leaves);
+  gs.level_nodes[0] = nid; gs.level_count[0] = 1;
+  gs.part_action[0] = children_evaluated ? 1 : 0;
+  gs.tile_prefix[0] = 0; gs.tile_prefix[1] = children_evaluated ? (gs.seg_count[nid] + kPartTile - 1) / kPartTile : 0u;
+  if (children_evaluated) {
+    int* nxt = gs.level_nodes + (size_t)a.max_level_nodes;
+    nxt[0] = Lc; nxt[1] = Rc; gs.level_count[1] = 2;
+    const bool fewer_right = HRq < HLq;
+    const int bld = fewer_right ? Rc : Lc, sub = fewer_right ? Lc : Rc;
+    const int slot = (*gs.n_slots)++;
+    gs.hist_slot[bld] = slot; gs.hist_slot[sub] = gs.hist_slot[nid];
+    gs.build_nid[0] = bld; gs.build_sub_nid[0] = sub; gs.build_parent_slot[0] = gs.hist_slot[nid];
+    *gs.build_count = 1;
+  } else { gs.level_count[1] = 0; *gs.build_count = 0; }
+}
+
+// lossguide keeps every live row segment in ONE buffer set: the children written by the partition go straight back
+__global__ void __launch_bounds__(256) lg_copy_back_kernel(PartArgs a, unsigned* ridx_dst, float2* gp_dst, unsigned* tl_dst) {
+  const GrowState& gs = a.gs;
+  if (gs.level_count[0] <= 0 || !gs.part_action[0]) return;
+  const int nid = gs.level_nodes[0];
+  const unsigned b = gs.seg_begin[nid], c = gs.seg_count[nid];
+  for (unsigned p = b + blockIdx.x * blockDim.x + threadIdx.x; p < b + c; p += gridDim.x * blockDim.x) {
+    ridx_dst[p] = a.ridx_next[p]; gp_dst[p] = a.gp_next[p];
+    if (a.tl_next) tl_dst[p] = a.tl_next[p];
+  }
+}
+
+__global__ void __launch_bounds__(256) zero_build_slots_kernel(GrowState gs, GH64* pool, size_t stride) {
+  const int r = blockIdx.x;
+  if (r >= *gs.build_count) return;
+  GH64* h = pool + (size_t)gs.hist_slot[gs.build_nid[r]] * stride;
+  GH64 z; z.g = 0; z.h = 0;
+  for (size_t e = (size_t)blockIdx.y * blockDim.x + threadIdx.x; e < stride; e += (size_t)gridDim.y * blockDim.x) h[e] = z;
+}
+
+// multi-rank lossguide: the collective needs a fixed address, the freshly built slot is chosen on the device
+__global__ void __launch_bounds__(256) lg_stage_kernel(GrowState gs, GH64* pool, size_t stride, int to_stage) {
+  if (*gs.build_count <= 0) return;
+  GH64* slot = pool + (size_t)gs.hist_slot[gs.build_nid[0]] * stride;
+  GH64* stage = pool + (size_t)kLgStageSlot * stride;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < stride; e += (size_t)gridDim.x * blockDim.x) {
+    if (to_stage) stage[e] = slot[e]; else slot[e] = stage[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // row partition (stable), fused with the prediction-cache update for rows whose node became a leaf
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int find_node_of_tile(const unsigned* tile_prefix, int cnt, unsigned tile) {
@@ -510,6 +637,16 @@ void launch_init_tree(const GrowState& gs, const TreeArrays& t, unsigned n, int 
 void launch_scales(const GrowState& gs, int grad_bits, cudaStream_t s) { scales_kernel<<<1, 32, 0, s>>>(gs, grad_bits); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_eval(const EvalArgs& a, int max_nodes_level, cudaStream_t s) {
   dim3 grid(max_nodes_level, a.ngroups + (a.tw > 0 ? 1 : 0)); eval_kernel<<<grid, 32 * kEvalSegs, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+}
+void launch_apply_lossguide(const ApplyArgs& a, int iter, cudaStream_t s) { apply_lossguide_kernel<<<1, 256, 0, s>>>(a, iter); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
+void launch_lg_copy_back(const PartArgs& a, unsigned* ridx_dst, float2* gp_dst, unsigned* tl_dst, unsigned max_tiles, cudaStream_t s) {
+  lg_copy_back_kernel<<<max_tiles < 1184u ? max_tiles : 1184u, 256, 0, s>>>(a, ridx_dst, gp_dst, tl_dst); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+}
+void launch_zero_build_slots(const GrowState& gs, GH64* pool, size_t slot_entries, int max_build, cudaStream_t s) {
+  dim3 grid(max_build, (unsigned)((slot_entries + 1023) / 1024)); zero_build_slots_kernel<<<grid, 256, 0, s>>>(gs, pool, slot_entries); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
+}
+void launch_lg_stage(const GrowState& gs, GH64* pool, size_t slot_entries, int to_stage, cudaStream_t s) {
+  lg_stage_kernel<<<(unsigned)((slot_entries + 1023) / 1024), 256, 0, s>>>(gs, pool, slot_entries, to_stage); ++g_kernel_launches; CUDA_OK(cudaGetLastError());
 }
 void launch_apply(const ApplyArgs& a, cudaStream_t s) { apply_kernel<<<1, 256, 0, s>>>(a); ++g_kernel_launches; CUDA_OK(cudaGetLastError()); }
 void launch_partition(const PartArgs& a, unsigned max_tiles, int max_nodes_level, cudaStream_t s) {

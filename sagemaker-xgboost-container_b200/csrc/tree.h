@@ -57,6 +57,12 @@ struct HistArgs {
   unsigned long long* rows_counter;   // optional: += rows processed by this launch (profiling)
 };
 
+// grow_policy=lossguide (one expansion per iteration; tree.cu)
+constexpr int kLgRootSlot = 0, kLgStageSlot = 1, kLgFirstFreeSlot = 2;     // histogram pool slots: root, all-reduce staging, then one per expansion
+void launch_apply_lossguide(const ApplyArgs& a, int iter, cudaStream_t s);
+void launch_lg_copy_back(const PartArgs& a, unsigned* ridx_dst, float2* gp_dst, unsigned* tl_dst, unsigned max_tiles, cudaStream_t s);
+void launch_zero_build_slots(const GrowState& gs, GH64* pool, size_t slot_entries, int max_build, cudaStream_t s);
+void launch_lg_stage(const GrowState& gs, GH64* pool, size_t slot_entries, int to_stage, cudaStream_t s);
 void launch_hist_build(const HistArgs& a, int num_sms, cudaStream_t stream);
 void hist_configure();     // one-time function attributes (must happen outside stream capture)
 const char* hist_last_kernel();   // name of the kernel variant the last launch used (profiling / tests)

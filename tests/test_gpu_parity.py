@@ -429,6 +429,42 @@ def test_pred_contribs_add_up_to_the_margin_on_a_wide_deep_model(xgb):
         bst.predict(d, pred_interactions=True)
 
 
+@pytest.mark.parametrize("hp,objective,kind,n,F", [
+    (dict(max_leaves=16, max_depth=0), "reg:squarederror", "reg", 20000, 28),
+    (dict(max_leaves=0, max_depth=4), "reg:squarederror", "reg", 8000, 100),       # bounded by depth only: ends as a full tree
+    (dict(max_leaves=12, max_depth=3, gamma=2.0), "binary:logistic", "bin", 15000, 12),   # a top candidate at max_depth ends the tree early
+    (dict(max_leaves=40, max_depth=0, min_child_weight=5, eta=0.2), "binary:logistic", "bin", 30000, 40),
+])
+def test_lossguide_growth_matches_oracle(xgb, oracle, hp, objective, kind, n, F):
+    """grow_policy=lossguide (hyperparameter_validation.py accepts it with max_leaves): best-first expansion, one node per
+    iteration, node ids in expansion order -- structure, leaf values and pred_leaf against the oracle's restatement of
+    upstream's loss-guided Driver."""
+    rounds = 5
+    X, y = synth(n, F, 97, kind)
+    params = dict(dict(objective=objective, tree_method="hist", grow_policy="lossguide", eta=0.3), **hp)
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=rounds, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, rounds).model()
+    assert first_structural_difference(m, mr) is None
+    assert_same_structure(m, mr)
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    if hp["max_leaves"]:
+        leaves = [int((m["left"][a:b] == -1).sum()) for a, b in zip(m["tree_offset"][:-1], m["tree_offset"][1:])]
+        assert max(leaves) <= hp["max_leaves"]
+    np.testing.assert_array_equal(bst.predict(d, pred_leaf=True).astype(np.int32), oracle.predict_leaf(mr, X))
+    np.testing.assert_allclose(bst.predict(d, output_margin=True), oracle.predict_margin(mr, X).ravel(), rtol=0, atol=MARGIN_TOL)
+    if hp["max_leaves"] == 40:          # best-first growth stops at 40 leaves: not a level-complete tree
+        assert max(leaves) == 40
+        t0 = slice(m["tree_offset"][0], m["tree_offset"][1])
+        depth = np.zeros(t0.stop - t0.start, int)
+        for i, p in enumerate(m["parent"][t0]):
+            if i:
+                depth[i] = depth[p] + 1
+        leaf_depths = depth[m["left"][t0] == -1]
+        assert leaf_depths.max() > leaf_depths.min()
+
+
 @pytest.mark.parametrize("weighted", [False, True])
 def test_auc_matches_sklearn(xgb, weighted):
     """Native `auc` (the one HPO metric the container does not compute itself, train_utils.py:45-76) against
