@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     out, n, F, rounds, objective = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5]
+    extra = eval(sys.argv[6]) if len(sys.argv) > 6 else {}          # test-supplied dict literal of extra hyperparameters
     import sagemaker_xgboost_container_b200 as xgb
     from sagemaker_xgboost_container_b200 import collective
     from util import synth
@@ -22,7 +23,7 @@ def main():
     lo, hi = rank * n // world, (rank + 1) * n // world
     d = xgb.DMatrix(X[lo:hi], label=y[lo:hi])
     res = {}
-    bst = xgb.train(dict(objective=objective, max_depth=5, eta=0.3, max_bin=256), d, num_boost_round=rounds, evals=[(d, "train")],
+    bst = xgb.train(dict(dict(objective=objective, max_depth=5, eta=0.3, max_bin=256), **extra), d, num_boost_round=rounds, evals=[(d, "train")],
                     evals_result=res, verbose_eval=False)
     if rank == 0:
         with open(out + ".path", "w") as f:
