@@ -28,6 +28,11 @@ def _from_cstr_array(ptr, n):
     return [ptr[i].decode("utf-8") for i in range(n)]
 
 
+_utf8_and_size = C.pythonapi.PyUnicode_AsUTF8AndSize
+_utf8_and_size.restype = C.c_void_p
+_utf8_and_size.argtypes = [C.py_object, C.POINTER(C.c_ssize_t)]
+
+
 class CudaBackend:
     """Thin, stateless wrapper: one method per C-ABI entry point."""
 
@@ -106,12 +111,18 @@ class CudaBackend:
 
     def dmatrix_from_csv(self, payload, delimiter=","):
         """Device-side CSV parse (csv.cu).  Returns (handle, status); handle is None unless status == 0."""
-        if isinstance(payload, str):
-            payload = payload.encode("utf-8")
         h = C.c_void_p()
         st = C.c_int(0)
-        self._check(self.lib.XGB200DMatrixCreateFromCSV(C.c_char_p(payload), C.c_ulong(len(payload)), C.c_char(delimiter.encode("ascii")),
-                                                        C.byref(st), C.byref(h)))
+        if isinstance(payload, str):
+            # CPython caches the UTF-8 form of a str (for ASCII text it IS the object's own buffer): no 200 MB .encode() copy
+            size = C.c_ssize_t(0)
+            ptr = _utf8_and_size(payload, C.byref(size))
+            if not ptr:
+                raise ValueError("CSV payload is not valid UTF-8")
+            text, length = C.c_char_p(ptr), size.value
+        else:
+            text, length = C.c_char_p(bytes(payload) if not isinstance(payload, bytes) else payload), len(payload)
+        self._check(self.lib.XGB200DMatrixCreateFromCSV(text, C.c_ulong(length), C.c_char(delimiter.encode("ascii")), C.byref(st), C.byref(h)))
         return (h if st.value == 0 else None), int(st.value)
 
     def dmatrix_free(self, h):

@@ -11,6 +11,9 @@
 //
 // Kernels: (1) newline positions (flag + CUB select), (2) one thread per row walks its fields.  Text is read once from
 // HBM (L1-cached byte loads; rows are short and contiguous per thread).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cub/cub.cuh>
 #include <cstring>
 #include "booster.h"
@@ -117,8 +120,18 @@ static CsvScratch& csv_scratch() { static thread_local CsvScratch s; return s; }
 // returns 0 = ok, 1 = ragged rows, 2 = a field outside the exact fast path / malformed (caller falls back to the host parser)
 int parse_csv_device(const char* h_text, int64_t len, char delim, int F, int64_t* n_rows_out, DevBuf<float>* X, cudaStream_t s) {
   CsvScratch& sc = csv_scratch();
+  static const bool prof = getenv("B200XGB_CSV_PROFILE") != nullptr;          // stage times on stderr (microbench/csv_stages.py)
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    cudaStreamSynchronize(s);
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[csv] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   sc.text.ensure((size_t)len + 16); sc.cnt.ensure(2); sc.err.ensure(1);
   CUDA_OK(cudaMemcpyAsync(sc.text.p, h_text, (size_t)len, cudaMemcpyHostToDevice, s));
+  lap("h2d of the text");
   CUDA_OK(cudaMemsetAsync(sc.cnt.p, 0, 16, s));
   CUDA_OK(cudaMemsetAsync(sc.err.p, 0, 4, s));
   count_newlines_kernel<<<148 * 8, 256, 0, s>>>(sc.text.p, len, sc.cnt.p); ++g_kernel_launches;
@@ -126,6 +139,7 @@ int parse_csv_device(const char* h_text, int64_t len, char delim, int F, int64_t
   unsigned long long nnl = 0;
   CUDA_OK(cudaMemcpyAsync(&nnl, sc.cnt.p, sizeof(nnl), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
+  lap("count newlines");
   const int64_t n = (int64_t)nnl + 1;
   *n_rows_out = n;
   sc.nl.ensure((size_t)nnl + 1);
@@ -139,12 +153,15 @@ int parse_csv_device(const char* h_text, int64_t len, char delim, int F, int64_t
     CUDA_OK(cub::DeviceSelect::If(sc.tmp.p, tmp_bytes, idx, sc.nl.p, d_num, len, pred, s));
     ++g_kernel_launches;
   }
+  lap("newline positions");
   X->alloc((size_t)n * F);
+  lap("alloc X");
   csv_parse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(sc.text.p, len, sc.nl.p, n, F, delim, X->p, sc.err.p); ++g_kernel_launches;
   CUDA_OK(cudaGetLastError());
   int err = 0;
   CUDA_OK(cudaMemcpyAsync(&err, sc.err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
+  lap("parse kernel");
   return err;
 }
 
