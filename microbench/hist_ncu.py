@@ -21,7 +21,7 @@ gpair = np.empty((a.rows, 2), np.float32); gpair[:, 0] = rng.standard_normal(a.r
 for m in a.modes.split(","):
     if m == "s":
         sub = np.sort(rng.choice(a.rows, size=a.rows // 4, replace=False).astype(np.uint32))
-        r = be.build_histogram_ex(b.handle, d.handle, gpair[:len(sub)], mode=0, row_ids=sub, repeats=1)
+        r = be.build_histogram_ex(b.handle, d.handle, gpair[:len(sub)], mode=4, row_ids=sub, repeats=1)     # 4: tail words by position, like the training path
     else:
         r = be.build_histogram_ex(b.handle, d.handle, gpair, mode=int(m), repeats=1)
     print(m, r[3], r[2], flush=True)

@@ -1074,6 +1074,11 @@ void Booster::predict(DMatrix* dm, int type, bool training, int iter_begin, int 
   else shape->assign({(uint64_t)n, (uint64_t)out_cols});
 }
 
+__global__ void gather_u32_kernel(const unsigned* src, const unsigned* idx, unsigned* dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
 // Kernel-level entry point for parity tests and the roofline bench: build the histogram of all rows (or of the row
 // subset `row_ids`, gradient pairs by position) from host gradient pairs `repeats` times; returns the int64 histogram in
 // pool layout ([ngroups][256][32]{g,h} then the tail [256][tw]{g,h}) and the fixed-point scales.
@@ -1102,7 +1107,12 @@ void Booster::debug_build_root_hist(DMatrix* dm, const float* gpair_host, std::v
   ha.ridx = row_ids ? g.ridx0.p : nullptr;
   ha.build_count = g.gs.build_count; ha.build_nid = g.gs.build_nid; ha.build_prefix = g.gs.build_prefix; ha.seg_begin = g.gs.seg_begin;
   ha.hist_slot = g.gs.hist_slot; ha.scales = g.gs.scales; ha.hist_pool = g.hist_pool.p; ha.node_sum = g.gs.node_sum; ha.ngroups = bm.ngroups; ha.accumulate_sum = 1;
-  ha.force_gather = mode == 1 ? 1 : 0; ha.g_only = mode == 2 ? 1 : 0; ha.window_rows = job_window_rows(g.global_n);
+  ha.force_gather = (mode & 3) == 1 ? 1 : 0; ha.g_only = (mode & 3) == 2 ? 1 : 0; ha.window_rows = job_window_rows(g.global_n);
+  if ((mode & 4) && row_ids && bm.tw == 4) {      // the training path's variant: the rows' tail words by POSITION (as after a partition)
+    gather_u32_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(reinterpret_cast<const unsigned*>(bm.bins_tail), g.ridx0.p, g.tl0.p, rows); ++g_kernel_launches;
+    CUDA_OK(cudaGetLastError());
+    ha.tail_pos = g.tl0.p;
+  }
   g.root_h_valid = false;                       // the debug entry point overwrites gpair and the root slot
   cudaEvent_t e0, e1; CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
   float total = 0.f;

@@ -85,8 +85,9 @@ def test_root_histogram_bit_exact(xgb, oracle, n, F, mode):
         np.testing.assert_allclose(got, dref[optrs[f]:optrs[f + 1], 0], rtol=0, atol=2e-5 * max(1.0, np.abs(gpair[:, 0]).max()) * np.sqrt(n))
 
 
+@pytest.mark.parametrize("tail_by_position", [False, True])
 @pytest.mark.parametrize("n,F,frac,ordered", [(50000, 28, 0.3, True), (120000, 100, 0.25, True), (30000, 50, 0.5, False), (40000, 130, 0.1, True), (9000, 40, 1.0, False)])
-def test_gathered_histogram_bit_exact(xgb, oracle, n, F, frac, ordered):
+def test_gathered_histogram_bit_exact(xgb, oracle, n, F, frac, ordered, tail_by_position):
     """The deeper levels' access pattern: a row subset by row id (ascending like a partitioned node, or shuffled), gradient
     pairs by position."""
     X, gpair, d, b = _hist_inputs(xgb, n, F, seed=23)
@@ -96,7 +97,8 @@ def test_gathered_histogram_bit_exact(xgb, oracle, n, F, frac, ordered):
     if ordered:
         rows.sort()
     gp_pos = gpair[:m]
-    hist, scales, ms, kernel = _be().build_histogram_ex(b.handle, d.handle, gp_pos, mode=0, row_ids=rows)
+    # mode 4: the rows' 4 tail bytes are supplied by position, as after a partition (the training path); 0: gathered from bins_tail
+    hist, scales, ms, kernel = _be().build_histogram_ex(b.handle, d.handle, gp_pos, mode=4 if tail_by_position else 0, row_ids=rows)
     assert kernel == "hist_gather_kernel"
     gq = np.zeros(n, np.int32); hq = np.zeros(n, np.int32)
     gq[rows] = np.rint(gp_pos[:, 0] * scales[0]).astype(np.int32)
