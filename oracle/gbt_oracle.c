@@ -333,11 +333,30 @@ static inline void split_update(Split* best, float loss_chg, int f, float value,
   }
 }
 
+/* Monotone constraints.  [UPSTREAM src/tree/split_evaluator.h TreeEvaluator::SplitEvaluator: CalcWeight clamps to the node's
+ * [lower, upper]; CalcGainGivenWeight takes the general form -(2 G w + (H + lambda) w^2) whenever constraints exist;
+ * CalcSplitGain returns -inf when the child weights violate the feature's constraint; AddSplit hands mid = (wl + wr) / 2 down
+ * as the children's new bound on the constrained side] */
+typedef struct { const int32_t* c; float lo, hi; } Mono;      /* c == NULL: unconstrained */
+static inline float clamp_w(float w, float lo, float hi) { return w < lo ? lo : (w > hi ? hi : w); }
+static inline float gain_at_weight(const OrcParams* p, double G, double H, float w) {
+  if (H <= 0.0) return 0.0f;
+  const float g = (float)G, h = (float)H;
+  return -(2.0f * g * w + (h + p->lambda) * w * w);
+}
+static inline float split_loss_chg(const OrcParams* p, const Mono* mn, int f, double GL, double HL, double GR, double HR, float root_gain) {
+  if (!mn || !mn->c) return (float)(calc_split_gain(p, GL, HL, GR, HR) - root_gain);
+  const float wl = clamp_w(calc_weight(p, GL, HL), mn->lo, mn->hi), wr = clamp_w(calc_weight(p, GR, HR), mn->lo, mn->hi);
+  const int cf = mn->c[f];
+  if (cf != 0 && !(cf > 0 ? wl <= wr : wl >= wr)) return -INFINITY;
+  return gain_at_weight(p, GL, HL, wl) + gain_at_weight(p, GR, HR, wr) - root_gain;
+}
+
 /* hist: total_bins x 2 doubles (g,h) for one node. feat_mask: F bytes (1 = usable) or NULL.
  * [UPSTREAM src/tree/hist/evaluate_splits.h EnumerateSplit<+1/-1>, EvaluateSplits] */
-void orc_eval_split(const OrcParams* p, const double* hist, const int32_t* cut_ptrs, const float* cut_vals,
+static void eval_split_mono(const OrcParams* p, const double* hist, const int32_t* cut_ptrs, const float* cut_vals,
                     const float* min_vals, int32_t F, const uint8_t* feat_mask, double G, double H,
-                    float root_gain, Split* out) {
+                    float root_gain, const Mono* mn, Split* out) {
   Split best; memset(&best, 0, sizeof best); best.split_bin = -1;     /* SplitEntry{}: loss_chg 0, sindex 0 */
   for (int f = 0; f < F; ++f) {
     if (feat_mask && !feat_mask[f]) continue;
@@ -348,7 +367,7 @@ void orc_eval_split(const OrcParams* p, const double* hist, const int32_t* cut_p
       GL += hist[2 * i]; HL += hist[2 * i + 1];
       double GR = G - GL, HR = H - HL;
       if (HL >= p->min_child_weight && HR >= p->min_child_weight) {
-        float lc = (float)(calc_split_gain(p, GL, HL, GR, HR) - root_gain);
+        float lc = split_loss_chg(p, mn, f, GL, HL, GR, HR, root_gain);
         split_update(&fb, lc, f, cut_vals[i], i - ib, 0, GL, HL, GR, HR);
       }
     }
@@ -358,7 +377,7 @@ void orc_eval_split(const OrcParams* p, const double* hist, const int32_t* cut_p
         GRr += hist[2 * i]; HRr += hist[2 * i + 1];
         double GLl = G - GRr, HLl = H - HRr;
         if (HRr >= p->min_child_weight && HLl >= p->min_child_weight) {
-          float lc = (float)(calc_split_gain(p, GLl, HLl, GRr, HRr) - root_gain);
+          float lc = split_loss_chg(p, mn, f, GLl, HLl, GRr, HRr, root_gain);
           float sv = (i == ib) ? min_vals[f] : cut_vals[i - 1];
           split_update(&fb, lc, f, sv, i - ib - 1, 1, GLl, HLl, GRr, HRr);
         }
@@ -367,6 +386,12 @@ void orc_eval_split(const OrcParams* p, const double* hist, const int32_t* cut_p
     if (need_replace(best.loss_chg, best.findex, fb.loss_chg, fb.findex)) best = fb;
   }
   *out = best;
+}
+
+void orc_eval_split(const OrcParams* p, const double* hist, const int32_t* cut_ptrs, const float* cut_vals,
+                    const float* min_vals, int32_t F, const uint8_t* feat_mask, double G, double H,
+                    float root_gain, Split* out) {
+  eval_split_mono(p, hist, cut_ptrs, cut_vals, min_vals, F, feat_mask, G, H, root_gain, NULL, out);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -487,6 +512,7 @@ typedef struct {
   int32_t* row_leaf;          /* leaf node (tree-local id) per row of the tree being grown */
   OrcModel model;
   int32_t iter;               /* boosted rounds so far */
+  int32_t* monotone;          /* F entries (-1, 0, +1) or NULL */
   int32_t quant_bits;         /* 0 = reference behaviour; >0 = study knob: round gpair to a 2^-k grid like the
                                  product's fixed-point histogram (scale = power of two from max|g|, max h) */
 } OrcTrainer;
@@ -525,7 +551,7 @@ OrcTrainer* orc_trainer_create(const OrcParams* p, const uint8_t* bins, int64_t 
 
 void orc_trainer_free(OrcTrainer* t) {
   if (!t) return;
-  free(t->margins); free(t->gpair); free(t->ridx); free(t->ridx_tmp); free(t->row_leaf);
+  free(t->margins); free(t->gpair); free(t->ridx); free(t->ridx_tmp); free(t->row_leaf); free(t->monotone);
   OrcModel* m = &t->model;
   free(m->tree_offset); free(m->tree_info); free(m->left); free(m->right); free(m->parent);
   free(m->split_index); free(m->split_bin); free(m->default_left); free(m->split_cond);
@@ -535,6 +561,7 @@ void orc_trainer_free(OrcTrainer* t) {
 
 typedef struct {
   int nid, depth; Split split; double G, H; float root_gain, weight;
+  float lo, hi;            /* weight interval of the node under monotone constraints */
   int64_t begin, count;    /* row segment in ridx */
   double* hist;            /* owned */
 } Cand;
@@ -659,9 +686,11 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
     double G = 0, H = 0;
     if (!t->has_missing) { for (int i = t->cut_ptrs[0]; i < t->cut_ptrs[1]; ++i) { G += c.hist[2 * i]; H += c.hist[2 * i + 1]; } }
     else { for (int64_t r = 0; r < n; ++r) { G += gp[r * gs]; H += gp[r * gs + 1]; } }
-    c.G = G; c.H = H; c.root_gain = calc_gain(p, G, H); c.weight = calc_weight(p, G, H);
+    c.G = G; c.H = H; c.lo = -INFINITY; c.hi = INFINITY;
+    c.weight = calc_weight(p, G, H);
+    c.root_gain = t->monotone ? gain_at_weight(p, G, H, c.weight) : calc_gain(p, G, H);
     m->base_weight[base] = c.weight; m->sum_hess[base] = (float)H; m->split_cond[base] = p->eta * c.weight;
-    orc_eval_split(p, c.hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(0, 0), G, H, c.root_gain, &c.split);
+    { Mono mn = { t->monotone, c.lo, c.hi }; eval_split_mono(p, c.hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(0, 0), G, H, c.root_gain, &mn, &c.split); }
     cur[0] = c; ncur = 1;
   }
   int num_leaves = 1;
@@ -696,6 +725,12 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
       int L = new_node(m, base, c->nid), R = new_node(m, base, c->nid);
       gi = base + c->nid;
       float wl = calc_weight(p, c->split.GL, c->split.HL), wr = calc_weight(p, c->split.GR, c->split.HR);
+      float llo = c->lo, lhi = c->hi, rlo = c->lo, rhi = c->hi;
+      if (t->monotone) {            /* children weights clamped by the PARENT's interval; AddSplit */
+        wl = clamp_w(wl, c->lo, c->hi); wr = clamp_w(wr, c->lo, c->hi);
+        const float mid = (wl + wr) / 2.0f; const int cf = t->monotone[c->split.findex];
+        if (cf < 0) { llo = mid; rhi = mid; } else if (cf > 0) { lhi = mid; rlo = mid; }
+      }
       m->left[gi] = L; m->right[gi] = R; m->split_index[gi] = c->split.findex; m->split_cond[gi] = c->split.split_value;
       m->split_bin[gi] = c->split.split_bin; m->default_left[gi] = (uint8_t)c->split.default_left;
       m->base_weight[gi] = c->weight; m->loss_chg[gi] = c->split.loss_chg; m->sum_hess[gi] = (float)c->H;
@@ -714,6 +749,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
       cl.nid = L; cr.nid = R; cl.depth = cr.depth = c->depth + 1;
       cl.begin = c->begin; cl.count = nl; cr.begin = c->begin + nl; cr.count = nr;
       cl.G = c->split.GL; cl.H = c->split.HL; cr.G = c->split.GR; cr.H = c->split.HR;
+      cl.lo = llo; cl.hi = lhi; cr.lo = rlo; cr.hi = rhi;
       if (child_ok) {
         int fewer_right = c->split.HR < c->split.HL;
         Cand* bld = fewer_right ? &cr : &cl; Cand* sub = fewer_right ? &cl : &cr;
@@ -724,8 +760,9 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
         Cand* two[2] = { &cl, &cr };
         for (int s = 0; s < 2; ++s) {
           Cand* ch = two[s];
-          ch->root_gain = calc_gain(p, ch->G, ch->H); ch->weight = calc_weight(p, ch->G, ch->H);
-          orc_eval_split(p, ch->hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(ch->depth, ch->nid), ch->G, ch->H, ch->root_gain, &ch->split);
+          ch->weight = t->monotone ? clamp_w(calc_weight(p, ch->G, ch->H), ch->lo, ch->hi) : calc_weight(p, ch->G, ch->H);
+          ch->root_gain = t->monotone ? gain_at_weight(p, ch->G, ch->H, ch->weight) : calc_gain(p, ch->G, ch->H);
+          { Mono mn = { t->monotone, ch->lo, ch->hi }; eval_split_mono(p, ch->hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(ch->depth, ch->nid), ch->G, ch->H, ch->root_gain, &mn, &ch->split); }
           if (ch->split.loss_chg > K_RT_EPS) next[nnext++] = *ch; else { free(ch->hist); ch->hist = NULL; }
         }
       }
@@ -781,6 +818,13 @@ int orc_update_one_iter(OrcTrainer* t) {
 
 /* accessors for the Python wrapper */
 void orc_set_quant_bits(OrcTrainer* t, int32_t bits) { t->quant_bits = bits; }
+void orc_set_monotone(OrcTrainer* t, const int32_t* c, int32_t ncon) {
+  free(t->monotone); t->monotone = NULL;
+  int any = 0; for (int i = 0; i < ncon; ++i) any |= c[i] != 0;
+  if (!any) return;
+  t->monotone = (int32_t*)calloc((size_t)t->F, sizeof(int32_t));
+  for (int i = 0; i < ncon && i < t->F; ++i) t->monotone[i] = c[i];
+}
 void orc_set_margins(OrcTrainer* t, const float* m) { const int K = t->p.num_class > 1 ? t->p.num_class : 1; memcpy(t->margins, m, sizeof(float) * (size_t)(t->n * K)); }
 int32_t orc_num_trees(const OrcTrainer* t) { return t->model.n_trees; }
 int64_t orc_num_nodes(const OrcTrainer* t) { return t->model.n_nodes; }

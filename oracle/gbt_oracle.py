@@ -81,6 +81,7 @@ def lib():
         L.orc_predict.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9
         L.orc_num_threads.restype = C.c_int
         L.orc_set_quant_bits.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_set_monotone.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_set_margins.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -227,6 +228,12 @@ class Trainer:
         self.h = lib().orc_trainer_create(C.byref(self.p), _p(self.bins), self.n, self.F, _p(self.cut_ptrs),
                                           _p(self.cut_vals), _p(self.min_vals), _p(self.y), _p(self.w),
                                           int(self.has_missing), float(base_score or 0.0), int(base_score is not None))
+        mc = params.get("monotone_constraints")
+        if mc is not None:
+            if isinstance(mc, str):
+                mc = [int(t) for t in mc.strip("()[] ").split(",") if t.strip()]
+            self._mono = np.ascontiguousarray(list(mc), np.int32)
+            lib().orc_set_monotone(self.h, _p(self._mono), len(self._mono))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -230,7 +230,7 @@ _IGNORED_PARAMS = {
     "deterministic_histogram", "single_precision_histogram", "updater", "refresh_leaf", "process_type", "device", "gpu_id",
     "sampling_method", "validate_parameters", "max_cat_to_onehot", "max_cat_threshold", "num_parallel_tree",
     "rate_drop", "one_drop", "skip_drop", "sample_type", "normalize_type", "lambda_bias", "feature_selector", "top_k",
-    "monotone_constraints", "interaction_constraints", "aft_loss_distribution", "aft_loss_distribution_scale", "disable_default_eval_metric",
+    "interaction_constraints", "aft_loss_distribution", "aft_loss_distribution_scale", "disable_default_eval_metric",
     "multi_strategy", "max_cached_hist_node", "random_state",
 }
 
@@ -248,7 +248,13 @@ def _as_float(v, default):
 def _check_unapplied(k, v):
     """No silent hyperparameter divergence: every value the container validates as legal but this builder
     does not honour is either rejected or announced with a warning; returns the value to forward, or _DROP."""
-    if k in ("monotone_constraints", "interaction_constraints"):
+    if k == "monotone_constraints":           # applied (tree.cu constrained_split_gain); forwarded as "(1,0,-1)"
+        if isinstance(v, dict):
+            raise XGBoostError("monotone_constraints as a feature-name dict is not supported by the B200 hist builder; pass one entry per feature")
+        if isinstance(v, (list, tuple)):
+            return "(" + ",".join(str(int(x)) for x in v) + ")"
+        return str(v)
+    if k == "interaction_constraints":
         if str(v).strip("()[] ,0") != "":
             warnings.warn("%s is accepted for hyperparameter compatibility but NOT applied by the B200 hist builder" % k)
         return _DROP

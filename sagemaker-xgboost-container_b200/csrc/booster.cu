@@ -279,7 +279,7 @@ struct PinnedPool {
   void reset() { cur = 0; off = 0; }
 };
 
-struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts; int max_depth, max_leaves, lg_iters; float eta, lambda, alpha, gamma, mcw, mds, bynode; unsigned seed; int world, root_mode; int64_t n; };
+struct TreeGraphKey { uint64_t uid, binned_version; const void *margin, *mask, *packed, *bins, *bins_col, *cuts, *mono; int max_depth, max_leaves, lg_iters; float eta, lambda, alpha, gamma, mcw, mds, bynode; unsigned seed; int world, root_mode; int64_t n; };
 // The per-tree launch sequence as CUDA graphs.  On one GPU it is a single graph; with NCCL it is cut into SEGMENTS at every
 // collective (root + one per level): the segments are replayed as graphs and the all-reduces are issued between them as
 // ordinary stream operations, so no NCCL call is ever captured (a capture with lazily connecting NCCL channels hung an
@@ -303,7 +303,8 @@ struct GrowerImpl {
   DevBuf<unsigned char> tree_block;        // header + TreeArrays, copied to the host in one piece
   size_t tree_block_bytes = 0;
   DevBuf<GH64> hist_pool; DevBuf<unsigned> ridx0, ridx1, scratch;
-  DevBuf<float2> gpair, gp0, gp1; DevBuf<unsigned> tl0, tl1; DevBuf<int> err, tree_index_dev; DevBuf<unsigned char> feat_mask;
+  DevBuf<float2> gpair, gp0, gp1; DevBuf<unsigned> tl0, tl1; DevBuf<int> err, tree_index_dev, monotone_dev; DevBuf<unsigned char> feat_mask;
+  std::vector<int> monotone_host;          // what monotone_dev holds (re-uploaded when the constraints or the feature count change)
   DevBuf<double> dsum;
   PinnedPool pinned; std::vector<cudaEvent_t> free_events;
   DevBuf<DevNode> packed; std::vector<TreeGraph> graphs; std::vector<char> eager_done;
@@ -350,7 +351,7 @@ struct GrowerImpl {
     size_t o_bnid = take(4 * L), o_bsub = take(4 * L), o_bps = take(4 * L), o_bcount = take(4), o_bprefix = take(4 * (L + 1));
     size_t o_action = take(4 * L), o_tprefix = take(4 * (L + 1)), o_tleft = take(4 * (size_t)max_tiles), o_toff = take(4 * (size_t)max_tiles);
     size_t o_flags = take((size_t)n + 16), o_nleaves = take(4), o_scales = take(16), o_absmax = take(8);
-    size_t o_depth = take(4 * N), o_open = take(N), o_nslots = take(4), o_lgdone = take(4);
+    size_t o_depth = take(4 * N), o_open = take(N), o_nslots = take(4), o_lgdone = take(4), o_lower = take(4 * N), o_upper = take(4 * N);
     state_block.alloc(off); state_block.zero(engine_stream());
     unsigned char* b = state_block.p;
     gs.seg_begin = (unsigned*)(b + o_seg_begin); gs.seg_count = (unsigned*)(b + o_seg_count); gs.hist_slot = (int*)(b + o_slot);
@@ -360,6 +361,7 @@ struct GrowerImpl {
     gs.build_nid = (int*)(b + o_bnid); gs.build_sub_nid = (int*)(b + o_bsub); gs.build_parent_slot = (int*)(b + o_bps);
     gs.build_count = (int*)(b + o_bcount); gs.build_prefix = (unsigned*)(b + o_bprefix);
     gs.part_action = (int*)(b + o_action); gs.tile_prefix = (unsigned*)(b + o_tprefix); gs.tile_left = (unsigned*)(b + o_tleft); gs.tile_off = (unsigned*)(b + o_toff);
+    gs.lower = (float*)(b + o_lower); gs.upper = (float*)(b + o_upper);
     gs.depth = (int*)(b + o_depth); gs.open = b + o_open; gs.n_slots = (int*)(b + o_nslots); gs.lg_done = (int*)(b + o_lgdone);
     gs.flags = b + o_flags; gs.n_leaves = (int*)(b + o_nleaves); gs.scales = (float*)(b + o_scales); gs.absmax = (unsigned*)(b + o_absmax);
     // ---- tree block: [n_nodes + pad to 64][5 int arrays][4 float arrays][u8 array]
@@ -507,6 +509,17 @@ void Booster::configure() {
   if (gp != raw_params_.end()) {
     B200_CHECK(gp->second == "depthwise" || gp->second == "lossguide", "Invalid grow_policy: " + gp->second + " (depthwise, lossguide)");
     p.lossguide = gp->second == "lossguide" ? 1 : 0;
+  }
+  monotone_.clear();
+  auto mc = raw_params_.find("monotone_constraints");
+  if (mc != raw_params_.end()) {                 // "(1,0,-1)" / "1,0,-1" / "[1, 0, -1]": one entry per feature, missing ones are 0
+    std::string tok;
+    auto flush = [&]() { if (tok.empty()) return; int v = 0; try { v = std::stoi(tok); } catch (...) { throw Error("Invalid monotone_constraints entry: " + tok); }
+      B200_CHECK(v >= -1 && v <= 1, "monotone_constraints entries must be -1, 0 or 1"); monotone_.push_back(v); tok.clear(); };
+    for (char ch : mc->second) { if (ch == '-' || ch == '+' || (ch >= '0' && ch <= '9')) tok.push_back(ch); else flush(); }
+    flush();
+    bool any = false; for (int v : monotone_) any |= v != 0;
+    if (!any) monotone_.clear();
   }
   if (p.lossguide) {
     B200_CHECK(p.max_depth >= 0 && p.max_depth <= kMaxDepth, "max_depth must be in [0, 16]");
@@ -759,15 +772,20 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
   };
   allreduce_hist(g.hist_pool.p, g.slot_stride * 2);
   allreduce_hist(g.gs.node_sum, 2);
+  const int* mono_dev = nullptr;
+  if (!monotone_.empty()) {                       // uploaded outside the captured sequence by grow_one_tree
+    B200_CHECK((int)monotone_.size() <= bm.F, "monotone_constraints has more entries than the data has features");
+    mono_dev = g.monotone_dev.p;
+  }
   EvalArgs ea{}; ea.hist_pool = g.hist_pool.p; ea.gs = g.gs; ea.cut_ptrs = dtrain->d_cut_ptrs.p; ea.feat_mask = mask; ea.p = pd; ea.F = bm.F;
   ea.ngroups = bm.ngroups; ea.tw = bm.tw; ea.ntail = bm.ntail; ea.has_missing = bm.has_missing; ea.level = 0; ea.max_level_nodes = g.max_level_nodes;
-  ea.colsample_bynode = mask ? param_.colsample_bynode : 1.0f; ea.seed = param_.seed; ea.tree_index = g.tree_index_dev.p;
+  ea.colsample_bynode = mask ? param_.colsample_bynode : 1.0f; ea.seed = param_.seed; ea.tree_index = g.tree_index_dev.p; ea.monotone = mono_dev;
   launch_eval(ea, 1, s);
 
   const int lg_iters = lossguide_iters(param_);
   for (int it = 0; it < lg_iters; ++it) {                 // grow_policy=lossguide: one expansion per iteration (tree.cu apply_lossguide_kernel)
     ApplyArgs aa{}; aa.gs = g.gs; aa.tree = g.ta; aa.cut_ptrs = dtrain->d_cut_ptrs.p; aa.cut_vals = dtrain->d_cut_vals.p; aa.min_vals = dtrain->d_min_vals.p;
-    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups + (bm.tw > 0 ? 1 : 0); aa.level = 0; aa.max_level_nodes = g.max_level_nodes;
+    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups + (bm.tw > 0 ? 1 : 0); aa.level = 0; aa.max_level_nodes = g.max_level_nodes; aa.monotone = mono_dev;
     launch_apply_lossguide(aa, it, s);
     // live row segments always sit in buffer set 0; the partition writes the children into set 1 and they are copied straight back
     const bool carry_tail = bm.tw == 4;
@@ -798,7 +816,7 @@ void Booster::enqueue_tree(DMatrix* dtrain, float* margin, int k, const unsigned
     const bool final_level = (L == D - 1);
     const int next_base = ((L + 1) & 1) * g.region, next_half = 1 << L;
     ApplyArgs aa{}; aa.gs = g.gs; aa.tree = g.ta; aa.cut_ptrs = dtrain->d_cut_ptrs.p; aa.cut_vals = dtrain->d_cut_vals.p; aa.min_vals = dtrain->d_min_vals.p;
-    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups + (bm.tw > 0 ? 1 : 0); aa.level = L; aa.max_level_nodes = g.max_level_nodes; aa.next_base = next_base; aa.next_half = next_half;
+    aa.p = pd; aa.scratch = g.scratch.p; aa.ngroups = bm.ngroups + (bm.tw > 0 ? 1 : 0); aa.level = L; aa.max_level_nodes = g.max_level_nodes; aa.next_base = next_base; aa.next_half = next_half; aa.monotone = mono_dev;
     launch_apply(aa, s);
     if (final_level) break;                  // children of the last level are leaves: no partition, no histograms
     PartArgs pa{}; pa.gs = g.gs; pa.tree = g.ta; pa.bins_col = bm.bins_col; pa.n = bm.n;
@@ -849,6 +867,15 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     Comm::get().sync_stream(s);
     mask = g.feat_mask.p;
   }
+  if (!monotone_.empty()) {                     // per-feature constraints in device memory (padded with 0 to the feature count)
+    std::vector<int> mh(monotone_); mh.resize((size_t)std::max<int>(dtrain->F, (int)mh.size()), 0);
+    if (mh != g.monotone_host || g.monotone_dev.n < mh.size()) {
+      g.monotone_dev.ensure(mh.size());
+      CUDA_OK(cudaMemcpyAsync(g.monotone_dev.p, mh.data(), sizeof(int) * mh.size(), cudaMemcpyHostToDevice, s));
+      Comm::get().sync_stream(s);
+      g.monotone_host = mh;
+    }
+  }
   g.packed.ensure((size_t)g.cap_nodes);
   static const bool no_graph = getenv("B200XGB_NO_GRAPH") != nullptr;
   static const bool no_graph_multi = getenv("B200XGB_NO_GRAPH_MULTI") != nullptr;      // multi-rank: issue every launch directly
@@ -878,7 +905,7 @@ void Booster::grow_one_tree(DMatrix* dtrain, PredCache& cache, int k, int tree_i
     key.bins = dtrain->bins.p; key.bins_col = dtrain->bins_col.p; key.cuts = dtrain->d_cut_vals.p;     // re-binning invalidates the capture
     key.max_leaves = param_.max_leaves; key.lg_iters = lossguide_iters(param_); key.eta = param_.eta; key.lambda = param_.lambda; key.alpha = param_.alpha; key.gamma = param_.gamma;
     key.mcw = param_.min_child_weight; key.mds = param_.max_delta_step; key.world = Comm::get().world(); key.n = dtrain->n;
-    key.bynode = param_.colsample_bynode; key.seed = param_.seed;
+    key.bynode = param_.colsample_bynode; key.seed = param_.seed; key.mono = monotone_.empty() ? nullptr : g.monotone_dev.p;
     if (tg.segs.empty() || memcmp(&tg.key, &key, sizeof key) != 0) {
       tg.destroy();
       const long long launches_before = g_kernel_launches;

@@ -117,6 +117,7 @@ class Booster {
   friend struct GrowerImpl;
   std::map<std::string, std::string> raw_params_;
   std::vector<std::string> eval_metrics_;
+  std::vector<int> monotone_;              // parsed monotone_constraints (empty = none)
   bool configured_ = false;
   TrainParam param_;
   std::string objective_name_ = "reg:squarederror";

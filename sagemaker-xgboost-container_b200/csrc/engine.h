@@ -143,6 +143,8 @@ struct GrowState {
   int* n_nodes; int* n_leaves;
   // grow_policy=lossguide: depth and open-candidate flag per node, next free histogram slot, sticky end-of-tree flag
   int* depth; unsigned char* open; int* n_slots; int* lg_done;
+  // monotone constraints: weight bounds per node (upstream TreeEvaluator lower_bounds_ / upper_bounds_)
+  float* lower; float* upper;
   float* scales;                                // [0]=sg [1]=sh [2]=1/sg [3]=1/sh
   unsigned* absmax;                             // [0]=max|g| bits [1]=max h bits
 };

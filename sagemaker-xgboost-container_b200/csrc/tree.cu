@@ -35,6 +35,23 @@ __device__ __forceinline__ float calc_split_gain(const TrainParamDev& p, double 
   return calc_gain_given_weight(p, GL, HL, wl) + calc_gain_given_weight(p, GR, HR, wr);
 }
 
+// Monotone constraints (upstream src/tree/split_evaluator.h TreeEvaluator): weights are clamped to the node's [lower, upper]
+// interval, the gain is evaluated AT the clamped weights (always the general form, never the t^2 / (H + lambda) shortcut), a
+// candidate whose child weights violate the feature's constraint is rejected, and a split hands mid = (wl + wr) / 2 down to the
+// children as the new bound on the constrained side.
+__device__ __forceinline__ float clamp_weight(float w, float lo, float hi) { return w < lo ? lo : (w > hi ? hi : w); }
+__device__ __forceinline__ float gain_at_weight(const TrainParamDev& p, double G, double H, float w) {
+  if (H <= 0.0) return 0.0f;
+  const float g = (float)G, h = (float)H;
+  return -(2.0f * g * w + (h + p.lambda) * w * w);
+}
+// gain of a candidate under constraints; returns false when it violates the feature's constraint c
+__device__ __forceinline__ bool constrained_split_gain(const TrainParamDev& p, double GL, double HL, double GR, double HR, float lo, float hi, int c, float* gain) {
+  const float wl = clamp_weight(calc_weight(p, GL, HL), lo, hi), wr = clamp_weight(calc_weight(p, GR, HR), lo, hi);
+  *gain = gain_at_weight(p, GL, HL, wl) + gain_at_weight(p, GR, HR, wr);
+  return c == 0 || (c > 0 ? wl <= wr : wl >= wr);
+}
+
 // counter-based RNG shared with the host and the oracle (splitmix64 on (seed, stream, index)); booster.cu subset_mask
 __device__ __forceinline__ unsigned long long splitmix64_tree(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -58,6 +75,7 @@ __global__ void init_tree_kernel(GrowState gs, TreeArrays t, unsigned n, int roo
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   *gs.n_nodes = 1; *gs.n_leaves = 1;
   *gs.n_slots = kLgFirstFreeSlot; *gs.lg_done = 0; gs.depth[0] = 0; gs.open[0] = 0;
+  gs.lower[0] = -INFINITY; gs.upper[0] = INFINITY;
   for (int d = 0; d < kMaxDepth + 2; ++d) gs.level_count[d] = 0;
   gs.level_count[0] = 1; gs.level_nodes[0] = 0;
   gs.seg_begin[0] = 0; gs.seg_count[0] = n; gs.hist_slot[0] = root_slot;
@@ -122,8 +140,12 @@ __global__ void __launch_bounds__(32 * kEvalSegs) eval_kernel(EvalArgs a) {
   const double isg = (double)a.gs.scales[2], ish = (double)a.gs.scales[3];
   const GH64 tot = a.gs.node_sum[nid];
   const double G = (double)tot.g * isg, H = (double)tot.h * ish;
-  const float root_gain = calc_gain(a.p, G, H);
-  if (threadIdx.x == 0 && group == 0) { a.gs.root_gain[nid] = root_gain; a.gs.weight[nid] = calc_weight(a.p, G, H); }
+  const bool mono = a.monotone != nullptr;
+  const float w_lo = mono ? a.gs.lower[nid] : 0.f, w_hi = mono ? a.gs.upper[nid] : 0.f;
+  const int mono_c = (mono && active) ? a.monotone[f] : 0;
+  const float node_w = mono ? clamp_weight(calc_weight(a.p, G, H), w_lo, w_hi) : calc_weight(a.p, G, H);
+  const float root_gain = mono ? gain_at_weight(a.p, G, H, node_w) : calc_gain(a.p, G, H);
+  if (threadIdx.x == 0 && group == 0) { a.gs.root_gain[nid] = root_gain; a.gs.weight[nid] = node_w; }
 
   __shared__ long long segG[kEvalSegs][32], segH[kEvalSegs][32];
   __shared__ unsigned long long wkey[kEvalSegs];
@@ -151,7 +173,9 @@ __global__ void __launch_bounds__(32 * kEvalSegs) eval_kernel(EvalArgs a) {
       double GL = (double)cG * isg, HL = (double)cH * ish;
       double GR = (double)(tot.g - cG) * isg, HR = (double)(tot.h - cH) * ish;
       if (HL >= mcw && HR >= mcw) {
-        float lc = calc_split_gain(a.p, GL, HL, GR, HR) - root_gain;
+        float lc;
+        if (mono) { float gsum; lc = constrained_split_gain(a.p, GL, HL, GR, HR, w_lo, w_hi, mono_c, &gsum) ? gsum - root_gain : 0.0f; }
+        else lc = calc_split_gain(a.p, GL, HL, GR, HR) - root_gain;
         unsigned long long k = cand_key(lc, f, b);
         if (k > bkey) { bkey = k; best.loss_chg = lc; best.feature = f; best.bin = b; best.dleft = 0; best.ord = b; best.GL = cG; best.HL = cH; }
       }
@@ -166,7 +190,9 @@ __global__ void __launch_bounds__(32 * kEvalSegs) eval_kernel(EvalArgs a) {
         long long lG = tot.g - rG, lH = tot.h - rH;       // left = everything else incl. missing
         double GL = (double)lG * isg, HL = (double)lH * ish, GR = (double)rG * isg, HR = (double)rH * ish;
         if (HR >= mcw && HL >= mcw) {
-          float lc = calc_split_gain(a.p, GL, HL, GR, HR) - root_gain;
+          float lc;
+          if (mono) { float gsum; lc = constrained_split_gain(a.p, GL, HL, GR, HR, w_lo, w_hi, mono_c, &gsum) ? gsum - root_gain : 0.0f; }
+          else lc = calc_split_gain(a.p, GL, HL, GR, HR) - root_gain;
           int ord = 256 + (255 - b);
           unsigned long long k = cand_key(lc, f, ord);
           if (k > bkey) { bkey = k; best.loss_chg = lc; best.feature = f; best.bin = b - 1; best.dleft = 1; best.ord = ord; best.GL = lG; best.HL = lH; }
@@ -271,7 +297,14 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
     const int Lc = n0 + 2 * r, Rc = Lc + 1;
     const long long GLq = best.GL, HLq = best.HL, GRq = tot.g - best.GL, HRq = tot.h - best.HL;
     const double GL = (double)GLq * isg, HL = (double)HLq * ish, GR = (double)GRq * isg, HR = (double)HRq * ish;
-    const float wl = calc_weight(a.p, GL, HL), wr = calc_weight(a.p, GR, HR);
+    float wl = calc_weight(a.p, GL, HL), wr = calc_weight(a.p, GR, HR);
+    if (a.monotone) {            // TreeEvaluator::AddSplit: children inherit the interval, mid bounds the constrained side
+      const float lo = gs.lower[nid], hi = gs.upper[nid];
+      wl = clamp_weight(wl, lo, hi); wr = clamp_weight(wr, lo, hi);
+      const float mid = (wl + wr) / 2.0f; const int mc = a.monotone[best.feature];
+      gs.lower[Lc] = lo; gs.upper[Lc] = hi; gs.lower[Rc] = lo; gs.upper[Rc] = hi;
+      if (mc < 0) { gs.lower[Lc] = mid; gs.upper[Rc] = mid; } else if (mc > 0) { gs.upper[Lc] = mid; gs.lower[Rc] = mid; }
+    }
     const int cb = a.cut_ptrs[best.feature];
     float thr = best.dleft ? (best.bin < 0 ? a.min_vals[best.feature] : a.cut_vals[cb + best.bin]) : a.cut_vals[cb + best.bin];
     t.left[nid] = Lc; t.right[nid] = Rc; t.split_index[nid] = best.feature; t.split_cond[nid] = thr;
@@ -366,7 +399,14 @@ __global__ void __launch_bounds__(256) apply_lossguide_kernel(ApplyArgs a, int i
   const int Lc = n0, Rc = n0 + 1, d = gs.depth[nid];
   const long long GLq = best.GL, HLq = best.HL, GRq = tot.g - best.GL, HRq = tot.h - best.HL;
   const double GL = (double)GLq * isg, HL = (double)HLq * ish, GR = (double)GRq * isg, HR = (double)HRq * ish;
-  const float wl = calc_weight(a.p, GL, HL), wr = calc_weight(a.p, GR, HR);
+  float wl = calc_weight(a.p, GL, HL), wr = calc_weight(a.p, GR, HR);
+  if (a.monotone) {
+    const float lo = gs.lower[nid], hi = gs.upper[nid];
+    wl = clamp_weight(wl, lo, hi); wr = clamp_weight(wr, lo, hi);
+    const float mid = (wl + wr) / 2.0f; const int mc = a.monotone[best.feature];
+    gs.lower[Lc] = lo; gs.upper[Lc] = hi; gs.lower[Rc] = lo; gs.upper[Rc] = hi;
+    if (mc < 0) { gs.lower[Lc] = mid; gs.upper[Rc] = mid; } else if (mc > 0) { gs.upper[Lc] = mid; gs.lower[Rc] = mid; }
+  }
   const int cb = a.cut_ptrs[best.feature];
   const float thr = best.dleft ? (best.bin < 0 ? a.min_vals[best.feature] : a.cut_vals[cb + best.bin]) : a.cut_vals[cb + best.bin];
   t.left[nid] = Lc; t.right[nid] = Rc; t.split_index[nid] = best.feature; t.split_cond[nid] = thr;

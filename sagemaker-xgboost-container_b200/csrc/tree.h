@@ -14,12 +14,14 @@ struct TrainParamDev {
 struct EvalArgs {
   const GH64* hist_pool; GrowState gs; const int* cut_ptrs; const unsigned char* feat_mask;
   TrainParamDev p; int F, ngroups, tw, ntail, has_missing, level, max_level_nodes;
+  const int* monotone;            // per-feature monotone constraint (-1, 0, +1), nullptr = none
   float colsample_bynode; unsigned seed; const int* tree_index;     // per-node feature subset inside feat_mask (the level's set); tree index in device memory (graph replay)
 };
 
 struct ApplyArgs {
   GrowState gs; TreeArrays tree; const int* cut_ptrs; const float* cut_vals; const float* min_vals;
   TrainParamDev p; unsigned* scratch; int ngroups /* candidate blocks per node: groups + tail */, level, max_level_nodes, next_base, next_half;
+  const int* monotone;            // as in EvalArgs
 };
 
 struct PartArgs {

@@ -467,6 +467,37 @@ def test_lossguide_growth_matches_oracle(xgb, oracle, hp, objective, kind, n, F)
         assert leaf_depths.max() > leaf_depths.min()
 
 
+@pytest.mark.parametrize("extra", [dict(max_depth=5), dict(max_depth=4, alpha=0.3, max_delta_step=0.5), dict(grow_policy="lossguide", max_leaves=20, max_depth=0)])
+def test_monotone_constraints_match_oracle_and_hold(xgb, oracle, extra):
+    """monotone_constraints (hyperparameter_validation.py passes the tuple through): clamped weights, gain at the clamped weights,
+    rejected violating candidates, bounds handed to the children -- same trees as the oracle's restatement of upstream's
+    TreeEvaluator, and the fitted function really is monotone in the constrained features."""
+    n, F, rounds = 20000, 6, 8
+    rng = np.random.default_rng(12)
+    X, _ = synth(n, F, 12, "reg")
+    y = (np.sin(2 * X[:, 0]) + 0.5 * X[:, 1] - X[:, 2] ** 2 + 0.2 * rng.standard_normal(n)).astype(np.float32)
+    cons = (1, -1, 0, 0, 0, 0)
+    params = dict(dict(objective="reg:squarederror", eta=0.3, monotone_constraints=cons), **extra)
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=rounds, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, rounds).model()
+    assert first_structural_difference(m, mr) is None
+    assert_same_structure(m, mr)
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    for f, sign in ((0, 1), (1, -1)):
+        for trial in range(20):
+            grid = np.tile(X[rng.integers(n)], (128, 1)).astype(np.float32)
+            grid[:, f] = np.linspace(-3.5, 3.5, 128, dtype=np.float32)
+            p = bst.predict(xgb.DMatrix(grid), output_margin=True)
+            assert np.all(sign * np.diff(p) >= -1e-6), "feature %d is not monotone" % f
+    assert "monotone_constraints" in bst.save_config()
+    # the unconstrained fit is NOT monotone in feature 0 (sin): the constraint did something
+    free = xgb.train(dict(objective="reg:squarederror", eta=0.3, max_depth=5), d, num_boost_round=rounds, verbose_eval=False)
+    grid = np.tile(np.median(X, 0), (128, 1)).astype(np.float32); grid[:, 0] = np.linspace(-3.5, 3.5, 128, dtype=np.float32)
+    assert np.any(np.diff(free.predict(xgb.DMatrix(grid), output_margin=True)) < -1e-3)
+
+
 @pytest.mark.parametrize("weighted", [False, True])
 def test_auc_matches_sklearn(xgb, weighted):
     """Native `auc` (the one HPO metric the container does not compute itself, train_utils.py:45-76) against

@@ -100,3 +100,20 @@ def test_lossguide_bounded_only_by_depth_grows_the_depthwise_tree():
         # best-first: a node is expanded before any node with a smaller gain that was open at the same time; in particular
         # the root comes first and the children ids are consecutive pairs
         assert internal[order][0] == 0 and np.all(np.diff(np.sort(left[internal])) == 2)
+
+
+def test_oracle_monotone_constraints_give_monotone_models():
+    n = 6000
+    rng = np.random.default_rng(3)
+    X, _ = synth(n, 5, 14, "reg")
+    y = (np.sin(2 * X[:, 0]) + 0.5 * X[:, 1] - X[:, 2] ** 2 + 0.2 * rng.standard_normal(n)).astype(np.float32)
+    m = O.train(dict(objective="reg:squarederror", max_depth=5, monotone_constraints=(1, -1, 0, 0, 0)), X, y, 10).model()
+    for f, sign in ((0, 1), (1, -1)):
+        for trial in range(20):
+            grid = np.tile(X[rng.integers(n)], (100, 1)).astype(np.float32)
+            grid[:, f] = np.linspace(-3.5, 3.5, 100, dtype=np.float32)
+            assert np.all(sign * np.diff(O.predict_margin(m, grid).ravel()) >= -1e-6)
+    # all-zero constraints are the unconstrained model
+    a = O.train(dict(objective="reg:squarederror", max_depth=4), X, y, 3).model()
+    b = O.train(dict(objective="reg:squarederror", max_depth=4, monotone_constraints="(0,0,0,0,0)"), X, y, 3).model()
+    np.testing.assert_array_equal(a["split_cond"], b["split_cond"])
