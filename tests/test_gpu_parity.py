@@ -139,6 +139,7 @@ CASES = [
     ("binary:logistic", "bin", 1, dict(max_depth=4, eta=0.1, alpha=0.5, scale_pos_weight=2.0), 10000, 40, 10),
     ("multi:softprob", "multi", 4, dict(max_depth=4, eta=0.3), 12000, 20, 5),
     ("reg:squarederror", "reg", 1, dict(max_depth=3, eta=0.5, max_delta_step=0.7), 5000, 100, 6),
+    ("binary:logistic", "bin", 1, dict(max_depth=5, eta=0.3), 40000, 100, 6),      # 3 groups + tail with G and H: 192 KB of planes, the root pass runs in the gather kernel
 ]
 
 
