@@ -513,6 +513,7 @@ typedef struct {
   OrcModel model;
   int32_t iter;               /* boosted rounds so far */
   int32_t* monotone;          /* F entries (-1, 0, +1) or NULL */
+  uint8_t* ic_sets; int32_t n_ic_sets;    /* interaction constraints: membership matrix [n_ic_sets][F], or NULL */
   int32_t quant_bits;         /* 0 = reference behaviour; >0 = study knob: round gpair to a 2^-k grid like the
                                  product's fixed-point histogram (scale = power of two from max|g|, max h) */
 } OrcTrainer;
@@ -551,7 +552,7 @@ OrcTrainer* orc_trainer_create(const OrcParams* p, const uint8_t* bins, int64_t 
 
 void orc_trainer_free(OrcTrainer* t) {
   if (!t) return;
-  free(t->margins); free(t->gpair); free(t->ridx); free(t->ridx_tmp); free(t->row_leaf); free(t->monotone);
+  free(t->margins); free(t->gpair); free(t->ridx); free(t->ridx_tmp); free(t->row_leaf); free(t->monotone); free(t->ic_sets);
   OrcModel* m = &t->model;
   free(m->tree_offset); free(m->tree_info); free(m->left); free(m->right); free(m->parent);
   free(m->split_index); free(m->split_bin); free(m->default_left); free(m->split_cond);
@@ -562,9 +563,38 @@ void orc_trainer_free(OrcTrainer* t) {
 typedef struct {
   int nid, depth; Split split; double G, H; float root_gain, weight;
   float lo, hi;            /* weight interval of the node under monotone constraints */
+  uint8_t* path; uint8_t* allowed;   /* interaction constraints: features on the path / features this node may split on (owned, F bytes) */
   int64_t begin, count;    /* row segment in ridx */
   double* hist;            /* owned */
 } Cand;
+
+/* [UPSTREAM-RECALL src/tree/constraints.cc FeatureInteractionConstraintHost]: the root may use any feature; a child may use the
+ * features on its path plus every feature of each constraint set that contains ALL path features. */
+void orc_set_interaction(OrcTrainer* t, const uint8_t* sets, int32_t n_sets) {
+  free(t->ic_sets); t->ic_sets = NULL; t->n_ic_sets = 0;
+  if (n_sets <= 0) return;
+  t->ic_sets = (uint8_t*)malloc((size_t)n_sets * (size_t)t->F); memcpy(t->ic_sets, sets, (size_t)n_sets * (size_t)t->F); t->n_ic_sets = n_sets;
+}
+static void cand_free(Cand* c) { free(c->hist); c->hist = NULL; free(c->path); c->path = NULL; free(c->allowed); c->allowed = NULL; }
+static void interaction_child(const OrcTrainer* t, const uint8_t* parent_path, int f, uint8_t** path_out, uint8_t** allowed_out) {
+  const int F = t->F;
+  uint8_t* path = (uint8_t*)malloc((size_t)F); uint8_t* allowed = (uint8_t*)malloc((size_t)F);
+  for (int j = 0; j < F; ++j) { path[j] = (parent_path[j] || j == f) ? 1 : 0; allowed[j] = path[j]; }
+  for (int s = 0; s < t->n_ic_sets; ++s) {
+    const uint8_t* set = t->ic_sets + (size_t)s * F;
+    int relevant = 1;
+    for (int j = 0; j < F && relevant; ++j) if (path[j] && !set[j]) relevant = 0;
+    if (relevant) for (int j = 0; j < F; ++j) if (set[j]) allowed[j] = 1;
+  }
+  *path_out = path; *allowed_out = allowed;
+}
+/* usable features of a node = sampling mask AND interaction-allowed mask (either may be absent) */
+static const uint8_t* combine_masks(const uint8_t* a, const uint8_t* b, int F, uint8_t* scratch) {
+  if (!a) return b;
+  if (!b) return a;
+  for (int j = 0; j < F; ++j) scratch[j] = a[j] && b[j];
+  return scratch;
+}
 
 static int new_node(OrcModel* m, int64_t base, int parent) {
   model_reserve_nodes(m, 1);
@@ -662,6 +692,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
   const int sampling = p->colsample_bytree < 1.0f || p->colsample_bylevel < 1.0f || p->colsample_bynode < 1.0f;
   uint8_t* tree_mask = NULL; uint8_t* level_masks = NULL; uint8_t* node_mask = NULL;
   const int maxd = p->max_depth > 0 ? p->max_depth : 1;
+  uint8_t* ic_scratch = (uint8_t*)malloc((size_t)(F > 0 ? F : 1));
   if (sampling) {
     uint8_t* all = (uint8_t*)malloc((size_t)F); memset(all, 1, (size_t)F);
     tree_mask = (uint8_t*)malloc((size_t)F);
@@ -687,10 +718,11 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
     if (!t->has_missing) { for (int i = t->cut_ptrs[0]; i < t->cut_ptrs[1]; ++i) { G += c.hist[2 * i]; H += c.hist[2 * i + 1]; } }
     else { for (int64_t r = 0; r < n; ++r) { G += gp[r * gs]; H += gp[r * gs + 1]; } }
     c.G = G; c.H = H; c.lo = -INFINITY; c.hi = INFINITY;
+    if (t->ic_sets) { c.path = (uint8_t*)calloc((size_t)F, 1); c.allowed = (uint8_t*)malloc((size_t)F); memset(c.allowed, 1, (size_t)F); }
     c.weight = calc_weight(p, G, H);
     c.root_gain = t->monotone ? gain_at_weight(p, G, H, c.weight) : calc_gain(p, G, H);
     m->base_weight[base] = c.weight; m->sum_hess[base] = (float)H; m->split_cond[base] = p->eta * c.weight;
-    { Mono mn = { t->monotone, c.lo, c.hi }; eval_split_mono(p, c.hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(0, 0), G, H, c.root_gain, &mn, &c.split); }
+    { Mono mn = { t->monotone, c.lo, c.hi }; eval_split_mono(p, c.hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, combine_masks(NODE_MASK(0, 0), c.allowed, F, ic_scratch), G, H, c.root_gain, &mn, &c.split); }
     cur[0] = c; ncur = 1;
   }
   int num_leaves = 1;
@@ -718,7 +750,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
       else if (c->split.loss_chg < p->gamma) valid = 0;
       else if (p->max_depth > 0 && c->depth == p->max_depth) valid = 0;
       else if (p->max_leaves > 0 && num_leaves == p->max_leaves) valid = 0;
-      if (!valid) { free(c->hist); c->hist = NULL; if (lossguide) stop = 1; continue; }
+      if (!valid) { cand_free(c); if (lossguide) stop = 1; continue; }
       num_leaves++;
       /* ApplySplit / ExpandNode */
       int64_t gi = base + c->nid;
@@ -750,6 +782,7 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
       cl.begin = c->begin; cl.count = nl; cr.begin = c->begin + nl; cr.count = nr;
       cl.G = c->split.GL; cl.H = c->split.HL; cr.G = c->split.GR; cr.H = c->split.HR;
       cl.lo = llo; cl.hi = lhi; cr.lo = rlo; cr.hi = rhi;
+      if (t->ic_sets) { interaction_child(t, c->path, c->split.findex, &cl.path, &cl.allowed); interaction_child(t, c->path, c->split.findex, &cr.path, &cr.allowed); }
       if (child_ok) {
         int fewer_right = c->split.HR < c->split.HL;
         Cand* bld = fewer_right ? &cr : &cl; Cand* sub = fewer_right ? &cl : &cr;
@@ -762,17 +795,17 @@ static void grow_tree(OrcTrainer* t, int k, int tree_index) {
           Cand* ch = two[s];
           ch->weight = t->monotone ? clamp_w(calc_weight(p, ch->G, ch->H), ch->lo, ch->hi) : calc_weight(p, ch->G, ch->H);
           ch->root_gain = t->monotone ? gain_at_weight(p, ch->G, ch->H, ch->weight) : calc_gain(p, ch->G, ch->H);
-          { Mono mn = { t->monotone, ch->lo, ch->hi }; eval_split_mono(p, ch->hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, NODE_MASK(ch->depth, ch->nid), ch->G, ch->H, ch->root_gain, &mn, &ch->split); }
-          if (ch->split.loss_chg > K_RT_EPS) next[nnext++] = *ch; else { free(ch->hist); ch->hist = NULL; }
+          { Mono mn = { t->monotone, ch->lo, ch->hi }; eval_split_mono(p, ch->hist, t->cut_ptrs, t->cut_vals, t->min_vals, F, combine_masks(NODE_MASK(ch->depth, ch->nid), ch->allowed, F, ic_scratch), ch->G, ch->H, ch->root_gain, &mn, &ch->split); }
+          if (ch->split.loss_chg > K_RT_EPS) next[nnext++] = *ch; else cand_free(ch);
         }
-      }
-      free(c->hist); c->hist = NULL;
+      } else { cand_free(&cl); cand_free(&cr); }
+      cand_free(c);
     }
     free(cur); cur = next; ncur = nnext;
-    if (stop) { for (int ci = 0; ci < ncur; ++ci) free(cur[ci].hist); ncur = 0; }
+    if (stop) { for (int ci = 0; ci < ncur; ++ci) cand_free(&cur[ci]); ncur = 0; }
   }
   free(cur);
-  free(tree_mask); free(level_masks); free(node_mask);
+  free(tree_mask); free(level_masks); free(node_mask); free(ic_scratch);
 #undef NODE_MASK
   /* finalize tree + prediction cache: traverse by bins (exact for training rows) */
   m->tree_offset[m->n_trees + 1] = m->n_nodes; m->tree_info[m->n_trees] = k; m->n_trees++;

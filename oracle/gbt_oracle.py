@@ -82,6 +82,7 @@ def lib():
         L.orc_num_threads.restype = C.c_int
         L.orc_set_quant_bits.argtypes = [C.c_void_p, C.c_int32]
         L.orc_set_monotone.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.orc_set_interaction.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_set_margins.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -234,6 +235,16 @@ class Trainer:
                 mc = [int(t) for t in mc.strip("()[] ").split(",") if t.strip()]
             self._mono = np.ascontiguousarray(list(mc), np.int32)
             lib().orc_set_monotone(self.h, _p(self._mono), len(self._mono))
+        ic = params.get("interaction_constraints")
+        if ic:
+            if isinstance(ic, str):
+                import json
+                ic = json.loads(ic.replace("(", "[").replace(")", "]"))
+            sets = np.zeros((len(ic), self.F), np.uint8)
+            for si, grp in enumerate(ic):
+                sets[si, [int(f) for f in grp]] = 1
+            self._ic = np.ascontiguousarray(sets)
+            lib().orc_set_interaction(self.h, _p(self._ic), len(ic))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -230,7 +230,7 @@ _IGNORED_PARAMS = {
     "deterministic_histogram", "single_precision_histogram", "updater", "refresh_leaf", "process_type", "device", "gpu_id",
     "sampling_method", "validate_parameters", "max_cat_to_onehot", "max_cat_threshold", "num_parallel_tree",
     "rate_drop", "one_drop", "skip_drop", "sample_type", "normalize_type", "lambda_bias", "feature_selector", "top_k",
-    "interaction_constraints", "aft_loss_distribution", "aft_loss_distribution_scale", "disable_default_eval_metric",
+    "aft_loss_distribution", "aft_loss_distribution_scale", "disable_default_eval_metric",
     "multi_strategy", "max_cached_hist_node", "random_state",
 }
 
@@ -254,10 +254,12 @@ def _check_unapplied(k, v):
         if isinstance(v, (list, tuple)):
             return "(" + ",".join(str(int(x)) for x in v) + ")"
         return str(v)
-    if k == "interaction_constraints":
-        if str(v).strip("()[] ,0") != "":
-            warnings.warn("%s is accepted for hyperparameter compatibility but NOT applied by the B200 hist builder" % k)
-        return _DROP
+    if k == "interaction_constraints":        # applied (tree.cu interaction_children); forwarded as "[[0,1],[2,3,4]]"
+        if isinstance(v, (list, tuple)):
+            if any(isinstance(x, str) for grp in v for x in (grp if isinstance(grp, (list, tuple)) else [grp])):
+                raise XGBoostError("interaction_constraints with feature names are not supported by the B200 hist builder; use feature indices")
+            return "[" + ",".join("[" + ",".join(str(int(x)) for x in grp) + "]" for grp in v) + "]"
+        return str(v)
     if k == "max_bin" and _as_float(v, 256) > 256:
         warnings.warn("max_bin=%s exceeds the 256 bins per feature of the uint8 bin codes; using max_bin=256" % v)
         return 256

@@ -118,6 +118,7 @@ class Booster {
   std::map<std::string, std::string> raw_params_;
   std::vector<std::string> eval_metrics_;
   std::vector<int> monotone_;              // parsed monotone_constraints (empty = none)
+  std::vector<std::vector<int>> interaction_;   // parsed interaction_constraints (empty = none)
   bool configured_ = false;
   TrainParam param_;
   std::string objective_name_ = "reg:squarederror";

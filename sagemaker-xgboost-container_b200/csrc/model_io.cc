@@ -184,6 +184,11 @@ JPtr Booster::config_to_json() {
   f("max_delta_step", param_.max_delta_step); i("max_depth", param_.max_depth); i("max_leaves", param_.max_leaves); f("min_child_weight", param_.min_child_weight);
   f("subsample", param_.subsample);
   if (!monotone_.empty()) { std::string v = "("; for (size_t j = 0; j < monotone_.size(); ++j) { if (j) v += ","; v += std::to_string(monotone_[j]); } v += ")"; ttp->set("monotone_constraints", S(v)); }
+  if (!interaction_.empty()) {
+    std::string v = "[";
+    for (size_t si = 0; si < interaction_.size(); ++si) { v += si ? ",[" : "["; for (size_t j = 0; j < interaction_[si].size(); ++j) { if (j) v += ","; v += std::to_string(interaction_[si][j]); } v += "]"; }
+    v += "]"; ttp->set("interaction_constraints", S(v));
+  }
   gb->set("tree_train_param", ttp);
   learner->set("gradient_booster", gb);
   JPtr lmp = JValue::Object(); lmp->set("base_score", S(float_repr(base_score_))); lmp->set("boost_from_average", S("1"));

@@ -35,6 +35,24 @@ __device__ __forceinline__ float calc_split_gain(const TrainParamDev& p, double 
   return calc_gain_given_weight(p, GL, HL, wl) + calc_gain_given_weight(p, GR, HR, wr);
 }
 
+// Interaction constraints (upstream src/tree/constraints.cc FeatureInteractionConstraintHost::SplitImpl [UPSTREAM-RECALL]): a
+// child may split on the features already used on its path, plus every feature of each constraint set that contains ALL of the
+// path's features; the root may use any feature.
+__device__ __forceinline__ void interaction_children(const ApplyArgs& a, int nid, int f, int Lc, int Rc) {
+  if (a.node_allowed == nullptr) return;
+  const size_t F = (size_t)a.F;
+  unsigned char* pl = a.node_path + (size_t)Lc * F; unsigned char* pr = a.node_path + (size_t)Rc * F;
+  unsigned char* al = a.node_allowed + (size_t)Lc * F; unsigned char* ar = a.node_allowed + (size_t)Rc * F;
+  const unsigned char* pp = a.node_path + (size_t)nid * F;
+  for (int j = 0; j < a.F; ++j) { const unsigned char v = (pp[j] || j == f) ? 1 : 0; pl[j] = v; pr[j] = v; al[j] = v; ar[j] = v; }
+  for (int s = 0; s < a.n_ic_sets; ++s) {
+    const unsigned char* set = a.ic_sets + (size_t)s * F;
+    bool relevant = true;
+    for (int j = 0; j < a.F && relevant; ++j) if (pl[j] && !set[j]) relevant = false;
+    if (relevant) for (int j = 0; j < a.F; ++j) if (set[j]) { al[j] = 1; ar[j] = 1; }
+  }
+}
+
 // Monotone constraints (upstream src/tree/split_evaluator.h TreeEvaluator): weights are clamped to the node's [lower, upper]
 // interval, the gain is evaluated AT the clamped weights (always the general form, never the t^2 / (H + lambda) shortcut), a
 // candidate whose child weights violate the feature's constraint is rejected, and a split hands mid = (wl + wr) / 2 down to the
@@ -118,6 +136,7 @@ __global__ void __launch_bounds__(32 * kEvalSegs) eval_kernel(EvalArgs a) {
   const int slot = threadIdx.x & 31, seg = threadIdx.x >> 5;
   const int f = group * kSlots + slot;
   bool active = slot < stride && f < a.F && (a.feat_mask == nullptr || a.feat_mask[f] != 0);
+  if (active && a.node_allowed != nullptr) active = a.node_allowed[(size_t)nid * a.F + f] != 0;
   if (a.feat_mask != nullptr && a.colsample_bynode < 1.0f) {
     // colsample_bynode: keep the max(1, floor(frac * |level set|)) features of the level's set with the smallest hash of this node
     __shared__ int s_rank[32], s_cnt;
@@ -305,6 +324,7 @@ __global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
       gs.lower[Lc] = lo; gs.upper[Lc] = hi; gs.lower[Rc] = lo; gs.upper[Rc] = hi;
       if (mc < 0) { gs.lower[Lc] = mid; gs.upper[Rc] = mid; } else if (mc > 0) { gs.upper[Lc] = mid; gs.lower[Rc] = mid; }
     }
+    interaction_children(a, nid, best.feature, Lc, Rc);
     const int cb = a.cut_ptrs[best.feature];
     float thr = best.dleft ? (best.bin < 0 ? a.min_vals[best.feature] : a.cut_vals[cb + best.bin]) : a.cut_vals[cb + best.bin];
     t.left[nid] = Lc; t.right[nid] = Rc; t.split_index[nid] = best.feature; t.split_cond[nid] = thr;
@@ -407,6 +427,7 @@ __global__ void __launch_bounds__(256) apply_lossguide_kernel(ApplyArgs a, int i
     gs.lower[Lc] = lo; gs.upper[Lc] = hi; gs.lower[Rc] = lo; gs.upper[Rc] = hi;
     if (mc < 0) { gs.lower[Lc] = mid; gs.upper[Rc] = mid; } else if (mc > 0) { gs.upper[Lc] = mid; gs.lower[Rc] = mid; }
   }
+  interaction_children(a, nid, best.feature, Lc, Rc);
   const int cb = a.cut_ptrs[best.feature];
   const float thr = best.dleft ? (best.bin < 0 ? a.min_vals[best.feature] : a.cut_vals[cb + best.bin]) : a.cut_vals[cb + best.bin];
   t.left[nid] = Lc; t.right[nid] = Rc; t.split_index[nid] = best.feature; t.split_cond[nid] = thr;

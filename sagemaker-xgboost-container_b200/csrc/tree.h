@@ -15,6 +15,7 @@ struct EvalArgs {
   const GH64* hist_pool; GrowState gs; const int* cut_ptrs; const unsigned char* feat_mask;
   TrainParamDev p; int F, ngroups, tw, ntail, has_missing, level, max_level_nodes;
   const int* monotone;            // per-feature monotone constraint (-1, 0, +1), nullptr = none
+  const unsigned char* node_allowed;   // interaction constraints: [cap_nodes][F] flags of the features a node may split on, nullptr = none
   float colsample_bynode; unsigned seed; const int* tree_index;     // per-node feature subset inside feat_mask (the level's set); tree index in device memory (graph replay)
 };
 
@@ -22,6 +23,9 @@ struct ApplyArgs {
   GrowState gs; TreeArrays tree; const int* cut_ptrs; const float* cut_vals; const float* min_vals;
   TrainParamDev p; unsigned* scratch; int ngroups /* candidate blocks per node: groups + tail */, level, max_level_nodes, next_base, next_half;
   const int* monotone;            // as in EvalArgs
+  // interaction constraints (upstream FeatureInteractionConstraintHost): per node the features used on its path and the features
+  // it may split on ([cap_nodes][F] each), the constraint sets as a membership matrix [n_sets][F]
+  unsigned char* node_path; unsigned char* node_allowed; const unsigned char* ic_sets; int n_ic_sets, F;
 };
 
 struct PartArgs {

@@ -499,6 +499,45 @@ def test_monotone_constraints_match_oracle_and_hold(xgb, oracle, extra):
     assert np.any(np.diff(free.predict(xgb.DMatrix(grid), output_margin=True)) < -1e-3)
 
 
+def _paths_respect(model, groups):
+    """every root-to-leaf path uses features of ONE constraint set (or a single feature outside every set)"""
+    for t in range(len(model["tree_info"])):
+        a, b = model["tree_offset"][t], model["tree_offset"][t + 1]
+        left, right, si = model["left"][a:b], model["right"][a:b], model["split_index"][a:b]
+        stack = [(0, frozenset())]
+        while stack:
+            i, feats = stack.pop()
+            if left[i] == -1:
+                if len(feats) > 1 and not any(feats <= set(g) for g in groups):
+                    return False
+                continue
+            f = feats | {int(si[i])}
+            stack.append((int(left[i]), f)); stack.append((int(right[i]), f))
+    return True
+
+
+@pytest.mark.parametrize("extra", [dict(max_depth=5), dict(grow_policy="lossguide", max_leaves=24, max_depth=0)])
+def test_interaction_constraints_match_oracle_and_hold(xgb, oracle, extra):
+    n, F, rounds = 20000, 7, 8
+    rng = np.random.default_rng(21)
+    X, _ = synth(n, F, 21, "reg")
+    y = (X[:, 0] * X[:, 1] + X[:, 2] * X[:, 3] + X[:, 4] + 0.5 * X[:, 5] * X[:, 0] + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    groups = [[0, 1], [2, 3, 4]]                                    # features 5 and 6 are in no set
+    params = dict(dict(objective="reg:squarederror", eta=0.3, interaction_constraints=groups), **extra)
+    d = xgb.DMatrix(X, label=y)
+    bst = xgb.train(params, d, num_boost_round=rounds, verbose_eval=False)
+    m = _be().booster_export_model(bst.handle)
+    mr = oracle.train(params, X, y, rounds).model()
+    assert first_structural_difference(m, mr) is None
+    assert_same_structure(m, mr)
+    assert max_leaf_diff(m, mr) <= LEAF_TOL
+    assert _paths_respect(m, groups)
+    free_bst = xgb.train(dict(objective="reg:squarederror", eta=0.3, max_depth=5), d, num_boost_round=rounds, verbose_eval=False)
+    free = _be().booster_export_model(free_bst.handle)              # (keep the Booster alive: its handle dies with it)
+    assert not _paths_respect(free, groups)                         # the unconstrained trees do mix the sets
+    assert "interaction_constraints" in bst.save_config()
+
+
 @pytest.mark.parametrize("weighted", [False, True])
 def test_auc_matches_sklearn(xgb, weighted):
     """Native `auc` (the one HPO metric the container does not compute itself, train_utils.py:45-76) against

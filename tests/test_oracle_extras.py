@@ -117,3 +117,27 @@ def test_oracle_monotone_constraints_give_monotone_models():
     a = O.train(dict(objective="reg:squarederror", max_depth=4), X, y, 3).model()
     b = O.train(dict(objective="reg:squarederror", max_depth=4, monotone_constraints="(0,0,0,0,0)"), X, y, 3).model()
     np.testing.assert_array_equal(a["split_cond"], b["split_cond"])
+
+
+def test_oracle_interaction_constraints_keep_paths_inside_one_set():
+    n = 5000
+    rng = np.random.default_rng(8)
+    X, _ = synth(n, 6, 15, "reg")
+    y = (X[:, 0] * X[:, 1] + X[:, 2] * X[:, 3] + X[:, 4] + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    groups = [[0, 1], [2, 3, 4]]
+    m = O.train(dict(objective="reg:squarederror", max_depth=5, interaction_constraints=groups), X, y, 6).model()
+    for t in range(len(m["tree_info"])):
+        a, b = m["tree_offset"][t], m["tree_offset"][t + 1]
+        left, right, si = m["left"][a:b], m["right"][a:b], m["split_index"][a:b]
+        stack = [(0, frozenset())]
+        while stack:
+            i, feats = stack.pop()
+            if left[i] == -1:
+                assert len(feats) <= 1 or any(feats <= set(g) for g in groups), feats
+                continue
+            f = feats | {int(si[i])}
+            stack.append((int(left[i]), f)); stack.append((int(right[i]), f))
+    # one set holding every feature constrains nothing
+    a = O.train(dict(objective="reg:squarederror", max_depth=4), X, y, 3).model()
+    b = O.train(dict(objective="reg:squarederror", max_depth=4, interaction_constraints="[[0,1,2,3,4,5]]"), X, y, 3).model()
+    np.testing.assert_array_equal(a["split_cond"], b["split_cond"])
