@@ -170,6 +170,13 @@ XGB_DLL int XGB200BoosterGetProfile(BoosterHandle handle, const char** out_json)
 XGB_DLL int XGB200LaunchCount(long long* out);
 /* wait for all device work queued by this library */
 XGB_DLL int XGB200Synchronize(void);
+/* Host-only converter: a pre-JSON binary model (Booster.save_model of xgboost < 2, optionally behind the "CONFIG-offset:"
+ * prefix of a pickled 1.x Booster) -> the UBJSON model document XGBoosterLoadModelFromBuffer reads.  The loaders call the
+ * same code internally (legacy_io.cc); exported so that old model archives can be migrated, and checked, without a GPU.
+ * Replaces: libxgboost's LearnerIO::LoadModel legacy branch behind serve_utils.get_loaded_booster
+ * (algorithm_mode/serve_utils.py:171-197; fixtures test/resources/models/{saved_booster,pickled_model}).
+ * *out is a thread-local buffer, valid until the next call of this function on the same thread. */
+XGB_DLL int XGB200LegacyModelToUBJ(const void* buf, bst_ulong len, bst_ulong* out_len, const char** out);
 
 #ifdef __cplusplus
 }

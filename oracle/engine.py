@@ -10,6 +10,7 @@ import pickle
 import numpy as np
 
 from . import gbt_oracle as O
+from . import legacy_model
 from . import ubjson
 
 
@@ -282,7 +283,10 @@ class OracleBackend:
 
     def booster_load_raw(self, h, buf):
         buf = bytes(buf)
-        doc = json.loads(buf.decode()) if buf[:2] in (b'{"', b"{ ", b"{\n") else ubjson.loads(buf)
+        if legacy_model.is_legacy(buf):                  # pre-JSON binary file / pickled 1.x state (serve_utils.py:171-197)
+            doc = legacy_model.to_document(buf)
+        else:
+            doc = json.loads(buf.decode()) if buf[:2] in (b'{"', b"{ ", b"{\n") else ubjson.loads(buf)
         if "Model" in doc:
             doc = doc["Model"]
         m = ubjson.model_from_xgb_json(doc)
@@ -298,6 +302,8 @@ class OracleBackend:
         return ubjson.dumps({"Model": _model_to_doc(h.model(), h.attrs, h.names), "Config": json.loads(self.booster_save_config(h))})
 
     def booster_unserialize(self, h, buf):
+        if legacy_model.is_legacy(bytes(buf)):
+            return self.booster_load_raw(h, buf)
         doc = ubjson.loads(bytes(buf))
         self.booster_load_raw(h, ubjson.dumps(doc["Model"]))
         self.booster_load_config(h, json.dumps(_jsonable(doc["Config"])))

@@ -316,12 +316,30 @@ class Booster:
         return state
 
     def __setstate__(self, state):
+        # Also opens pickles written by xgboost itself (serve_utils.get_loaded_booster tries pickle.load first,
+        # algorithm_mode/serve_utils.py:179-181): upstream's state keeps the serialized booster under "handle" (UBJSON
+        # {Model, Config} today, "CONFIG-offset:" + the binary model for 1.x) next to plain attributes.
+        state = dict(state)
         raw = state.pop("_raw", None)
-        self.__dict__.update(state)
+        if raw is None and isinstance(state.get("handle"), (bytes, bytearray)):
+            raw = state["handle"]
+        state.pop("handle", None)
+        names, types = state.pop("feature_names", None), state.pop("feature_types", None)
+        best_it, best_score = state.pop("best_iteration", None), state.pop("best_score", None)
+        state.pop("booster", None)                       # 1.x: the booster type ("gbtree"); the document carries it
+        self.__dict__.update(state)                      # (1.x also keeps best_ntree_limit, which stays a plain attribute)
         self._cache_refs = []
         self.handle = get_backend().booster_create([])
         if raw is not None:
             get_backend().booster_unserialize(self.handle, bytes(raw))
+        if names and self.feature_names is None:
+            self.feature_names = names
+        if types and self.feature_types is None:
+            self.feature_types = types
+        if best_it is not None and self.attr("best_iteration") is None:
+            self.set_attr(best_iteration=str(best_it))
+        if best_score is not None and self.attr("best_score") is None:
+            self.set_attr(best_score=str(best_score))
 
     def __copy__(self):
         return self.copy()
@@ -508,7 +526,7 @@ class Booster:
     # ---- model IO
     def save_raw(self, raw_format="ubj"):
         if raw_format == "deprecated":
-            raise XGBoostError("the legacy binary model format is not supported; use 'ubj' or 'json'")
+            raise XGBoostError("writing the legacy binary model format is not supported (it is read by load_model); use 'ubj' or 'json'")
         return bytearray(get_backend().booster_save_raw(self.handle, raw_format))
 
     def save_model(self, fname):

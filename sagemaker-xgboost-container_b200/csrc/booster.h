@@ -69,6 +69,11 @@ struct PendingTree {            // a tree still on its way from the device (asyn
 
 struct PredCache { DevBuf<float> margin; int trees_applied = 0; int64_t n = 0; uint64_t model_version = 0; };
 
+// legacy_io.cc: the pre-JSON binary model format -> the 3.x model document
+bool looks_like_legacy_binary(const char* buf, size_t len);
+JPtr legacy_binary_to_doc(const char* buf, size_t len);
+std::pair<const char*, size_t> legacy_serialized_model_section(const char* buf, size_t len);
+
 class Booster {
  public:
   Booster();

@@ -537,5 +537,16 @@ int XGB200BoosterGetProfile(BoosterHandle handle, const char** out_json) {
 }
 int XGB200LaunchCount(long long* out) { API_BEGIN(); *out = g_kernel_launches; API_END(); }
 int XGB200Synchronize(void) { API_BEGIN(); CUDA_OK(cudaStreamSynchronize(engine_stream())); API_END(); }
+int XGB200LegacyModelToUBJ(const void* buf, bst_ulong len, bst_ulong* out_len, const char** out) {
+  API_BEGIN();
+  B200_CHECK(buf != nullptr && out_len != nullptr && out != nullptr, "XGB200LegacyModelToUBJ: NULL argument");
+  const char* p = (const char*)buf; size_t n = (size_t)len;
+  auto sect = legacy_serialized_model_section(p, n);
+  if (sect.first != nullptr) { p = sect.first; n = sect.second; }
+  B200_CHECK(looks_like_legacy_binary(p, n), "XGB200LegacyModelToUBJ: the buffer is not a legacy binary model");
+  g_ret_str.clear(); ubj_write(*legacy_binary_to_doc(p, n), &g_ret_str);
+  *out_len = g_ret_str.size(); *out = g_ret_str.data();
+  API_END();
+}
 
 }  // extern "C"

@@ -156,13 +156,17 @@ std::string Booster::save_model_buffer(const std::string& format) {
 static JPtr parse_any(const char* buf, size_t len) {
   B200_CHECK(len >= 2, "model buffer is empty");
   size_t i = 0; while (i < len && (buf[i] == ' ' || buf[i] == '\n' || buf[i] == '\t' || buf[i] == '\r')) ++i;
-  B200_CHECK(i < len && buf[i] == '{', "Unknown model format: only the xgboost JSON and UBJSON formats are supported (the legacy binary format was removed upstream in 3.1 and is not implemented here)");
+  B200_CHECK(i < len && buf[i] == '{', "Unknown model format: expected an xgboost JSON / UBJSON document or a legacy binary model");
   char c = i + 1 < len ? buf[i + 1] : 0;
   if (c == '"' || c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '}') return JsonReader(buf + i, len - i).parse();
   return UbjReader(reinterpret_cast<const unsigned char*>(buf + i), len - i).parse();
 }
 
 void Booster::load_model_buffer(const char* buf, size_t len) {
+  // pre-JSON binary files and the pickled state of xgboost 1.x Boosters (serve_utils.py:171-197 meets both): legacy_io.cc
+  auto sect = legacy_serialized_model_section(buf, len);
+  if (sect.first != nullptr) { model_from_json(*legacy_binary_to_doc(sect.first, sect.second)); return; }   // (its 1.x config section names only defaults)
+  if (looks_like_legacy_binary(buf, len)) { model_from_json(*legacy_binary_to_doc(buf, len)); return; }
   JPtr doc = parse_any(buf, len);
   if (doc->has("Model")) { model_from_json(doc->at("Model")); if (doc->has("Config")) config_from_json(doc->at("Config")); }
   else model_from_json(*doc);

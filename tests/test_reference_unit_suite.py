@@ -42,3 +42,7 @@ def test_reference_unit_file_passes_on_this_package(path, deselect, min_passed, 
     assert r.returncode == 0, tail
     assert " failed" not in r.stdout.splitlines()[-1], tail
     assert m and int(m.group(1)) >= min_passed, tail
+    if path.endswith("test_serve_utils.py"):
+        # test_get_loaded_booster[pickled_model|saved_booster] is xfail in the reference ("serialized with XGBoost <3.0 ...
+        # incompatible", test_serve_utils.py:80): this package reads both legacy forms (csrc/legacy_io.cc), so they pass
+        assert "2 xpassed" in r.stdout, tail
