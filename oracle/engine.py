@@ -177,11 +177,32 @@ class OracleBackend:
         else:
             h.params[k] = v
 
+    def _gathered(self, dh):
+        """Multi-rank runs on this TEST engine (world_size-2 CPU tests of the launcher, tests/test_multi_gpu_launcher.py): every
+        rank assembles the row shards of all ranks and trains / evaluates on the whole matrix, which is what the CUDA engine's
+        histogram all-reduce amounts to.  Collective: all ranks must call this for the same matrices in the same order."""
+        from sagemaker_xgboost_container_b200 import collective
+        world, rank = collective.get_world_size(), collective.get_rank()
+        if world <= 1:
+            return dh
+        if getattr(dh, "_full", None) is None:
+            parts = []
+            for r in range(world):
+                mine = {"X": dh.X.tobytes(), "shape": list(dh.X.shape), "info": {k: v.tobytes() for k, v in dh.info.items()}} if r == rank else None
+                parts.append(collective.broadcast(mine, r))
+            full = _DM(np.concatenate([np.frombuffer(p["X"], np.float32).reshape(p["shape"]) for p in parts]))
+            for k in dh.info:
+                full.info[k] = np.concatenate([np.frombuffer(p["info"][k], np.float32) for p in parts])
+            dh._full = full
+        return dh._full
+
     def _ensure_trainer(self, h, dh):
         if h.trainer is not None and h.trainer_dm is dh:
             return
         if h.trainer is not None:
             raise self.err("oracle engine: training matrix changed")
+        local = dh
+        dh = self._gathered(dh)
         y = dh.info["label"]
         if len(y) != dh.X.shape[0]:
             raise self.err("Check failed: preds.size() == info.labels_.size() : labels are not correctly provided")
@@ -197,7 +218,7 @@ class OracleBackend:
             h.trainer = O.Trainer(params, X=dh.X, y=y, weights=w)
         except ValueError as e:
             raise self.err(str(e))
-        h.trainer_dm = dh
+        h.trainer_dm = local
         h.num_feature = dh.X.shape[1]
         if h.loaded is not None and len(h.loaded["tree_info"]):
             h.trainer.set_margins(O.predict_margin(h.loaded, dh.X))
@@ -222,6 +243,7 @@ class OracleBackend:
         metrics = h.metrics or [{"reg:squarederror": "rmse", "reg:logistic": "rmse", "binary:logistic": "logloss", "binary:logitraw": "logloss"}.get(h.objective(), "mlogloss")]
         msg = "[%d]" % it
         for dh, name in zip(dhs, names):
+            dh = self._gathered(dh)
             m, margin = self._margin(h, dh)
             y = dh.info["label"].astype(np.float64)
             w = dh.info["weight"].astype(np.float64) if len(dh.info["weight"]) else np.ones(len(y))
