@@ -135,6 +135,14 @@ XGB_DLL int XGB200DMatrixCreateFromCSVEx(const char* text, bst_ulong len, char d
                              int* status, DMatrixHandle* out);
 /* 1 when the per-level histogram all-reduce runs as the NVLink peer-memory kernel (nvlink.cu), 0 when it goes through NCCL */
 XGB_DLL int XGB200CommPeerReduceActive(void);
+/* Columnar training input without a dense float32 matrix on the host (Parquet through pyarrow, pandas frames): `ncols` host
+ * buffers of `nrow` items each, col_types[c] in {0 f32, 1 f64, 2 i32, 3 i64, 4 u8, 5 i8, 6 i16, 7 u16, 8 u32, 9 u64, 10 bool};
+ * the buffers cross PCIe as they are and are converted (round to nearest, like numpy's astype(float32)) and transposed into
+ * the row-major matrix on the device (ingest.cu).  label_column / weight_column (-1 = none) become the label / weight info.
+ * Replaces the host copies of data_utils.get_parquet_dmatrix (data_utils.py:368-390: read_table -> to_pandas -> to_numpy ->
+ * data[:, 1:]) in front of XGDMatrixCreateFromMat. */
+XGB_DLL int XGB200DMatrixCreateFromColumns(const void* const* cols, const int* col_types, int ncols, bst_ulong nrow, int label_column,
+                                   int weight_column, DMatrixHandle* out);
 /* the float32 feature matrix as the engine holds it (row-major n x F, NaN = missing), for bit-exact checks of the input paths */
 XGB_DLL int XGB200DMatrixGetRaw(DMatrixHandle handle, float* out_row_major);
 /* binned feature blocks back on the host in plain row-major n x F order (for bit-exact checks of the binning kernel) */

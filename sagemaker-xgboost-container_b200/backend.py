@@ -109,6 +109,28 @@ class CudaBackend:
                                                           C.c_int(label_column), C.c_int(weight_column), C.byref(st), C.byref(h)))
         return (h if st.value == 0 else None), int(st.value)
 
+    _COL_TYPES = {"<f4": 0, "<f8": 1, "<i4": 2, "<i8": 3, "|u1": 4, "|i1": 5, "<i2": 6, "<u2": 7, "<u4": 8, "<u8": 9, "|b1": 10}
+
+    def dmatrix_from_columns(self, columns, label_column=-1, weight_column=-1):
+        """Columnar input (ingest.cu): one contiguous 1-D numpy array per column, in its own dtype where the device converts it
+        (float32/64, (u)int8..64, bool), anything else converted to float32 one column at a time -- never a dense host matrix."""
+        cols = []
+        for c in columns:
+            a = np.asarray(c)
+            if a.ndim != 1:
+                raise ValueError("columns must be 1-dimensional")
+            if a.dtype.str not in self._COL_TYPES:
+                a = a.astype(np.float32)
+            cols.append(np.ascontiguousarray(a))
+        n = len(cols[0]) if cols else 0
+        if any(len(a) != n for a in cols):
+            raise ValueError("columns have different lengths")
+        ptrs = (C.c_void_p * len(cols))(*[a.ctypes.data for a in cols])
+        types = (C.c_int * len(cols))(*[self._COL_TYPES[a.dtype.str] for a in cols])
+        h = C.c_void_p()
+        self._check(self.lib.XGB200DMatrixCreateFromColumns(ptrs, types, C.c_int(len(cols)), C.c_ulong(n), C.c_int(label_column), C.c_int(weight_column), C.byref(h)))
+        return h
+
     def dmatrix_from_csv(self, payload, delimiter=","):
         """Device-side CSV parse (csv.cu).  Returns (handle, status); handle is None unless status == 0."""
         h = C.c_void_p()

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "lib", "libb200xgb.so")
-SOURCES = ["hist.cu", "tree.cu", "misc.cu", "quantile.cu", "auc.cu", "shap.cu", "csv.cu", "nvlink.cu", "booster.cu", "model_io.cc", "legacy_io.cc", "comm.cc", "capi.cc"]
+SOURCES = ["hist.cu", "tree.cu", "misc.cu", "quantile.cu", "auc.cu", "shap.cu", "csv.cu", "ingest.cu", "nvlink.cu", "booster.cu", "model_io.cc", "legacy_io.cc", "comm.cc", "capi.cc"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
          "-diag-suppress", "177", "-I", os.path.join(HERE, "..", "include")]

@@ -60,7 +60,12 @@ class DMatrix:
         elif _is_pandas_df(data):
             if feature_names is None:
                 feature_names = [str(c) for c in data.columns]
-            self.handle = be.dmatrix_from_dense(data.to_numpy(dtype=np.float32, na_value=np.nan) if hasattr(data, "to_numpy") else np.asarray(data), miss)
+            if hasattr(be, "dmatrix_from_columns") and missing is None and len(data.columns) > 0 and all(
+                    isinstance(t, np.dtype) and t.kind in "fiub" for t in data.dtypes):
+                # column buffers straight to the device (csrc/ingest.cu): no dense float32 copy of the frame on the host
+                self.handle = be.dmatrix_from_columns([data.iloc[:, j].to_numpy() for j in range(len(data.columns))])
+            else:
+                self.handle = be.dmatrix_from_dense(data.to_numpy(dtype=np.float32, na_value=np.nan) if hasattr(data, "to_numpy") else np.asarray(data), miss)
         elif isinstance(data, DMatrix):
             raise TypeError("cannot construct a DMatrix from a DMatrix")
         else:

@@ -84,18 +84,7 @@ std::unique_ptr<DMatrix> DMatrix::from_device(const float* dptr, int64_t nrow, i
   return dm;
 }
 
-std::unique_ptr<DMatrix> DMatrix::from_csr(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr,
-                                           size_t nelem, size_t ncol) {
-  // densify on the host with NaN for absent entries (upstream keeps CSR; the hist path needs a dense bin matrix anyway)
-  B200_CHECK(nindptr >= 1, "DMatrix: empty indptr");
-  const size_t nrow = nindptr - 1;
-  size_t F = ncol;
-  for (size_t i = 0; i < nelem; ++i) F = std::max<size_t>(F, (size_t)indices[i] + 1);
-  std::vector<float> dense(nrow * F, std::nanf(""));
-  for (size_t r = 0; r < nrow; ++r)
-    for (size_t j = indptr[r]; j < indptr[r + 1]; ++j) dense[r * F + indices[j]] = data[j];
-  return from_dense(dense.data(), (int64_t)nrow, (int)F, std::nanf(""));
-}
+// DMatrix::from_csr / from_columns: ingest.cu (device-side densify / column transpose, no dense host copy)
 
 __global__ void gather_rows_kernel(const float* X, int F, const int* idx, int64_t len, float* out) {
   const int64_t total = len * F;

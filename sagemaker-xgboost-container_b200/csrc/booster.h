@@ -39,6 +39,9 @@ class DMatrix {
   static std::unique_ptr<DMatrix> from_csv_text(const char* text, int64_t len, char delim, int* status);
   // training channel: columns label_col / weight_col (-1 = none) become the label / weight info, the rest the features
   static std::unique_ptr<DMatrix> from_csv_text_labeled(const char* text, int64_t len, char delim, int label_col, int weight_col, int* status);
+  // columnar input (ingest.cu): `ncols` host column buffers of `nrow` items each, type codes as in include/b200xgb.h; columns
+  // label_col / weight_col (-1 = none) become the label / weight info, the others the features in order
+  static std::unique_ptr<DMatrix> from_columns(const void* const* cols, const int* types, int ncols, int64_t nrow, int label_col, int weight_col);
   static std::unique_ptr<DMatrix> from_csr(const size_t* indptr, const unsigned* indices, const float* data, size_t nindptr, size_t nelem, size_t ncol);
   std::unique_ptr<DMatrix> slice(const int* idx, int64_t len) const;
   void set_float_info(const std::string& field, const float* v, size_t len);

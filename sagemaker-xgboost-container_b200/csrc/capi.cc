@@ -537,6 +537,14 @@ int XGB200BoosterGetProfile(BoosterHandle handle, const char** out_json) {
 }
 int XGB200LaunchCount(long long* out) { API_BEGIN(); *out = g_kernel_launches; API_END(); }
 int XGB200Synchronize(void) { API_BEGIN(); CUDA_OK(cudaStreamSynchronize(engine_stream())); API_END(); }
+int XGB200DMatrixCreateFromColumns(const void* const* cols, const int* col_types, int ncols, bst_ulong nrow, int label_column, int weight_column, DMatrixHandle* out) {
+  API_BEGIN();
+  B200_CHECK(out != nullptr && (ncols == 0 || (cols != nullptr && col_types != nullptr)), "XGB200DMatrixCreateFromColumns: NULL argument");
+  auto box = new DMatrixBox(); std::unique_ptr<DMatrixBox> guard(box);
+  box->dm = DMatrix::from_columns(cols, col_types, ncols, (int64_t)nrow, label_column, weight_column);
+  *out = guard.release();
+  API_END();
+}
 int XGB200LegacyModelToUBJ(const void* buf, bst_ulong len, bst_ulong* out_len, const char** out) {
   API_BEGIN();
   B200_CHECK(buf != nullptr && out_len != nullptr && out != nullptr, "XGB200LegacyModelToUBJ: NULL argument");

@@ -143,3 +143,41 @@ def load_uri(uri):
     if fmt == "libsvm":
         return _load_libsvm(files, q)
     raise XGBoostError("Unknown data format in URI: %s" % fmt)
+
+
+def _arrow_columns(table):
+    """pyarrow Table -> one numpy array per column without assembling a frame: a column without nulls is handed over in its
+    own dtype (zero-copy for a single chunk), nulls become NaN (float64, as Table.to_pandas does for numeric columns)."""
+    cols = []
+    for i in range(table.num_columns):
+        col = table.column(i)
+        if col.num_chunks != 1:
+            col = col.combine_chunks()
+        else:
+            col = col.chunk(0)
+        try:
+            cols.append(col.to_numpy(zero_copy_only=col.null_count == 0))
+        except Exception:
+            cols.append(np.asarray(col.to_numpy(zero_copy_only=False), np.float32))
+    return cols
+
+
+def parquet_to_dmatrix(files_path):
+    """Parquet channel -> DMatrix, column 0 = label (what data_utils._get_parquet_dmatrix_file_mode builds, data_utils.py:368-390)
+    without its host copies (Table -> DataFrame -> ndarray -> data[:, 1:]): the arrow column buffers go to the device as they are
+    and are converted / transposed there (csrc/ingest.cu).  Optional binding in the container, like encoder.csv_to_dmatrix:
+
+        def _get_parquet_dmatrix_file_mode(files_path):
+            return sagemaker_xgboost_container_b200.data.parquet_to_dmatrix(files_path)
+    """
+    import pyarrow.parquet as pq
+    from .backend import get_backend
+    from .core import DMatrix
+    table = pq.read_table(files_path)
+    be = get_backend()
+    if table.num_columns < 1:
+        raise XGBoostError("Parquet input has no columns")
+    if not hasattr(be, "dmatrix_from_columns"):
+        data = table.to_pandas().to_numpy()
+        return DMatrix(data[:, 1:], label=data[:, 0])
+    return DMatrix._from_handle(be.dmatrix_from_columns(_arrow_columns(table), label_column=0))

@@ -124,7 +124,11 @@ def load_shard(path, content_type, rank, world):
     if not parts:
         raise ValueError("worker %d of %d has no rows: %s holds %d rows" % (rank, world, path, n))
     t = pa.concat_tables(parts)
-    cols = [np.asarray(t.column(i).to_numpy(zero_copy_only=False), np.float32) for i in range(t.num_columns)]
+    from .data import _arrow_columns
+    be = get_backend()
+    if hasattr(be, "dmatrix_from_columns"):               # arrow column buffers straight to the device (csrc/ingest.cu)
+        return DMatrix._from_handle(be.dmatrix_from_columns(_arrow_columns(t), label_column=0)), n
+    cols = [np.asarray(c, np.float32) for c in _arrow_columns(t)]
     X = np.empty((len(cols[0]), len(cols) - 1), np.float32)
     for j, c in enumerate(cols[1:]):
         X[:, j] = c
