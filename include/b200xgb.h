@@ -134,6 +134,13 @@ XGB_DLL int XGB200DMatrixCreateFromCSV(const char* text, bst_ulong len, char del
 XGB_DLL int XGB200DMatrixCreateFromCSVEx(const char* text, bst_ulong len, char delimiter, int label_column, int weight_column,
                              int* status, DMatrixHandle* out);
 /* 1 when the per-level histogram all-reduce runs as the NVLink peer-memory kernel (nvlink.cu), 0 when it goes through NCCL */
+/* A libsvm request body ("label idx:val ..." lines, already stripped) parsed on the device into a dense matrix.
+ * whitespace_mode 0 / absent NaN = serve_utils._get_sparse_matrix_from_libsvm + xgb.DMatrix(csr) (algorithm_mode/serve_utils.py:94-118,
+ * 132-137: tokens split on ' ', entries a line does not list are missing); whitespace_mode 1 / absent 0 = encoder.libsvm_to_dmatrix
+ * (encoder.py:54-86: split on any whitespace, dense zeros).  Indices shift to 0-based when the smallest one is >= 1, as both do.
+ * *status: 0 ok; 2 = the body holds something the Python routes treat specially (non-digit index, literal outside the exact
+ * fast path, repeated index in a line, trailing empty lines ...): take the host route; 3 = no entry at all (ditto). */
+XGB_DLL int XGB200DMatrixCreateFromLibsvmText(const char* text, bst_ulong len, int whitespace_mode, float absent, int* status, DMatrixHandle* out);
 XGB_DLL int XGB200CommPeerReduceActive(void);
 /* Columnar training input without a dense float32 matrix on the host (Parquet through pyarrow, pandas frames): `ncols` host
  * buffers of `nrow` items each, col_types[c] in {0 f32, 1 f64, 2 i32, 3 i64, 4 u8, 5 i8, 6 i16, 7 u16, 8 u32, 9 u64, 10 bool};

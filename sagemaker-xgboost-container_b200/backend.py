@@ -131,6 +131,21 @@ class CudaBackend:
         self._check(self.lib.XGB200DMatrixCreateFromColumns(ptrs, types, C.c_int(len(cols)), C.c_ulong(n), C.c_int(label_column), C.c_int(weight_column), C.byref(h)))
         return h
 
+    def dmatrix_from_libsvm_text(self, payload, whitespace_mode, absent):
+        """Device-side parse of a libsvm request body (csv.cu).  Returns (handle, status); handle is None unless status == 0."""
+        h = C.c_void_p()
+        st = C.c_int(0)
+        if isinstance(payload, str):
+            size = C.c_ssize_t(0)
+            ptr = _utf8_and_size(payload, C.byref(size))
+            if not ptr:
+                raise ValueError("libsvm payload is not valid UTF-8")
+            text, length = C.c_char_p(ptr), size.value
+        else:
+            text, length = C.c_char_p(bytes(payload) if not isinstance(payload, bytes) else payload), len(payload)
+        self._check(self.lib.XGB200DMatrixCreateFromLibsvmText(text, C.c_ulong(length), C.c_int(whitespace_mode), C.c_float(absent), C.byref(st), C.byref(h)))
+        return (h if st.value == 0 else None), int(st.value)
+
     def dmatrix_from_csv(self, payload, delimiter=","):
         """Device-side CSV parse (csv.cu).  Returns (handle, status); handle is None unless status == 0."""
         h = C.c_void_p()

@@ -485,6 +485,15 @@ int XGB200DMatrixCreateFromCSV(const char* text, bst_ulong len, char delimiter, 
   if (st == 0) { auto box = new DMatrixBox(); box->dm = std::move(dm); *out = box; }
   API_END();
 }
+int XGB200DMatrixCreateFromLibsvmText(const char* text, bst_ulong len, int whitespace_mode, float absent, int* status, DMatrixHandle* out) {
+  API_BEGIN();
+  int st = 0;
+  auto dm = DMatrix::from_libsvm_text(text, (int64_t)len, whitespace_mode, absent, &st);
+  if (status) *status = st;
+  *out = nullptr;
+  if (st == 0) { auto box = new DMatrixBox(); box->dm = std::move(dm); *out = box; }
+  API_END();
+}
 int XGB200BuildRootHistogram(BoosterHandle handle, DMatrixHandle dmat, const float* gpair, int repeats, int64_t* out_hist, float* scales, float* out_ms) {
   API_BEGIN();
   DMatrix* dm = DM(dmat);

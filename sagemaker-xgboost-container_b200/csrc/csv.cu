@@ -113,6 +113,10 @@ __global__ void __launch_bounds__(256) count_newlines_kernel(const char* text, i
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+__global__ void fill_value_kernel(float* X, int64_t count, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) X[i] = v;
+}
+
 // request-sized scratch kept across calls (a serving process parses one body after another): no cudaMalloc per request
 struct CsvScratch { DevBuf<char> text; DevBuf<int64_t> nl; DevBuf<unsigned char> tmp; DevBuf<unsigned long long> cnt; DevBuf<int> err; };
 static CsvScratch& csv_scratch() { static thread_local CsvScratch s; return s; }
@@ -163,6 +167,118 @@ int parse_csv_device(const char* h_text, int64_t len, char delim, int F, int64_t
   CUDA_OK(cudaStreamSynchronize(s));
   lap("parse kernel");
   return err;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// libsvm request bodies ("label idx:val idx:val ..." per line): serve_utils._get_sparse_matrix_from_libsvm
+// (algorithm_mode/serve_utils.py:94-118, per-token Python loop -> COO -> csr_matrix -> DMatrix: absent entries are MISSING) and
+// encoder.libsvm_to_dmatrix (encoder.py:54-86, script mode: dense zeros, absent entries are 0.0).  Both shift the indices to
+// 0-based when the smallest index in the body is >= 1.  One thread per line, two passes over the text: (1) index range and
+// entry check, (2) values into the pre-filled matrix.  Anything the two Python routes treat specially -- an index that is not
+// plain digits, a value outside the exact fast path or empty, an index repeated inside a line (COO sums it, the dict keeps the
+// last), a token with a second ':' -- raises the fallback flag and the caller takes the reference's own host route.
+struct LibsvmRange { int min_idx, max_idx; unsigned long long entries; int err; int last_row_entries; };
+
+template <bool kFill>
+__global__ void __launch_bounds__(256) libsvm_kernel(const char* text, int64_t len, const int64_t* nl, int64_t n, LibsvmRange* rg, int whitespace_mode,
+                                                     float* X, int F, int shift, float absent) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const char* p = text + (r ? nl[r - 1] + 1 : 0);
+  const char* e = text + (r < n - 1 ? nl[r] : len);
+  int lo = 0x7fffffff, hi = -1, cnt = 0; bool bad = false;
+  const char* q = p;
+  while (q < e) {
+    // token = run of non-separator characters; serve_utils splits on ' ' only, the encoder on any whitespace
+    while (q < e && (*q == ' ' || (whitespace_mode && (*q == '\t' || *q == '\r' || *q == '\f' || *q == '\v')))) ++q;
+    const char* t = q;
+    while (q < e && !(*q == ' ' || (whitespace_mode && (*q == '\t' || *q == '\r' || *q == '\f' || *q == '\v')))) ++q;
+    if (t == q) break;
+    const char* c = t; while (c < q && *c != ':') ++c;
+    if (c == q) continue;                                                        // no colon: the label (or junk both routes ignore)
+    int idx = 0; bool ok = c > t && (c - t) <= 9;
+    for (const char* d = t; d < c && ok; ++d) { if (*d < '0' || *d > '9') ok = false; else idx = idx * 10 + (*d - '0'); }
+    const char* v = c + 1;
+    for (const char* d = v; d < q && ok; ++d) if (*d == ':' || *d == '_') ok = false;       // second colon / digit separators: host decides
+    float val = 0.f;
+    if (ok) { if (v == q || !parse_field(v, q, &val)) ok = false; else if (v < q && (is_space(*v) || is_space(q[-1]))) ok = false; }
+    if (!ok) { bad = true; continue; }
+    ++cnt; lo = min(lo, idx); hi = max(hi, idx);
+    if (kFill) {
+      float* slot = X + r * F + (idx - shift);
+      // serve_utils' COO -> CSR conversion SUMS an index repeated inside a line (the encoder's dict keeps the last one, which is
+      // what this sequential walk does): with NaN as the fill value a slot that is no longer NaN has been written before
+      if (!whitespace_mode && (val != val || *slot == *slot)) bad = true;
+      *slot = val;
+    }
+  }
+  if (bad) atomicMax(&rg->err, 2);
+  if (!kFill) {
+    if (cnt) { atomicMin(&rg->min_idx, lo); atomicMax(&rg->max_idx, hi); atomicAdd(&rg->entries, (unsigned long long)cnt); }
+    if (r == n - 1) rg->last_row_entries = cnt;
+  }
+}
+
+// status: 0 ok, 2 host route needed (see above), 3 no entries at all (both routes special-case it on the host)
+int parse_libsvm_device(const char* h_text, int64_t len, int whitespace_mode, float absent, int64_t* n_rows_out, int* F_out, DevBuf<float>* X, cudaStream_t s) {
+  CsvScratch& sc = csv_scratch();
+  sc.text.ensure((size_t)len + 16); sc.cnt.ensure(2); sc.err.ensure(16);
+  CUDA_OK(cudaMemcpyAsync(sc.text.p, h_text, (size_t)len, cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaMemsetAsync(sc.cnt.p, 0, 16, s));
+  count_newlines_kernel<<<148 * 8, 256, 0, s>>>(sc.text.p, len, sc.cnt.p); ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
+  unsigned long long nnl = 0;
+  CUDA_OK(cudaMemcpyAsync(&nnl, sc.cnt.p, sizeof(nnl), cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  const int64_t n = (int64_t)nnl + 1;
+  sc.nl.ensure((size_t)nnl + 1);
+  if (nnl > 0) {
+    cub::CountingInputIterator<int64_t> idx(0);
+    IsNewline pred{sc.text.p};
+    size_t tmp_bytes = 0;
+    long long* d_num = reinterpret_cast<long long*>(sc.cnt.p + 1);
+    CUDA_OK(cub::DeviceSelect::If(nullptr, tmp_bytes, idx, sc.nl.p, d_num, len, pred, s));
+    sc.tmp.ensure(tmp_bytes);
+    CUDA_OK(cub::DeviceSelect::If(sc.tmp.p, tmp_bytes, idx, sc.nl.p, d_num, len, pred, s));
+    ++g_kernel_launches;
+  }
+  static_assert(sizeof(LibsvmRange) <= 16 * sizeof(int), "range block lives in the err scratch");
+  LibsvmRange* rg = reinterpret_cast<LibsvmRange*>(sc.err.p);
+  LibsvmRange init{0x7fffffff, -1, 0ull, 0, 0};
+  CUDA_OK(cudaMemcpyAsync(rg, &init, sizeof init, cudaMemcpyHostToDevice, s));
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  libsvm_kernel<false><<<grid, 256, 0, s>>>(sc.text.p, len, sc.nl.p, n, rg, whitespace_mode, nullptr, 0, 0, absent); ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
+  LibsvmRange h{};
+  CUDA_OK(cudaMemcpyAsync(&h, rg, sizeof h, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  if (h.err != 0) return 2;
+  if (h.entries == 0) return 3;
+  if (!whitespace_mode && h.last_row_entries == 0) return 2;      // csr_matrix((data, (row, col))) infers its row count: trailing empty lines vanish there
+  const int shift = h.min_idx >= 1 ? 1 : 0;
+  const int F = h.max_idx - shift + 1;
+  B200_CHECK((double)n * (double)F < 4e9, "libsvm body: the dense matrix would exceed 4e9 entries");
+  X->alloc((size_t)n * F);
+  fill_value_kernel<<<148 * 8, 256, 0, s>>>(X->p, (int64_t)n * F, absent); ++g_kernel_launches;
+  libsvm_kernel<true><<<grid, 256, 0, s>>>(sc.text.p, len, sc.nl.p, n, rg, whitespace_mode, X->p, F, shift, absent); ++g_kernel_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(&h, rg, sizeof h, cudaMemcpyDeviceToHost, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  if (h.err != 0) return 2;
+  *n_rows_out = n; *F_out = F;
+  return 0;
+}
+
+std::unique_ptr<DMatrix> DMatrix::from_libsvm_text(const char* text, int64_t len, int whitespace_mode, float absent, int* status) {
+  auto dm = std::make_unique<DMatrix>();
+  cudaStream_t s = engine_stream();
+  int64_t n = 0; int F = 0;
+  *status = parse_libsvm_device(text, len, whitespace_mode, absent, &n, &F, &dm->X, s);
+  if (*status != 0) return nullptr;
+  B200_CHECK(n < (int64_t)0x7fffffff, "DMatrix: more than 2^31-1 rows per GPU are not supported");
+  dm->n = n; dm->F = F;
+  dm->finish_upload(std::nanf(""));
+  return dm;
 }
 
 // training channels (data_utils.py:289-318: "?format=csv&label_column=0[&weight_column=1]"): the label / weight columns

@@ -53,6 +53,72 @@ def csv_to_dmatrix(input, dtype=None):
     return DMatrix(_host_csv_to_array(input if isinstance(input, str) else input.decode("utf-8"), delimiter, float if dtype is None else dtype))
 
 
+def _host_sparse_matrix_from_libsvm(payload):
+    """The reference's own route (algorithm_mode/serve_utils.py:94-118), kept for the bodies the device parser hands back."""
+    from scipy.sparse import csr_matrix
+    row, col, data = [], [], []
+    for row_idx, line in enumerate(x.split(" ") for x in payload.split("\n")):
+        for item in line:
+            if ":" in item:
+                parts = item.split(":")
+                col.append(int(parts[0]))
+                row.append(row_idx)
+                data.append(parts[1])
+    row, col = np.array(row), np.array(col).astype(int)
+    if len(col) > 0 and col.min() >= 1:
+        col = col - 1
+    data = np.array(data).astype(float)
+    if not (len(row) == len(col) and len(col) == len(data)):
+        raise RuntimeError("Dimension checking failed when transforming sparse matrix.")
+    return csr_matrix((data, (row, col)))
+
+
+def sparse_libsvm_to_dmatrix(payload):
+    """`xgb.DMatrix(_get_sparse_matrix_from_libsvm(decoded_payload))` of serve_utils.parse_content_data (serve_utils.py:132-137)
+    in one step: the body (str, already stripped) is parsed on the device, entries a line does not list are missing."""
+    be = get_backend()
+    if hasattr(be, "dmatrix_from_libsvm_text") and len(payload) > 0:
+        handle, status = be.dmatrix_from_libsvm_text(payload, 0, float("nan"))
+        if status == 0:
+            return DMatrix._from_handle(handle)
+    return DMatrix(_host_sparse_matrix_from_libsvm(payload if isinstance(payload, str) else payload.decode("utf-8")))
+
+
+def _host_libsvm_rows(string_like):
+    rows = []
+    for line in string_like.strip().split("\n"):                 # encoder.py:64-72
+        row = {}
+        for token in line.strip().split():
+            if ":" in token:
+                idx, val = token.split(":", 1)
+                row[int(idx)] = float(val)
+        rows.append(row)
+    return rows
+
+
+def libsvm_to_dmatrix(string_like):
+    """encoder.libsvm_to_dmatrix (encoder.py:54-86): dense matrix, entries a line does not list are 0.0."""
+    if isinstance(string_like, (bytes, bytearray)):
+        string_like = string_like.decode("utf-8")
+    body = string_like.strip()
+    be = get_backend()
+    if hasattr(be, "dmatrix_from_libsvm_text") and len(body) > 0:
+        handle, status = be.dmatrix_from_libsvm_text(body, 1, 0.0)
+        if status == 0:
+            return DMatrix._from_handle(handle)
+    rows = _host_libsvm_rows(string_like)
+    if not rows or not any(rows):
+        return DMatrix(np.empty((0, 0)))
+    min_idx = min(idx for row in rows for idx in row)
+    offset = 1 if min_idx >= 1 else 0
+    max_col = max(idx for row in rows for idx in row) - offset + 1
+    data = np.zeros((len(rows), max_col))
+    for i, row in enumerate(rows):
+        for idx, val in row.items():
+            data[i, idx - offset] = val
+    return DMatrix(data)
+
+
 def _predict_one(booster, dtest):
     best_iteration = getattr(booster, "best_ntree_limit", 0)          # serve_utils.py:228-250
     try:
@@ -75,4 +141,4 @@ def predict(model, model_format, dtest, input_content_type, objective=None):
     return _predict_one(model, dtest)
 
 
-__all__ = ["csv_to_dmatrix", "predict", "Booster", "DMatrix", "XGBoostError"]
+__all__ = ["csv_to_dmatrix", "sparse_libsvm_to_dmatrix", "libsvm_to_dmatrix", "predict", "Booster", "DMatrix", "XGBoostError"]

@@ -105,3 +105,112 @@ def test_training_csv_channel_is_parsed_on_the_device_like_the_host_loader(xgb, 
     np.testing.assert_array_equal(dm.get_weight(), ref[:, 1])
     np.testing.assert_allclose(np.nan_to_num(got, nan=-777.0), np.nan_to_num(X, nan=-777.0), rtol=2e-7, atol=0)
     np.testing.assert_allclose(dm.get_label(), y, rtol=2e-7)
+
+
+# ------------------------------------------------------------------------------------------------ libsvm request bodies
+def _ref_sparse_route(payload):
+    """serve_utils._get_sparse_matrix_from_libsvm + xgb.DMatrix(csr) (algorithm_mode/serve_utils.py:94-118,132-137), restated"""
+    from scipy.sparse import csr_matrix
+    row, col, data = [], [], []
+    for r, line in enumerate(x.split(" ") for x in payload.split("\n")):
+        for item in line:
+            if ":" in item:
+                col.append(int(item.split(":")[0])); row.append(r); data.append(item.split(":")[1])
+    row, col = np.array(row), np.array(col).astype(int)
+    if len(col) > 0 and col.min() >= 1:
+        col = col - 1
+    m = csr_matrix((np.array(data).astype(float), (row, col)))
+    out = np.full(m.shape, np.nan, np.float32)
+    coo = m.tocoo()
+    out[coo.row, coo.col] = coo.data.astype(np.float32)
+    return out
+
+
+def _ref_dense_route(payload):
+    """encoder.libsvm_to_dmatrix (encoder.py:54-86), restated"""
+    rows = []
+    for line in payload.strip().split("\n"):
+        row = {}
+        for token in line.strip().split():
+            if ":" in token:
+                idx, val = token.split(":", 1)
+                row[int(idx)] = float(val)
+        rows.append(row)
+    mn = min(i for r in rows for i in r)
+    off = 1 if mn >= 1 else 0
+    data = np.zeros((len(rows), max(i for r in rows for i in r) - off + 1))
+    for i, r in enumerate(rows):
+        for k, v in r.items():
+            data[i, k - off] = v
+    return data.astype(np.float32)
+
+
+def _libsvm_body(rng, n, F, one_based=True, fmt="%.6g"):
+    lines = []
+    for r in range(n):
+        k = int(rng.integers(0, F + 1)) if r not in (0, n - 1) else max(1, int(rng.integers(1, F + 1)))
+        idx = np.sort(rng.choice(F, size=k, replace=False))
+        if r == 0:
+            idx = np.union1d(idx, [0])                                    # the smallest index decides the 1-based shift: pin it
+        idx = idx + (1 if one_based else 0)
+        vals = rng.standard_normal(len(idx)) * np.exp(rng.uniform(-10, 10, len(idx)))
+        toks = ["%d" % int(rng.integers(0, 3))] + ["%d:%s" % (i, (fmt % v) if j % 7 else "%d" % int(v)) for j, (i, v) in enumerate(zip(idx, vals))]
+        lines.append(" ".join(toks))
+    return "\n".join(lines)
+
+
+@pytest.mark.parametrize("one_based", [True, False])
+def test_libsvm_bodies_on_the_device_match_both_container_routes(xgb, one_based):
+    from sagemaker_xgboost_container_b200 import serving
+    rng = np.random.default_rng(31 + one_based)
+    body = _libsvm_body(rng, 5000, 40, one_based)
+    be = xgb.get_backend()
+    h, st = be.dmatrix_from_libsvm_text(body, 0, float("nan"))
+    assert st == 0                                                        # the fast path took it (no silent host fallback in this test)
+    d = xgb.DMatrix._from_handle(h)
+    want = _ref_sparse_route(body)
+    got = be.dmatrix_get_raw(d.handle).reshape(d.num_row(), d.num_col())
+    assert got.shape == want.shape and got.view(np.uint32).tobytes() == want.view(np.uint32).tobytes()
+    h, st = be.dmatrix_from_libsvm_text(body, 1, 0.0)
+    assert st == 0
+    d = xgb.DMatrix._from_handle(h)
+    want = _ref_dense_route(body)
+    got = be.dmatrix_get_raw(d.handle).reshape(d.num_row(), d.num_col())
+    assert got.shape == want.shape and got.view(np.uint32).tobytes() == want.view(np.uint32).tobytes()
+    d2 = serving.sparse_libsvm_to_dmatrix(body)
+    assert (d2.num_row(), d2.num_col()) == _ref_sparse_route(body).shape
+
+
+@pytest.mark.parametrize("body,why", [
+    ("1 1:0.5 1:0.25 2:3", "index repeated inside a line (COO sums, dict keeps the last)"),
+    ("1 1:0.5 2:3\n0\n", "trailing line without entries"),
+    ("1 +1:0.5 2:3", "index that is not plain digits"),
+    ("1 1:0.12345678901234567890123 2:3", "literal outside the exact fast path"),
+    ("1 1:nan 2:3", "NaN value"),
+    ("1 1:2\t3:4 5:6", "tab inside a token"),
+])
+def test_libsvm_special_cases_take_the_host_route_and_agree(xgb, body, why):
+    from sagemaker_xgboost_container_b200 import serving
+    be = xgb.get_backend()
+    h, st = be.dmatrix_from_libsvm_text(body.strip(), 0, float("nan"))
+    assert st == 2 and h is None, why
+    try:
+        want = _ref_sparse_route(body.strip())
+    except Exception as e:                                               # the reference raises: so must the mirror
+        with pytest.raises(type(e)):
+            serving.sparse_libsvm_to_dmatrix(body.strip())
+        return
+    d = serving.sparse_libsvm_to_dmatrix(body.strip())
+    got = be.dmatrix_get_raw(d.handle).reshape(d.num_row(), d.num_col())
+    np.testing.assert_array_equal(got, want)
+
+
+def test_libsvm_dense_route_edge_cases(xgb):
+    from sagemaker_xgboost_container_b200 import serving
+    be = xgb.get_backend()
+    for body in ["1 1:0.5 1:0.25 2:3\n0\n1 4:1", "0 3:1e-3\t7:2 \n\n1 1:5", "1 0:1 5:2\n0 2:3"]:
+        d = serving.libsvm_to_dmatrix(body)
+        want = _ref_dense_route(body)
+        got = be.dmatrix_get_raw(d.handle).reshape(d.num_row(), d.num_col())
+        assert got.shape == want.shape and got.view(np.uint32).tobytes() == want.view(np.uint32).tobytes(), body
+    assert serving.libsvm_to_dmatrix("1\n0\n").num_row() == 0            # no entry at all: the reference's empty DMatrix
