@@ -67,21 +67,24 @@ class JsonReader {
   explicit JsonReader(const char* p, size_t n) : p_(p), e_(p + n) {}
   JPtr parse() { ws(); JPtr v = value(); return v; }
  private:
-  const char* p_; const char* e_;
+  const char* p_; const char* e_; int depth_ = 0;
+  static constexpr int kMaxDepth = 64;              // model / config documents nest 7 deep; a hostile file must not exhaust the stack
+  struct Nest { int& d; explicit Nest(int& x) : d(x) { if (++d > kMaxDepth) throw std::runtime_error("json parse error: nesting too deep"); } ~Nest() { --d; } };
   void ws() { while (p_ < e_ && (*p_ == ' ' || *p_ == '\n' || *p_ == '\t' || *p_ == '\r')) ++p_; }
   [[noreturn]] void fail(const char* m) { throw std::runtime_error(std::string("json parse error: ") + m); }
+  bool lit(const char* w, size_t n) { if ((size_t)(e_ - p_) < n || memcmp(p_, w, n) != 0) return false; p_ += n; return true; }     // length first: the buffer need not be terminated
   JPtr value() {
     ws(); if (p_ >= e_) fail("eof");
     char c = *p_;
     if (c == '{') return object();
     if (c == '[') return array();
     if (c == '"') return JValue::Str(string());
-    if (!strncmp(p_, "true", 4) && e_ - p_ >= 4) { p_ += 4; return JValue::Bool(true); }
-    if (!strncmp(p_, "false", 5) && e_ - p_ >= 5) { p_ += 5; return JValue::Bool(false); }
-    if (!strncmp(p_, "null", 4) && e_ - p_ >= 4) { p_ += 4; return JValue::Null(); }
-    if (!strncmp(p_, "NaN", 3) && e_ - p_ >= 3) { p_ += 3; return JValue::Float(NAN); }
-    if (!strncmp(p_, "Infinity", 8) && e_ - p_ >= 8) { p_ += 8; return JValue::Float(INFINITY); }
-    if (!strncmp(p_, "-Infinity", 9) && e_ - p_ >= 9) { p_ += 9; return JValue::Float(-INFINITY); }
+    if (lit("true", 4)) return JValue::Bool(true);
+    if (lit("false", 5)) return JValue::Bool(false);
+    if (lit("null", 4)) return JValue::Null();
+    if (lit("NaN", 3)) return JValue::Float(NAN);
+    if (lit("Infinity", 8)) return JValue::Float(INFINITY);
+    if (lit("-Infinity", 9)) return JValue::Float(-INFINITY);
     return number();
   }
   JPtr number() {
@@ -99,7 +102,7 @@ class JsonReader {
     while (p_ < e_ && *p_ != '"') {
       if (*p_ == '\\') { ++p_; if (p_ >= e_) fail("eof in string");
         switch (*p_) { case 'n': out += '\n'; break; case 't': out += '\t'; break; case 'r': out += '\r'; break; case 'b': out += '\b'; break;
-          case 'f': out += '\f'; break; case 'u': { unsigned cp = 0; for (int k = 0; k < 4 && p_ + 1 < e_; ++k) { ++p_; cp = cp * 16 + (unsigned)(std::isdigit(*p_) ? *p_ - '0' : (std::tolower(*p_) - 'a' + 10)); }
+          case 'f': out += '\f'; break; case 'u': { unsigned cp = 0; for (int k = 0; k < 4 && p_ + 1 < e_; ++k) { ++p_; const unsigned char h = (unsigned char)*p_; if (!std::isxdigit(h)) fail("bad \\u escape"); cp = cp * 16 + (unsigned)(std::isdigit(h) ? h - '0' : (std::tolower(h) - 'a' + 10)); }
             if (cp < 0x80) out += (char)cp; else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
             else { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); } break; }
           default: out += *p_; }
@@ -110,12 +113,14 @@ class JsonReader {
     ++p_; return out;
   }
   JPtr array() {
+    Nest nest(depth_);
     ++p_; JPtr a = JValue::Array(); ws();
     if (p_ < e_ && *p_ == ']') { ++p_; return a; }
     while (true) { a->arr.push_back(value()); ws(); if (p_ >= e_) fail("eof in array"); if (*p_ == ',') { ++p_; continue; } if (*p_ == ']') { ++p_; break; } fail("expected , or ]"); }
     return a;
   }
   JPtr object() {
+    Nest nest(depth_);
     ++p_; JPtr o = JValue::Object(); ws();
     if (p_ < e_ && *p_ == '}') { ++p_; return o; }
     while (true) { ws(); if (p_ >= e_ || *p_ != '"') fail("expected key"); std::string k = string(); ws(); if (p_ >= e_ || *p_ != ':') fail("expected :"); ++p_;
@@ -182,8 +187,12 @@ class UbjReader {
   UbjReader(const unsigned char* p, size_t n) : p_(p), e_(p + n) {}
   JPtr parse() { return value(take()); }
  private:
-  const unsigned char* p_; const unsigned char* e_;
+  const unsigned char* p_; const unsigned char* e_; int depth_ = 0;
+  static constexpr int kMaxDepth = 64;
+  struct Nest { int& d; explicit Nest(int& x) : d(x) { if (++d > kMaxDepth) throw std::runtime_error("ubjson parse error: nesting too deep"); } ~Nest() { --d; } };
   [[noreturn]] void fail(const char* m) { throw std::runtime_error(std::string("ubjson parse error: ") + m); }
+  // a count field is checked against the bytes that are left BEFORE anything is allocated for it
+  size_t counted(int64_t cnt, size_t itemsize) { if (cnt < 0 || (uint64_t)cnt > (uint64_t)(e_ - p_) / itemsize) fail("count runs past the end of the buffer"); return (size_t)cnt; }
   unsigned char take() { if (p_ >= e_) fail("eof"); return *p_++; }
   unsigned char peek() { if (p_ >= e_) fail("eof"); return *p_; }
   const unsigned char* bytes(size_t n) { if ((size_t)(e_ - p_) < n) fail("eof"); const unsigned char* r = p_; p_ += n; return r; }
@@ -191,7 +200,7 @@ class UbjReader {
     switch (m) { case 'i': return (int8_t)*bytes(1); case 'U': return *bytes(1); case 'I': return be_get<int16_t>(bytes(2));
       case 'l': return be_get<int32_t>(bytes(4)); case 'L': return be_get<int64_t>(bytes(8)); default: fail("bad integer marker"); }
   }
-  std::string str() { int64_t n = integer(take()); const unsigned char* b = bytes((size_t)n); return std::string((const char*)b, (size_t)n); }
+  std::string str() { const size_t n = counted(integer(take()), 1); const unsigned char* b = bytes(n); return std::string((const char*)b, n); }
   JPtr value(unsigned char m) {
     switch (m) {
       case 'Z': return JValue::Null(); case 'T': return JValue::Bool(true); case 'F': return JValue::Bool(false);
@@ -203,12 +212,15 @@ class UbjReader {
     }
   }
   JPtr array() {
+    Nest nest(depth_);
     int typ = 0; int64_t cnt = -1;
     if (peek() == '$') { take(); typ = take(); }
-    if (peek() == '#') { take(); cnt = integer(take()); }
+    if (peek() == '#') { take(); cnt = integer(take()); if (cnt < 0) fail("negative count"); }
     if (typ) {
       if (cnt < 0) fail("typed array without count");
-      size_t n = (size_t)cnt;
+      const size_t item = typ == 'd' || typ == 'l' ? 4 : typ == 'D' || typ == 'L' ? 8 : typ == 'I' ? 2 : typ == 'U' || typ == 'i' || typ == 'C' ? 1 : 0;
+      if (item == 0 && (typ == 'Z' || typ == 'T' || typ == 'F' || typ == 'N') && cnt > (1 << 20)) fail("implausible count of payload-free values");
+      size_t n = item ? counted(cnt, item) : (size_t)cnt;
       if (typ == 'd') { std::vector<float> v(n); const unsigned char* b = bytes(4 * n); for (size_t k = 0; k < n; ++k) v[k] = be_get<float>(b + 4 * k); return JValue::F32(std::move(v)); }
       if (typ == 'D') { std::vector<float> v(n); const unsigned char* b = bytes(8 * n); for (size_t k = 0; k < n; ++k) v[k] = (float)be_get<double>(b + 8 * k); return JValue::F32(std::move(v)); }
       if (typ == 'l') { std::vector<int32_t> v(n); const unsigned char* b = bytes(4 * n); for (size_t k = 0; k < n; ++k) v[k] = be_get<int32_t>(b + 4 * k); return JValue::I32(std::move(v)); }
@@ -224,8 +236,9 @@ class UbjReader {
     take(); return a;
   }
   JPtr object() {
+    Nest nest(depth_);
     int64_t cnt = -1;
-    if (peek() == '#') { take(); cnt = integer(take()); }
+    if (peek() == '#') { take(); cnt = integer(take()); if (cnt < 0) fail("negative count"); }
     JPtr o = JValue::Object();
     if (cnt >= 0) { for (int64_t k = 0; k < cnt; ++k) { std::string key = str(); o->obj.emplace_back(key, value(take())); } return o; }
     while (peek() != '}') { std::string key = str(); o->obj.emplace_back(key, value(take())); }

@@ -128,6 +128,9 @@ void Booster::model_from_json(const JValue& doc) {
   const JValue& model = gb.at("model");
   const JValue& trees = model.at("trees");
   const JValue& tinfo = model.at("tree_info");
+  B200_CHECK(trees.type == JValue::kArray && tinfo.length() == trees.arr.size(), "model: tree_info does not have one entry per tree");
+  { int K = std::max(1, nc); if (nc <= 1) if (auto sp = obj.get("softmax_multiclass_param")) K = std::max(1, (int)sp->at("num_class").as_int());
+    for (size_t t = 0; t < trees.arr.size(); ++t) { const double g = tinfo.num_at(t); B200_CHECK(g >= 0 && g < K, "model: tree_info entry out of range"); } }
   for (size_t t = 0; t < trees.arr.size(); ++t) {
     const JValue& tj = *trees.arr[t];
     HostTree h;
@@ -141,6 +144,15 @@ void Booster::model_from_json(const JValue& doc) {
     if (auto st = tj.get("split_type")) for (size_t i = 0; i < st->length(); ++i) B200_CHECK(st->num_at(i) == 0, "categorical splits are not supported on the B200 path");
     const size_t nn = h.left.size();
     B200_CHECK(h.right.size() == nn && h.split_index.size() == nn && h.split_cond.size() == nn && h.default_left.size() == nn, "model: inconsistent tree array lengths");
+    B200_CHECK(nn >= 1 && h.parent.size() == nn && h.base_weight.size() == nn && h.loss_chg.size() == nn && h.sum_hess.size() == nn, "model: inconsistent tree array lengths");
+    // the device kernels walk these arrays unchecked: children must exist and lie AFTER their parent (xgboost allocates node ids
+    // in expansion order), which also rules out cycles; split features must exist
+    for (size_t i = 0; i < nn; ++i) {
+      const int l = h.left[i], r = h.right[i];
+      if (l == -1 && r == -1) continue;
+      B200_CHECK(l > (int)i && r > (int)i && (size_t)l < nn && (size_t)r < nn && l != r, "model: tree " + std::to_string(t) + " node " + std::to_string(i) + " has child indices out of order or out of range");
+      B200_CHECK(h.split_index[i] >= 0 && h.split_index[i] < std::max(num_feature_, 1), "model: tree " + std::to_string(t) + " node " + std::to_string(i) + " splits on feature " + std::to_string(h.split_index[i]) + " but the model has " + std::to_string(num_feature_) + " features");
+    }
     trees_.push_back(std::move(h)); tree_info_.push_back((int)tinfo.num_at(t)); pending_.emplace_back(); on_device_.push_back(0);
   }
   ++model_version_;

@@ -3,7 +3,7 @@ a single row, weights -- the shapes the reference's own unit tests use (100 x 5 
 import numpy as np
 import pytest
 
-from util import assert_same_structure, max_leaf_diff
+from util import assert_same_structure, max_leaf_diff, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -103,3 +103,34 @@ def test_c_abi_array_interface_and_uri_constructors(xgb, tmp_path):
     got = be.dmatrix_get_raw(h3).reshape(2, 4)
     assert got[0, 1] == 0.5 and got[0, 3] == 2.0 and got[1, 2] == 1.5 and np.isnan(got[0, 0])
     be.dmatrix_free(h3)
+
+
+def test_damaged_model_documents_are_refused_before_they_reach_a_kernel(xgb, tmp_path):
+    """The predictor walks the tree arrays unchecked, so the loader must refuse what would send it out of bounds or in circles:
+    a child that points back at its parent, a child index past the array, a split on a feature the model does not have, a
+    tree_info shorter than the tree list, a count field larger than the file (UBJSON)."""
+    import json
+    X, y = synth(500, 4, 3)
+    bst = xgb.train(dict(objective="reg:squarederror", max_depth=3), xgb.DMatrix(X, label=y), num_boost_round=2, verbose_eval=False)
+    doc = json.loads(bytes(bst.save_raw("json")).decode())
+    tree = doc["learner"]["gradient_booster"]["model"]["trees"][0]
+    assert tree["left_children"][0] == 1                                 # a real split at the root
+
+    def damaged(edit):
+        d = json.loads(json.dumps(doc))
+        edit(d["learner"]["gradient_booster"]["model"])
+        return json.dumps(d).encode()
+
+    def cycle(m): m["trees"][0]["left_children"][1] = 0; m["trees"][0]["right_children"][1] = 2
+    def past_end(m): m["trees"][0]["right_children"][0] = 10 ** 6
+    def bad_feature(m): m["trees"][0]["split_indices"][0] = 4
+    def short_info(m): m["tree_info"] = m["tree_info"][:1]
+    for edit in (cycle, past_end, bad_feature, short_info):
+        with pytest.raises(xgb.XGBoostError, match="model"):
+            xgb.Booster(model_file=bytearray(damaged(edit)))
+    raw = bytes(bst.save_raw("ubj"))
+    k = raw.index(b"[$d#")                                               # first typed float array: give it an absurd length
+    with pytest.raises(xgb.XGBoostError, match="count runs past the end"):
+        xgb.Booster(model_file=bytearray(raw[:k + 4] + b"L" + (2 ** 40).to_bytes(8, "big") + raw[k + 6:]))
+    ok = xgb.Booster(model_file=bytearray(json.dumps(doc).encode()))     # the undamaged document still loads and predicts the same
+    np.testing.assert_array_equal(ok.predict(xgb.DMatrix(X)), bst.predict(xgb.DMatrix(X)))
