@@ -150,3 +150,46 @@ def test_two_gpu_launcher_equals_single_gpu(xgb, tmp_path):
     m1, m2 = be.booster_export_model(single.handle), be.booster_export_model(multi.handle)
     for k in ("left", "right", "split_index", "split_cond"):
         np.testing.assert_array_equal(m1[k], m2[k])
+
+
+def test_two_hosts_with_one_gpu_each_rendezvous_through_the_master_tracker(tmp_path):
+    """Several hosts (train.py:236-269 analogue for the GPU route): every host calls run_training_with_dask with the same host
+    list; the first host runs the tracker on the fixed port, ranks follow (host, gpu), rank 0 alone writes the model.  Two
+    'hosts' on this machine (two names of the loopback interface), CPU test engine."""
+    import threading
+    from sagemaker_xgboost_container_b200 import multi_gpu
+    tr, va = _channels(tmp_path)
+    hosts = ["localhost", "127.0.0.1"]
+    hp = {"objective": "reg:squarederror", "tree_method": "hist", "num_round": 4, "max_depth": 3, "eta": 0.3}
+    dirs = [tmp_path / "model-host0", tmp_path / "model-host1"]
+    errors = []
+
+    def host(i):
+        try:
+            multi_gpu.run_training_with_dask(dict(hp), str(tr), str(va), str(dirs[i]), "csv", hosts, hosts[i], None, 1,
+                                             worker_init=oracle_worker_init.use_oracle_engine)
+        except BaseException as e:      # noqa: BLE001
+            errors.append((i, e))
+    threads = [threading.Thread(target=host, args=(i,)) for i in (1, 0)]          # the non-master host may well come up first
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    assert os.path.exists(dirs[0] / "xgboost-model") and not os.path.exists(dirs[1])      # the master (rank 0 lives on host 0) saves, nobody else
+    # same model as one process on all rows
+    import sagemaker_xgboost_container_b200 as xgb
+    from sagemaker_xgboost_container_b200 import backend
+    from oracle.engine import OracleBackend
+    from oracle import ubjson
+    old = backend._BACKEND
+    backend._BACKEND = OracleBackend(error_cls=xgb.XGBoostError)
+    try:
+        arr = np.concatenate([np.loadtxt(f, delimiter=",", dtype=np.float32) for f in sorted(str(p) for p in tr.iterdir())])
+        single = xgb.train({k: v for k, v in hp.items() if k != "num_round"}, xgb.DMatrix(arr[:, 1:], label=arr[:, 0]), num_boost_round=4, verbose_eval=False)
+        a = ubjson.model_from_xgb_json(ubjson.loads(bytes(single.save_raw("ubj"))))
+    finally:
+        backend._BACKEND = old
+    b = ubjson.model_from_xgb_json(ubjson.load(str(dirs[0] / "xgboost-model")))
+    for k in ("left", "split_index", "split_cond"):
+        np.testing.assert_array_equal(a[k], b[k])
