@@ -175,3 +175,25 @@ def test_legacy_files_predict_like_the_oracle_on_the_device(xgb):
     raw = b2.save_raw("ubj")                                            # round trip through the current format keeps the predictions
     b3 = xgb.Booster(model_file=raw)
     np.testing.assert_array_equal(b3.predict(d), b2.predict(d))
+
+
+def test_pickles_in_upstreams_current_state_layout_open_too(monkeypatch):
+    """xgboost >= 1.x pickles a Booster as its __dict__ with the serialized learner under "handle" (today UBJSON {Model, Config});
+    a pickle written by the real package therefore reaches Booster.__setstate__ with that key and no "_raw"."""
+    import sagemaker_xgboost_container_b200 as xgb
+    from sagemaker_xgboost_container_b200 import backend
+    from oracle.engine import OracleBackend
+    monkeypatch.setattr(backend, "_BACKEND", OracleBackend(error_cls=xgb.XGBoostError))
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((200, 5)).astype(np.float32)
+    y = (X[:, 0] > 0).astype(np.float32)
+    d = xgb.DMatrix(X, label=y, feature_names=["a", "b", "c", "d", "e"])
+    bst = xgb.train({"objective": "binary:logistic", "max_depth": 3}, d, num_boost_round=4, verbose_eval=False)
+    own = bst.__getstate__()
+    upstream_style = {"handle": bytearray(own["_raw"]), "feature_names": ["a", "b", "c", "d", "e"], "feature_types": None, "best_iteration": 3}
+    b2 = xgb.Booster.__new__(xgb.Booster)
+    b2.__setstate__(upstream_style)
+    np.testing.assert_array_equal(b2.predict(d), bst.predict(d))
+    assert b2.feature_names == ["a", "b", "c", "d", "e"] and b2.best_iteration == 3
+    b3 = pickle.loads(pickle.dumps(b2))                                  # and our own layout still round-trips
+    np.testing.assert_array_equal(b3.predict(d), bst.predict(d))
