@@ -193,3 +193,33 @@ def test_two_hosts_with_one_gpu_each_rendezvous_through_the_master_tracker(tmp_p
     b = ubjson.model_from_xgb_json(ubjson.load(str(dirs[0] / "xgboost-model")))
     for k in ("left", "split_index", "split_cond"):
         np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_memory_mapped_shards_equal_the_whole_file_split(tmp_path, monkeypatch):
+    """_csv_shard_text never loads the channel: it maps the files and scans them in chunks.  Against the obvious whole-file
+    implementation on random channels: several files, CRLF and LF endings, leading / trailing blank lines, empty files, scan
+    chunks far smaller than a line run."""
+    from sagemaker_xgboost_container_b200 import multi_gpu as mg
+
+    def whole_file(files, rank, world):
+        chunks = [b for b in (open(f, "rb").read().replace(b"\r\n", b"\n").strip(b"\n") for f in files) if b]
+        buf = np.frombuffer(b"\n".join(chunks), np.uint8)
+        ends = np.flatnonzero(buf == 10)
+        n = len(ends) + (1 if len(buf) else 0)
+        lo, hi = mg.shard_bounds(n, rank, world)
+        if hi <= lo:
+            return b"", n
+        return buf[(0 if lo == 0 else int(ends[lo - 1]) + 1):(len(buf) if hi == n else int(ends[hi - 1]))].tobytes(), n
+    monkeypatch.setattr(mg, "_SCAN_CHUNK", 37)
+    rng = np.random.default_rng(0)
+    for trial in range(120):
+        files = []
+        for k in range(int(rng.integers(1, 5))):
+            eol = b"\r\n" if rng.random() < 0.3 else b"\n"
+            body = eol.join(b",".join(b"%d" % int(x) for x in rng.integers(0, 1000, int(rng.integers(1, 6)))) for _ in range(int(rng.integers(0, 12))))
+            p = tmp_path / ("t%d_%d.csv" % (trial, k))
+            p.write_bytes(b"\n" * int(rng.integers(0, 3)) + body + eol * int(rng.integers(0, 3)))
+            files.append(str(p))
+        for world in (1, 2, 3, 7):
+            for r in range(world):
+                assert mg._csv_shard_text(files, r, world) == whole_file(files, r, world)
