@@ -25,7 +25,12 @@ CASES = [
     ("algorithm_mode/test_train_utils.py", None, 3),
     ("algorithm_mode/test_serve_utils.py", "not protobuf", 50),   # get_loaded_booster, predict, selectable inference
     ("test_prediction_utils.py", None, 9),
+    ("algorithm_mode/test_algorithm_mode.py", None, 15),      # the train entry point's error mapping (XGBoostError messages -> UserError / AlgorithmError)
+    ("distributed_gpu/test_distributed_gpu_training.py", None, 9),    # validate_gpu_train_configuration, with this package's xgboost.dask stub bound
+    ("distributed_gpu/test_dask_data_utils.py", None, 5),
 ]
+# Not runnable here for lack of third-party packages, all platform glue outside the hot path: algorithm_mode/test_serve.py (flask),
+# test_serving.py / test_handler_service.py / test_training.py / test_serving_mms.py (sagemaker_containers.beta).
 
 
 @pytest.mark.parametrize("path,deselect,min_passed", CASES)
