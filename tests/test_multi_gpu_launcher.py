@@ -223,3 +223,22 @@ def test_memory_mapped_shards_equal_the_whole_file_split(tmp_path, monkeypatch):
         for world in (1, 2, 3, 7):
             for r in range(world):
                 assert mg._csv_shard_text(files, r, world) == whole_file(files, r, world)
+
+
+@pytest.mark.skipif(not reference_stubs.reference_available(), reason="/root/reference is not mounted here")
+def test_the_references_own_validation_tests_pass_on_the_native_module(monkeypatch):
+    """test/unit/distributed_gpu/test_distributed_gpu_training.py, unmodified, with the module it imports
+    (distributed_gpu_training: validate_gpu_train_configuration + its four message constants) replaced by multi_gpu"""
+    import importlib.util
+    import unittest
+    import sagemaker_xgboost_container_b200 as xgb
+    from sagemaker_xgboost_container_b200 import multi_gpu
+    reference_stubs.install(xgb)
+    import sagemaker_xgboost_container.distributed_gpu  # noqa: F401  (the parent package must be importable)
+    monkeypatch.setitem(sys.modules, "sagemaker_xgboost_container.distributed_gpu.distributed_gpu_training", multi_gpu)
+    spec = importlib.util.spec_from_file_location("ref_distributed_gpu_training_tests", "/root/reference/test/unit/distributed_gpu/test_distributed_gpu_training.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.validate_gpu_train_configuration is multi_gpu.validate_gpu_train_configuration
+    result = unittest.TextTestRunner(verbosity=0).run(unittest.defaultTestLoader.loadTestsFromModule(mod))
+    assert result.wasSuccessful() and result.testsRun >= 9, (result.failures, result.errors)
