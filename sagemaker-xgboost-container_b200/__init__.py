@@ -7,7 +7,7 @@ run unchanged on top of the CUDA engine.
 """
 import sys
 
-from . import callback, collective, core, sklearn, tracker, training  # noqa: F401
+from . import callback, collective, core, dask, sklearn, tracker, training  # noqa: F401
 from .backend import XGBoostError, get_backend  # noqa: F401
 from .core import Booster, DMatrix  # noqa: F401
 from .training import cv, train  # noqa: F401
@@ -24,6 +24,6 @@ def install_as_xgboost():
     """Alias this package as `xgboost` (+ the submodules the container imports) in sys.modules."""
     me = sys.modules[__name__]
     sys.modules["xgboost"] = me
-    for sub in ("core", "callback", "collective", "tracker", "training", "sklearn"):
+    for sub in ("core", "callback", "collective", "tracker", "training", "sklearn", "dask"):
         sys.modules["xgboost." + sub] = getattr(me, sub)
     return me

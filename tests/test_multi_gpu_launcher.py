@@ -242,3 +242,45 @@ def test_the_references_own_validation_tests_pass_on_the_native_module(monkeypat
     assert mod.validate_gpu_train_configuration is multi_gpu.validate_gpu_train_configuration
     result = unittest.TextTestRunner(verbosity=0).run(unittest.defaultTestLoader.loadTestsFromModule(mod))
     assert result.wasSuccessful() and result.testsRun >= 9, (result.failures, result.errors)
+
+
+@pytest.mark.skipif(not reference_stubs.reference_available(), reason="/root/reference is not mounted here")
+def test_unbound_reference_dask_route_still_trains_through_xgboost_dask(tmp_path, monkeypatch, capfd):
+    """Without the multi_gpu binding the container's own run_training_with_dask (distributed_gpu_training.py:93-222) reaches
+    `xgboost.dask.DaskDMatrix` / `xgboost.dask.train` of this package: they must exist (train.py:46 imports the module at
+    start-up) and train.  The Dask cluster itself is stubbed (no dask in this image): a Client that is a context manager, and
+    dask.array.from_array returning the array."""
+    import types
+    import sagemaker_xgboost_container_b200 as xgb
+    from sagemaker_xgboost_container_b200 import backend
+    from oracle.engine import OracleBackend
+    monkeypatch.setattr(backend, "_BACKEND", OracleBackend(error_cls=xgb.XGBoostError))
+    reference_stubs.install(xgb)
+    import xgboost.dask as dxgb
+    assert dxgb is xgb.dask and sys.modules["xgboost"].dask is xgb.dask
+    from sagemaker_xgboost_container.distributed_gpu import distributed_gpu_training as dgt, dask_data_utils as ddu
+
+    class Client:
+        def __init__(self, address): self.address = address
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+        def wait_for_workers(self, n, timeout): pass
+        def scheduler_info(self): return {"workers": {"w0": {}, "w1": {}}}
+    monkeypatch.setattr(dgt, "Client", Client)
+    monkeypatch.setattr(dgt, "dxgb", xgb.dask)
+    monkeypatch.setattr(ddu, "dxgb", xgb.dask)
+    monkeypatch.setattr(ddu, "da", types.SimpleNamespace(from_array=lambda a, chunks=None: a))
+    monkeypatch.setattr(dgt, "start_daemons_in_current_instance", lambda *a, **k: None)
+    monkeypatch.setattr(dgt, "get_host_ip", lambda h: "127.0.0.1")
+    tr, va = _channels(tmp_path)
+    hp = {"objective": "reg:squarederror", "tree_method": "hist", "num_round": 5, "max_depth": 3, "eval_metric": ["rmse"]}
+    (tmp_path / "m").mkdir()                                             # /opt/ml/model exists in the container
+    with pytest.warns(UserWarning, match="multi_gpu.run_training_with_dask"):
+        dgt.run_training_with_dask(hyperparameters=dict(hp), train_path=str(tr), validation_path=str(va), model_dir=str(tmp_path / "m"),
+                                   content_type="csv", sm_hosts=["algo-1"], current_host="algo-1", checkpoint_dir=None, num_gpus=2)
+    out = capfd.readouterr().out
+    # every round twice, as with the real library: get_callbacks adds an EvaluationMonitor and the reference leaves dask.train's
+    # verbose_eval at its default True (distributed_gpu_training.py:184-192), which adds another
+    assert len([l for l in out.splitlines() if l.startswith("[") and "validation-rmse:" in l]) == 10
+    b = xgb.Booster(model_file=str(tmp_path / "m" / "xgboost-model"))
+    assert b.num_boosted_rounds() == 5 and b.num_features() == 8
