@@ -233,3 +233,28 @@ def test_tracker_frames_are_json_and_bad_handshakes_are_dropped():
     tr.wait_for(timeout=20)
     tr.free()
     probe.close(); junk.close()
+
+
+def test_libsvm_fast_and_plain_loaders_agree(tmp_path):
+    """data._load_libsvm takes scikit-learn's C parser when it can and a plain Python loop otherwise (weights in the label
+    token, qid); on files both accept they must give the same CSR matrix and labels."""
+    from sagemaker_xgboost_container_b200 import data
+    rng = np.random.default_rng(3)
+    files = []
+    for k in range(3):
+        lines = []
+        for r in range(int(rng.integers(1, 40))):
+            idx = np.sort(rng.choice(30, size=int(rng.integers(0, 8)), replace=False))
+            toks = ["%g" % rng.standard_normal()] + ["%d:%.7g" % (i, v) for i, v in zip(idx, rng.standard_normal(len(idx)) * 10 ** rng.uniform(-5, 5, len(idx)))]
+            lines.append(" ".join(toks) + ("  # trailing comment" if r % 9 == 0 else ""))
+        p = tmp_path / ("part-%d.libsvm" % k)
+        p.write_text("\n".join(lines) + "\n")
+        files.append(str(p))
+    Xf, yf, wf = data._load_libsvm_fast(files)
+    import unittest.mock as um
+    with um.patch.object(data, "_load_libsvm_fast", return_value=None):
+        Xs, ys, ws = data._load_libsvm(files, {})
+    assert wf is None and ws is None
+    np.testing.assert_array_equal(yf, ys)
+    assert Xf.shape == Xs.shape and (Xf != Xs).nnz == 0
+    np.testing.assert_array_equal(Xf.toarray().view(np.uint32), Xs.toarray().astype(np.float32).view(np.uint32))
